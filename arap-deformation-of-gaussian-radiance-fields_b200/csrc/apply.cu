@@ -1,0 +1,460 @@
+// Stage (d) apply pass + the per-step sample passes (a9, a10).
+//
+//   lbs_points      DeformGraph::predict_mesh / predict_samples  (Deform.hpp:230-268)
+//   end_points      GaussianView::GetEndPoints                   (GaussianView.cpp:4643-4668)
+//   fit_gaussians   GaussianView::UpdateAsSixPointsWithdrawBad   (GaussianView.cpp:3081-3166)
+//   node_quats      GaussianView::FastUpdateSamplesSH host part  (GaussianView.cpp:3169-3186)
+//   rotate_sample_shs  RotateSHs kernel                          (cudakdtree.cu:201-222)
+//   static_flags    CheckStaticSamples / CheckMovedGaussians     (GaussianView.cpp:2024-2109)
+//
+// HBM layout.  The rasteriser-facing SoA keeps the reference layout
+// (pos N x 3, rot N x 4 wxyz, scale N x 3, opacity N, shs N x 48 — the
+// Rasterizer::forward argument layout, GaussianView.cpp:1106-1112).  Internal
+// tables are ours: skinning rows are stored in blocks of 32 rows,
+//   idx[(blk*K + j)*32 + lane]  (uint16)     w[(blk*K + j)*32 + lane]  (double)
+// so a warp reading neighbour j of 32 consecutive rows issues one 64 B and one
+// 256 B fully-coalesced request.
+#include "device_math.cuh"
+#include "kernels.h"
+
+namespace arapgs {
+
+// ------------------------------------------------------------------ node xf
+__global__ void k_node_xf(int M, const double* __restrict__ rot, const double* __restrict__ trans,
+                          const float* __restrict__ node_pos, NodeXf* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  NodeXf x;
+#pragma unroll
+  for (int t = 0; t < 9; t++) x.A[t] = rot[9 * i + t];
+#pragma unroll
+  for (int t = 0; t < 3; t++) {
+    float g = node_pos[3 * i + t];
+    x.g[t] = g;
+    x.c[t] = trans[3 * i + t] + (double)g;
+  }
+  x.pad = 0.f;
+  out[i] = x;
+}
+
+// ------------------------------------------------------------------ LBS
+// One thread per point.  Double products, float accumulator rounded after each
+// neighbour — exactly the reference's `Pos output += double_expr` sequence.
+template <int K>
+__global__ void __launch_bounds__(256)
+k_lbs_points(const float* __restrict__ in, float* __restrict__ out, long long P, int k_rt,
+             const uint16_t* __restrict__ ridx, const double* __restrict__ rw,
+             const NodeXf* __restrict__ nodes, const uint8_t* __restrict__ skip, int group) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  if (skip && skip[i / group]) return;
+  const int k = K > 0 ? K : k_rt;
+  const float c0 = in[3 * i], c1 = in[3 * i + 1], c2 = in[3 * i + 2];
+  float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+  const long long base = (i >> 5) * (long long)(k * 32) + (i & 31);
+#pragma unroll
+  for (int j = 0; j < (K > 0 ? K : KNN_MAX); j++) {
+    if (K == 0 && j >= k) break;
+    const uint16_t nd = ridx[base + j * 32];
+    const double w = rw[base + j * 32];
+    const double2* n = reinterpret_cast<const double2*>(nodes + nd);
+    const double2 a01 = __ldg(n + 0), a23 = __ldg(n + 1), a45 = __ldg(n + 2), a67 = __ldg(n + 3);
+    const double2 a8c0 = __ldg(n + 4), c12 = __ldg(n + 5);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(n + 6));
+    const double t0 = (double)(c0 - g.x), t1 = (double)(c1 - g.y), t2 = (double)(c2 - g.z);
+    // A column-major: row r = (A[r], A[r+3], A[r+6])
+    const double e0 = fma(a67.x, t2, fma(a23.y, t1, fma(a01.x, t0, a8c0.y)));
+    const double e1 = fma(a67.y, t2, fma(a45.x, t1, fma(a01.y, t0, c12.x)));
+    const double e2 = fma(a8c0.x, t2, fma(a45.y, t1, fma(a23.x, t0, c12.y)));
+    o0 = (float)fma(w, e0, (double)o0);
+    o1 = (float)fma(w, e1, (double)o1);
+    o2 = (float)fma(w, e2, (double)o2);
+  }
+  out[3 * i] = o0; out[3 * i + 1] = o1; out[3 * i + 2] = o2;
+}
+
+// ------------------------------------------------------------------ end points
+__global__ void k_end_points(long long N, const float* __restrict__ pos, const float* __restrict__ rot,
+                             const float* __restrict__ scale, float* __restrict__ ends) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= N) return;
+  const float4 r4 = ldg4(rot + 4 * g);
+  Quat q = quat_normalized(Quat{r4.x, r4.y, r4.z, r4.w});
+  float R[3][3]; quat_to_matrix(q, R);
+  const float p0 = pos[3 * g], p1 = pos[3 * g + 1], p2 = pos[3 * g + 2];
+  float* e = ends + g * 18;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const float len = (scale[3 * g + i] + 1e-3f) * 2.0f;  // axis_padding, end_coeff (GaussianView.hpp:116-117)
+    const float v0 = R[0][i] * len, v1 = R[1][i] * len, v2 = R[2][i] * len;
+    e[6 * i + 0] = p0 + v0; e[6 * i + 1] = p1 + v1; e[6 * i + 2] = p2 + v2;
+    e[6 * i + 3] = p0 - v0; e[6 * i + 4] = p1 - v1; e[6 * i + 5] = p2 - v2;
+  }
+}
+
+// ------------------------------------------------------------------ fit
+// Polar factor of a 3x3 (double) by determinant-scaled Newton iteration
+// X <- (mu X + X^-T / mu)/2.  The polar decomposition is unique, so this
+// reproduces the reference's double JacobiSVD U V^T (helper.cpp:429-440) to
+// ~1e-15.  K = diag(R^T M) = diag(V Sigma V^T).
+__device__ __forceinline__ void polar_newton(const double (&M)[3][3], double (&X)[3][3]) {
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) X[r][c] = M[r][c];
+  for (int it = 0; it < 12; it++) {
+    double C[3][3];  // cofactors: X^-T = C / det
+    C[0][0] = fma(X[1][1], X[2][2], -(X[1][2] * X[2][1]));
+    C[0][1] = fma(X[1][2], X[2][0], -(X[1][0] * X[2][2]));
+    C[0][2] = fma(X[1][0], X[2][1], -(X[1][1] * X[2][0]));
+    C[1][0] = fma(X[0][2], X[2][1], -(X[0][1] * X[2][2]));
+    C[1][1] = fma(X[0][0], X[2][2], -(X[0][2] * X[2][0]));
+    C[1][2] = fma(X[0][1], X[2][0], -(X[0][0] * X[2][1]));
+    C[2][0] = fma(X[0][1], X[1][2], -(X[0][2] * X[1][1]));
+    C[2][1] = fma(X[0][2], X[1][0], -(X[0][0] * X[1][2]));
+    C[2][2] = fma(X[0][0], X[1][1], -(X[0][1] * X[1][0]));
+    const double det = fma(X[0][0], C[0][0], fma(X[0][1], C[0][1], X[0][2] * C[0][2]));
+    // scaling mu = |det|^(-1/3) while far from orthogonal, 1 near convergence
+    const float adet = fabsf((float)det);
+    const double mu = (adet > 1.25f || adet < 0.8f) ? (double)rcbrtf(adet) : 1.0;
+    const double a = 0.5 * mu, b = 0.5 / (mu * det);
+    double delta = 0.0;
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const double nx = fma(a, X[r][c], b * C[r][c]);
+        delta = fmax(delta, fabs(nx - X[r][c]));
+        X[r][c] = nx;
+      }
+    if (delta < 1e-15) break;
+  }
+}
+
+constexpr int FIT_TILE = 128;
+constexpr int SH_PITCH = 49;    // odd pitch: conflict-free per-thread rows
+constexpr int END_PITCH = 19;
+
+__global__ void __launch_bounds__(FIT_TILE)
+k_fit_gaussians(long long N, const float* __restrict__ ends, const float* __restrict__ scale_backup,
+                const uint8_t* __restrict__ is_static, float* __restrict__ pos, float* __restrict__ rot,
+                float* __restrict__ scale, float* __restrict__ shs) {
+  extern __shared__ float smem[];
+  float* s_sh = smem;                              // FIT_TILE x SH_PITCH
+  float* s_end = smem + FIT_TILE * SH_PITCH;       // FIT_TILE x END_PITCH
+  __shared__ uint8_t s_static[FIT_TILE];
+
+  const long long g0 = (long long)blockIdx.x * FIT_TILE;
+  const int tid = threadIdx.x;
+  const int rows = (int)min((long long)FIT_TILE, N - g0);
+  s_static[tid] = (tid < rows) ? (is_static ? is_static[g0 + tid] : 0) : 1;
+  __syncthreads();
+
+  // coalesced float4 staging of the SH tile (48 floats = 12 float4 per row) and
+  // the endpoint tile (18 floats per row; 2 rows = 9 float4)
+  const float* gsh = shs + g0 * SH_FLOATS;
+  for (int v = tid; v < rows * 12; v += FIT_TILE) {
+    const int r = v / 12, c4 = v - r * 12;
+    if (s_static[r]) continue;
+    const float4 x = ld_stream4(gsh + (size_t)v * 4);
+    float* d = s_sh + r * SH_PITCH + c4 * 4;
+    d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w;
+  }
+  const float* gend = ends + g0 * 18;
+  const int nend = rows * 18;
+  for (int v = tid * 2; v < nend; v += FIT_TILE * 2) {  // 8-byte granules (18 floats/row is even)
+    const int r = v / 18, c = v - r * 18;
+    const float2 x = __ldg(reinterpret_cast<const float2*>(gend + v));
+    s_end[r * END_PITCH + c] = x.x; s_end[r * END_PITCH + c + 1] = x.y;
+  }
+  __syncthreads();
+
+  const long long g = g0 + tid;
+  if (tid < rows && !s_static[tid]) {
+    const float* e = s_end + tid * END_PITCH;
+    const float4 o4 = ldg4(rot + 4 * g);
+    const Quat oq{o4.x, o4.y, o4.z, o4.w};
+    float c[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++)  // Eigen redux order: (p0+(p1+p2)) + (p3+(p4+p5))
+      c[r] = ((e[r] + (e[3 + r] + e[6 + r])) + (e[9 + r] + (e[12 + r] + e[15 + r]))) / 6.0f;
+    double Md[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const float a = e[6 * i + r] - c[r], b = e[6 * i + 3 + r] - c[r];
+        Md[r][i] = (double)(0.5f * a + (-0.5f) * b);
+      }
+    double Rd[3][3];
+    polar_newton(Md, Rd);
+    float Rf[3][3], K[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+#pragma unroll
+      for (int j = 0; j < 3; j++) Rf[i][j] = (float)Rd[i][j];
+      K[i] = (float)fma(Rd[0][i], Md[0][i], fma(Rd[1][i], Md[1][i], Rd[2][i] * Md[2][i]));
+    }
+    const Quat q = quat_normalized(quat_from_matrix(Rf));
+    *reinterpret_cast<float4*>(rot + 4 * g) = make_float4(q.w, q.x, q.y, q.z);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const float s0 = scale_backup[3 * g + i];
+      scale[3 * g + i] = K[i] / ((s0 + 1e-3f) * 2.0f) * s0;
+      pos[3 * g + i] = c[i];
+    }
+    const Quat rq = quat_normalized(quat_mul(q, quat_inverse(oq)));
+    float Rs[3][3]; quat_to_matrix(rq, Rs);
+    sh_rotate_flipped(Rs, s_sh + tid * SH_PITCH);
+  }
+  __syncthreads();
+  float* osh = shs + g0 * SH_FLOATS;
+  for (int v = tid; v < rows * 12; v += FIT_TILE) {
+    const int r = v / 12, c4 = v - r * 12;
+    if (s_static[r]) continue;
+    const float* d = s_sh + r * SH_PITCH + c4 * 4;
+    st_stream4(osh + (size_t)v * 4, make_float4(d[0], d[1], d[2], d[3]));
+  }
+}
+
+// ------------------------------------------------------------------ node quaternions
+// FastgetOthogonalMatrix (helper.cpp:506-517): float Newton polar iteration,
+// returns the iterate BEFORE the one that met the 1e-6 max-abs test.
+__global__ void k_node_quats(int M, const double* __restrict__ rot, float4* __restrict__ q_xyzw) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= M) return;
+  float A[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) A[r][c] = (float)rot[9 * n + c * 3 + r];
+  for (int it = 0; it < 100; it++) {
+    float T[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) T[r][c] = A[c][r];
+    float cof[3][3];
+    cof[0][0] = T[1][1] * T[2][2] - T[1][2] * T[2][1];
+    cof[0][1] = T[1][2] * T[2][0] - T[1][0] * T[2][2];
+    cof[0][2] = T[1][0] * T[2][1] - T[1][1] * T[2][0];
+    cof[1][0] = T[0][2] * T[2][1] - T[0][1] * T[2][2];
+    cof[1][1] = T[0][0] * T[2][2] - T[0][2] * T[2][0];
+    cof[1][2] = T[0][1] * T[2][0] - T[0][0] * T[2][1];
+    cof[2][0] = T[0][1] * T[1][2] - T[0][2] * T[1][1];
+    cof[2][1] = T[0][2] * T[1][0] - T[0][0] * T[1][2];
+    cof[2][2] = T[0][0] * T[1][1] - T[0][1] * T[1][0];
+    const float det = T[0][0] * cof[0][0] + T[0][1] * cof[0][1] + T[0][2] * cof[0][2];
+    const float invdet = 1.0f / det;
+    float nx[3][3]; float md = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const float inv = cof[c][r] * invdet;
+        nx[r][c] = 0.5f * (A[r][c] + inv);
+        md = fmaxf(md, fabsf(A[r][c] - nx[r][c]));
+      }
+    if (md < 1e-6f) break;
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) A[r][c] = nx[r][c];
+  }
+  const Quat q = quat_normalized(quat_from_matrix(A));
+  q_xyzw[n] = make_float4(q.x, q.y, q.z, q.w);
+}
+
+// ------------------------------------------------------------------ sample SH rotation
+// One thread per sample, 64-sample tiles staged through shared memory so the
+// 192 B feature rows move as coalesced float4.  Skinning weights (float) and
+// node ids use the same 32-row blocked layout as the LBS tables.
+constexpr int RS_TILE = 128;
+__global__ void __launch_bounds__(RS_TILE)
+k_rotate_sample_shs(long long S, int k, const float* __restrict__ w, const uint16_t* __restrict__ idx,
+                    const float4* __restrict__ q_xyzw, const uint8_t* __restrict__ is_static,
+                    float* __restrict__ feature) {
+  extern __shared__ float smem[];
+  float* s_sh = smem;
+  __shared__ uint8_t s_static[RS_TILE];
+  const long long s0 = (long long)blockIdx.x * RS_TILE;
+  const int tid = threadIdx.x;
+  const int rows = (int)min((long long)RS_TILE, S - s0);
+  s_static[tid] = (tid < rows) ? (is_static ? is_static[s0 + tid] : 0) : 1;
+  __syncthreads();
+  const float* gsh = feature + s0 * SH_FLOATS;
+  for (int v = tid; v < rows * 12; v += RS_TILE) {
+    const int r = v / 12, c4 = v - r * 12;
+    if (s_static[r]) continue;
+    const float4 x = ld_stream4(gsh + (size_t)v * 4);
+    float* d = s_sh + r * SH_PITCH + c4 * 4;
+    d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w;
+  }
+  __syncthreads();
+  const long long s = s0 + tid;
+  if (tid < rows && !s_static[tid]) {
+    Quat wq{1.0f, 0.0f, 0.0f, 0.0f};
+    float last = 0.0f;
+    const long long base = (s >> 5) * (long long)(k * 32) + (s & 31);
+    for (int j = 0; j < k; j++) {
+      const float cw = w[base + j * 32];
+      const float t = cw / (cw + last);
+      const float4 e = __ldg(q_xyzw + idx[base + j * 32]);
+      Quat eq{e.w, e.x, e.y, e.z};
+      const float cf = wq.x * eq.x + wq.y * eq.y + wq.z * eq.z + wq.w * eq.w;
+      double cosa = (double)cf;
+      if (cosa < 0) { eq.x = -eq.x; eq.y = -eq.y; eq.z = -eq.z; eq.w = -eq.w; cosa = -cosa; }
+      double rA, rB; const double td = (double)t;
+      if (cosa > (double)0.99995f) { rA = 1.0 - td; rB = td; }
+      else {
+        const double sina = sqrt(1.0 - cosa * cosa);
+        const double ang = atan2(sina, cosa);
+        rA = sin((1.0 - td) * ang) / sina;
+        rB = sin(td * ang) / sina;
+      }
+      Quat l;
+      l.x = (float)(rA * wq.x + rB * eq.x); l.y = (float)(rA * wq.y + rB * eq.y);
+      l.z = (float)(rA * wq.z + rB * eq.z); l.w = (float)(rA * wq.w + rB * eq.w);
+      wq = quat_normalized(l);
+      last += cw;
+    }
+    float R[3][3]; quat_to_matrix(quat_normalized(wq), R);
+    sh_rotate_flipped(R, s_sh + tid * SH_PITCH);
+  }
+  __syncthreads();
+  float* osh = feature + s0 * SH_FLOATS;
+  for (int v = tid; v < rows * 12; v += RS_TILE) {
+    const int r = v / 12, c4 = v - r * 12;
+    if (s_static[r]) continue;
+    const float* d = s_sh + r * SH_PITCH + c4 * 4;
+    st_stream4(osh + (size_t)v * 4, make_float4(d[0], d[1], d[2], d[3]));
+  }
+}
+
+// ------------------------------------------------------------------ static flags
+// out[g] = 1 iff every neighbour of every row in group g is an excluded node.
+__global__ void k_static_flags(long long G, int group, int k, const uint16_t* __restrict__ idx,
+                               const uint8_t* __restrict__ node_static, uint8_t* __restrict__ out) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  uint8_t st = 1;
+  for (long long r = g * group; r < (g + 1) * group; r++) {
+    const long long base = (r >> 5) * (long long)(k * 32) + (r & 31);
+    for (int j = 0; j < k; j++) st &= node_static[idx[base + j * 32]];
+  }
+  out[g] = st;
+}
+
+}  // namespace arapgs
+
+// ===========================================================================
+// launchers (kernel-level C ABI, see include/arapgs.h)
+// ===========================================================================
+using namespace arapgs;
+
+static bool g_sh_ready = false;
+static int ensure_sh_tables() {
+  if (g_sh_ready) return ARAP_OK;
+  ShCoef h;
+  auto fill = [](int L, double* u, double* v, double* w) {
+    for (int m = -L; m <= L; m++) for (int n = -L; n <= L; n++) {
+      const int d = (m == 0), am = m < 0 ? -m : m, an = n < 0 ? -n : n;
+      const double denom = (an == L) ? double(2 * L * (2 * L - 1)) : double((L + n) * (L - n));
+      const int i = (m + L) * (2 * L + 1) + (n + L);
+      u[i] = std::sqrt(double((L + m) * (L - m)) / denom);
+      v[i] = 0.5 * std::sqrt(double((1 + d) * (L + am - 1) * (L + am)) / denom) * (1 - 2 * d);
+      w[i] = -0.5 * std::sqrt(double((L - am - 1) * (L - am)) / denom) * (1 - d);
+    }
+  };
+  fill(2, h.u2, h.v2, h.w2);
+  fill(3, h.u3, h.v3, h.w3);
+  ARAP_CUDA_TRY(cudaMemcpyToSymbol(c_sh, &h, sizeof(h)));
+  g_sh_ready = true;
+  return ARAP_OK;
+}
+
+extern "C" int arapk_node_xf(int M, const double* rot, const double* trans, const float* node_pos, void* node_xf,
+                             cudaStream_t st) {
+  if (M <= 0) return ARAP_OK;
+  k_node_xf<<<(M + 127) / 128, 128, 0, st>>>(M, rot, trans, node_pos, (NodeXf*)node_xf);
+  ARAP_KERNEL_CHECK();
+  return ARAP_OK;
+}
+
+extern "C" int arapk_lbs_points(const float* in, float* out, long long P, int k, const uint16_t* ridx, const double* rw,
+                                const void* node_xf, const uint8_t* skip, int group, cudaStream_t st) {
+  if (P <= 0) return ARAP_OK;
+  if (k < 1 || k > KNN_MAX) { set_error("lbs_points: k out of range"); return ARAP_ERR_INVALID; }
+  const int bs = 256;
+  const unsigned grid = (unsigned)((P + bs - 1) / bs);
+  const NodeXf* nx = (const NodeXf*)node_xf;
+  if (group < 1) group = 1;
+  switch (k) {
+    case 8: k_lbs_points<8><<<grid, bs, 0, st>>>(in, out, P, k, ridx, rw, nx, skip, group); break;
+    case 10: k_lbs_points<10><<<grid, bs, 0, st>>>(in, out, P, k, ridx, rw, nx, skip, group); break;
+    case 12: k_lbs_points<12><<<grid, bs, 0, st>>>(in, out, P, k, ridx, rw, nx, skip, group); break;
+    default: k_lbs_points<0><<<grid, bs, 0, st>>>(in, out, P, k, ridx, rw, nx, skip, group); break;
+  }
+  ARAP_KERNEL_CHECK();
+  return ARAP_OK;
+}
+
+extern "C" int arapk_end_points(long long N, const float* pos, const float* rot, const float* scale, float* ends,
+                                cudaStream_t st) {
+  if (N <= 0) return ARAP_OK;
+  k_end_points<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, pos, rot, scale, ends);
+  ARAP_KERNEL_CHECK();
+  return ARAP_OK;
+}
+
+extern "C" int arapk_fit_gaussians(long long N, const float* ends, const float* scale_backup, const uint8_t* is_static,
+                                   float* pos, float* rot, float* scale, float* shs, cudaStream_t st) {
+  if (N <= 0) return ARAP_OK;
+  int rc = ensure_sh_tables(); if (rc) return rc;
+  const size_t smem = sizeof(float) * FIT_TILE * (SH_PITCH + END_PITCH);
+  k_fit_gaussians<<<(unsigned)((N + FIT_TILE - 1) / FIT_TILE), FIT_TILE, smem, st>>>(N, ends, scale_backup, is_static, pos, rot,
+                                                                                     scale, shs);
+  ARAP_KERNEL_CHECK();
+  return ARAP_OK;
+}
+
+extern "C" int arapk_node_quats(int M, const double* rot, float* q_xyzw, cudaStream_t st) {
+  if (M <= 0) return ARAP_OK;
+  k_node_quats<<<(M + 127) / 128, 128, 0, st>>>(M, rot, (float4*)q_xyzw);
+  ARAP_KERNEL_CHECK();
+  return ARAP_OK;
+}
+
+extern "C" int arapk_rotate_sample_shs(long long S, int k, const float* w, const uint16_t* idx, const float* q_xyzw,
+                                       const uint8_t* is_static, float* feature, cudaStream_t st) {
+  if (S <= 0) return ARAP_OK;
+  int rc = ensure_sh_tables(); if (rc) return rc;
+  const size_t smem = sizeof(float) * RS_TILE * SH_PITCH;
+  k_rotate_sample_shs<<<(unsigned)((S + RS_TILE - 1) / RS_TILE), RS_TILE, smem, st>>>(S, k, w, idx, (const float4*)q_xyzw,
+                                                                                      is_static, feature);
+  ARAP_KERNEL_CHECK();
+  return ARAP_OK;
+}
+
+extern "C" int arapk_static_flags(long long G, int group, int k, const uint16_t* idx, const uint8_t* node_static,
+                                  uint8_t* out, cudaStream_t st) {
+  if (G <= 0) return ARAP_OK;
+  k_static_flags<<<(unsigned)((G + 255) / 256), 256, 0, st>>>(G, group, k, idx, node_static, out);
+  ARAP_KERNEL_CHECK();
+  return ARAP_OK;
+}
+
+extern "C" int arapk_sh_rotate_test(const float* R9, float* shs48_dev, cudaStream_t st);
+namespace arapgs {
+__global__ void k_sh_rotate_test(const float* R9, float* shs) {
+  float R[3][3];
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) R[i][j] = R9[3 * i + j];
+  sh_rotate_flipped(R, shs);
+}
+}  // namespace arapgs
+extern "C" int arapk_sh_rotate_test(const float* R9, float* shs48_dev, cudaStream_t st) {
+  int rc = ensure_sh_tables(); if (rc) return rc;
+  k_sh_rotate_test<<<1, 1, 0, st>>>(R9, shs48_dev);
+  ARAP_KERNEL_CHECK();
+  return ARAP_OK;
+}

@@ -1,0 +1,550 @@
+// Stage (a): density grid — cell assignment, Gaussian re-ordering, per-Gaussian
+// cutoff boxes, per-cell Gaussian lists, sample emit, adaptive LPF, evaluation.
+//
+//   cell_assign       GetGsGrid + CUB scan + host re-order   (cudakdtree.cu:403-423, 508-528; GaussianView.cpp:3896-3953)
+//   gs_aabbs          per-Gaussian cutoff AABB               (GaussianView.cpp:3961-4019)
+//   footprint_count   GetBoxesGsGrid + scan                  (cudakdtree.cu:425-451, 533-553)
+//   footprint_fill    serial host fill, replaced             (GaussianView.cpp:4077-4100)
+//   valid_cells / emit_samples                               (GaussianView.cpp:4040-4053, 4111-4133)
+//   ada_lpf           GetAdaLpfRatio                         (GaussianView.cpp:4670-4751)
+//   grid_eval         Rasterizer::forward3d_grid (EXTERNAL, source absent; call site GaussianView.cpp:4159-4186)
+//
+// Cell indices and list contents are integer work and must equal the
+// reference's bit for bit: cells use the same float expression
+// floor((p - min) / step) (IEEE division, -fmad=false), and the lists are
+// produced by an atomic fill followed by an in-place per-cell sort, which gives
+// the serial host loop's order (ascending Gaussian index within a cell).
+#include <cfloat>
+#include "device_math.cuh"
+#include "kernels.h"
+
+namespace arapgs {
+
+// ------------------------------------------------------------------ scan (int32, inclusive)
+constexpr int SCAN_BLOCK = 1024;
+constexpr int SCAN_ITEMS = 4;  // per thread -> 4096 per block
+
+__device__ __forceinline__ int block_scan_incl(int v, int* s_warp) {
+  int x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += t; }
+  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int wv = s_warp[threadIdx.x];
+    int y = wv;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, y, o); if (threadIdx.x >= o) y += t; }
+    s_warp[threadIdx.x] = y - wv;
+  }
+  __syncthreads();
+  const int r = x + s_warp[threadIdx.x >> 5];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_block_sums(const int* __restrict__ in, long long n, int* __restrict__ sums) {
+  __shared__ int s_warp[32];
+  const long long base = (long long)blockIdx.x * SCAN_BLOCK * SCAN_ITEMS + (long long)threadIdx.x * SCAN_ITEMS;
+  int t = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) if (base + i < n) t += in[base + i];
+  const int inc = block_scan_incl(t, s_warp);
+  if (threadIdx.x == SCAN_BLOCK - 1) sums[blockIdx.x] = inc;
+}
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_sums(int* __restrict__ sums, int nb) {  // exclusive, single block
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int b = 0; b < nb; b += SCAN_BLOCK) {
+    const int i = b + threadIdx.x;
+    const int v = i < nb ? sums[i] : 0;
+    const int inc = block_scan_incl(v, s_warp);
+    const int carry = s_carry;
+    if (i < nb) sums[i] = carry + inc - v;
+    __syncthreads();
+    if (threadIdx.x == SCAN_BLOCK - 1) s_carry = carry + inc;
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_final(const int* __restrict__ in, long long n, const int* __restrict__ sums,
+                                                           int* __restrict__ out) {
+  __shared__ int s_warp[32];
+  const long long base = (long long)blockIdx.x * SCAN_BLOCK * SCAN_ITEMS + (long long)threadIdx.x * SCAN_ITEMS;
+  int v[SCAN_ITEMS]; int t = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) { v[i] = (base + i < n) ? in[base + i] : 0; t += v[i]; }
+  const int inc = block_scan_incl(t, s_warp);
+  int run = sums[blockIdx.x] + inc - t;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) { run += v[i]; if (base + i < n) out[base + i] = run; }
+}
+
+static int scan_inclusive(const int* in, int* out, long long n, int* sums_scratch, cudaStream_t st) {
+  if (n <= 0) return ARAP_OK;
+  const int per = SCAN_BLOCK * SCAN_ITEMS;
+  const int nb = (int)((n + per - 1) / per);
+  k_scan_block_sums<<<nb, SCAN_BLOCK, 0, st>>>(in, n, sums_scratch);
+  k_scan_sums<<<1, SCAN_BLOCK, 0, st>>>(sums_scratch, nb);
+  k_scan_final<<<nb, SCAN_BLOCK, 0, st>>>(in, n, sums_scratch, out);
+  ARAP_KERNEL_CHECK();
+  return ARAP_OK;
+}
+
+// ------------------------------------------------------------------ segmented in-place sort (ascending int)
+// Normalised bitonic network (all comparators point up) with virtual +inf
+// padding, so arbitrary segment lengths sort in place.
+constexpr int SEG_WARP_CAP = 1024;
+
+__device__ __forceinline__ void bitonic_steps(int* a, int n, int tid, int nthreads, bool block_sync) {
+  int np = 1; while (np < n) np <<= 1;
+  for (int k = 2; k <= np; k <<= 1) {
+    for (int i = tid; i < np; i += nthreads) {  // first sub-step: mirror within the k-block
+      const int p = i ^ (k - 1);
+      if (p > i && p < n) { const int x = a[i], y = a[p]; if (x > y) { a[i] = y; a[p] = x; } }
+    }
+    if (block_sync) __syncthreads(); else __syncwarp();
+    for (int j = k >> 2; j > 0; j >>= 1) {
+      for (int i = tid; i < np; i += nthreads) {
+        const int p = i ^ j;
+        if (p > i && p < n) { const int x = a[i], y = a[p]; if (x > y) { a[i] = y; a[p] = x; } }
+      }
+      if (block_sync) __syncthreads(); else __syncwarp();
+    }
+  }
+}
+
+// one warp per cell; segments longer than SEG_WARP_CAP go to the block kernel
+__global__ void __launch_bounds__(256)
+k_segsort_warp(long long ncell, const int* __restrict__ prefix, int* __restrict__ data, int* __restrict__ big_count,
+               int* __restrict__ big_list) {
+  __shared__ int s_buf[8][SEG_WARP_CAP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long c = (long long)blockIdx.x * 8 + warp;
+  if (c >= ncell) return;
+  const int b = c ? prefix[c - 1] : 0, e = prefix[c];
+  const int n = e - b;
+  if (n <= 1) return;
+  if (n > SEG_WARP_CAP) { if (lane == 0) big_list[atomicAdd(big_count, 1)] = (int)c; return; }
+  int* a = s_buf[warp];
+  for (int i = lane; i < n; i += 32) a[i] = data[b + i];
+  __syncwarp();
+  if (n <= 32) {
+    // rank sort: values are distinct Gaussian indices
+    const int v = lane < n ? a[lane] : 0x7fffffff;
+    int r = 0;
+    for (int i = 0; i < n; i++) r += (a[i] < v);
+    if (lane < n) data[b + r] = v;
+    return;
+  }
+  bitonic_steps(a, n, lane, 32, false);
+  for (int i = lane; i < n; i += 32) data[b + i] = a[i];
+}
+
+__global__ void __launch_bounds__(512)
+k_segsort_block(const int* __restrict__ big_list, const int* __restrict__ prefix, int* __restrict__ data) {
+  const int c = big_list[blockIdx.x];
+  const int b = c ? prefix[c - 1] : 0, e = prefix[c];
+  bitonic_steps(data + b, e - b, threadIdx.x, blockDim.x, true);
+}
+
+// ------------------------------------------------------------------ cell assignment
+__device__ __forceinline__ int cell_coord(float p, float mn, float step) { return (int)floorf((p - mn) / step); }
+
+__global__ void k_cell_hist(long long N, const float* __restrict__ pos, float3 mn, float step, int G, int* __restrict__ cell_out,
+                            int* __restrict__ cnt) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int x = cell_coord(pos[3 * i], mn.x, step), y = cell_coord(pos[3 * i + 1], mn.y, step), z = cell_coord(pos[3 * i + 2], mn.z, step);
+  const int c = x * G * G + y * G + z;
+  cell_out[i] = c;
+  if (c >= 0 && c < G * G * G) atomicAdd(&cnt[c], 1);
+}
+__global__ void k_cell_fill(long long N, int G, const int* __restrict__ cell, const int* __restrict__ prefix, int* __restrict__ fill,
+                            int* __restrict__ members) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int c = cell[i];
+  if (c < 0 || c >= G * G * G) return;  // outside the scene box (the reference would index out of bounds)
+  const int start = c ? prefix[c - 1] : 0;
+  members[start + atomicAdd(&fill[c], 1)] = (int)i;
+}
+__global__ void k_invert_perm(long long N, const int* __restrict__ members, int* __restrict__ new_idx) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N) return;
+  new_idx[members[t]] = (int)t;
+}
+
+// out[new_idx[i]] = in[i] for all five attribute arrays; one thread per (gaussian, 16-byte chunk of SH)
+__global__ void k_permute(long long N, const int* __restrict__ new_idx, const float* __restrict__ pos, const float* __restrict__ rot,
+                          const float* __restrict__ scale, const float* __restrict__ opacity, const float* __restrict__ shs,
+                          float* __restrict__ pos_o, float* __restrict__ rot_o, float* __restrict__ scale_o,
+                          float* __restrict__ opacity_o, float* __restrict__ shs_o) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = t / 12; const int c = (int)(t - i * 12);
+  if (i >= N) return;
+  const long long d = new_idx[i];
+  reinterpret_cast<float4*>(shs_o + d * 48)[c] = __ldg(reinterpret_cast<const float4*>(shs + i * 48) + c);
+  if (c == 0) {
+    pos_o[3 * d] = pos[3 * i]; pos_o[3 * d + 1] = pos[3 * i + 1]; pos_o[3 * d + 2] = pos[3 * i + 2];
+    scale_o[3 * d] = scale[3 * i]; scale_o[3 * d + 1] = scale[3 * i + 1]; scale_o[3 * d + 2] = scale[3 * i + 2];
+    reinterpret_cast<float4*>(rot_o)[d] = __ldg(reinterpret_cast<const float4*>(rot) + i);
+    opacity_o[d] = opacity[i];
+  }
+}
+
+// ------------------------------------------------------------------ Gaussian cutoff boxes
+__global__ void k_gs_aabbs(long long N, const float* __restrict__ pos, const float* __restrict__ rot, const float* __restrict__ scale,
+                           const float* __restrict__ opacity, float* __restrict__ aabb, float* __restrict__ clip,
+                           float* __restrict__ smax) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= N) return;
+  const float4 r4 = ldg4(rot + 4 * g);
+  const Quat q = quat_normalized(Quat{r4.x, r4.y, r4.z, r4.w});
+  float R[3][3]; quat_to_matrix(q, R);
+  const float op = opacity[g];
+  float s3[3];
+  if (op <= 1.0f / 255.0f) { s3[0] = s3[1] = s3[2] = 0.0f; }
+  else {
+    const float rad = sqrtf(-2.0f * logf(1.0f / 255.0f / op));  // CUTOFF_ALPHA (helper.hpp:62)
+#pragma unroll
+    for (int i = 0; i < 3; i++) s3[i] = rad * (scale[3 * g + i] + 0.0f);
+  }
+  if (clip) { clip[3 * g] = s3[0]; clip[3 * g + 1] = s3[1]; clip[3 * g + 2] = s3[2]; }
+  if (smax) { float m = s3[0]; if (s3[1] > m) m = s3[1]; if (s3[2] > m) m = s3[2]; smax[g] = m; }
+  const float p[3] = {pos[3 * g], pos[3 * g + 1], pos[3 * g + 2]};
+  float mn[3] = {p[0], p[1], p[2]}, mx[3] = {p[0], p[1], p[2]};
+#pragma unroll
+  for (int d = 0; d < 3; d++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const float v = R[c][d] * s3[d];
+      const float l = p[c] + v, r = p[c] + (-v);
+      mn[c] = fminf(mn[c], l); mx[c] = fmaxf(mx[c], l);
+      mn[c] = fminf(mn[c], r); mx[c] = fmaxf(mx[c], r);
+    }
+#pragma unroll
+  for (int c = 0; c < 3; c++) { aabb[6 * g + c] = mn[c]; aabb[6 * g + 3 + c] = mx[c]; }
+}
+
+__device__ __forceinline__ void cell_range(const float* a, float3 mn, float step, int G, int padding, int (&lo)[3], int (&hi)[3]) {
+  const float m[3] = {mn.x, mn.y, mn.z};
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    lo[c] = max((int)floorf((a[c] - m[c]) / step) - padding, 0);
+    hi[c] = min((int)floorf((a[3 + c] - m[c]) / step) + padding, G - 1);
+  }
+}
+
+template <bool FILL>
+__global__ void k_footprint(long long N, const float* __restrict__ aabb, float3 mn, float step, int G, int padding,
+                            int* __restrict__ cnt_or_fill, const int* __restrict__ prefix, int* __restrict__ lists) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= N) return;
+  float a[6];
+#pragma unroll
+  for (int c = 0; c < 6; c++) a[c] = aabb[6 * g + c];
+  int lo[3], hi[3]; cell_range(a, mn, step, G, padding, lo, hi);
+  for (int x = lo[0]; x <= hi[0]; x++) for (int y = lo[1]; y <= hi[1]; y++) for (int z = lo[2]; z <= hi[2]; z++) {
+    const int c = x * G * G + y * G + z;
+    if (FILL) {
+      const int start = c ? prefix[c - 1] : 0;
+      lists[start + atomicAdd(&cnt_or_fill[c], 1)] = (int)g;
+    } else atomicAdd(&cnt_or_fill[c], 1);
+  }
+}
+
+// ------------------------------------------------------------------ valid cells + samples
+__global__ void k_valid_flags(long long ncell, const int* __restrict__ prefix, int* __restrict__ flags) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  flags[c] = (prefix[c] - (c ? prefix[c - 1] : 0)) != 0;
+}
+__global__ void k_valid_compact(long long ncell, const int* __restrict__ flags, const int* __restrict__ incl, int* __restrict__ out) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  if (flags[c]) out[incl[c] - 1] = (int)c;
+}
+
+__global__ void k_emit_samples(int V, const int* __restrict__ valid, float3 mn, float step, int G, float* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = t >> 6; const int s = (int)(t & 63);
+  if (i >= V) return;
+  const int c = valid[i];
+  const int xi = c / (G * G), yi = (c - xi * G * G) / G, zi = c % G;
+  const float interval = step / 4;  // SAMPLES_PER_GRID
+  // float + int*float, then + 0.5*interval evaluated in double, rounded to float (GaussianView.cpp:4119-4121)
+  const float gx = (float)((double)(mn.x + xi * step) + 0.5 * (double)interval);
+  const float gy = (float)((double)(mn.y + yi * step) + 0.5 * (double)interval);
+  const float gz = (float)((double)(mn.z + zi * step) + 0.5 * (double)interval);
+  const int sx = s / 16, sy = (s - sx * 16) / 4, sz = s % 4;
+  float* o = out + t * 3;
+  o[0] = gx + sx * interval; o[1] = gy + sy * interval; o[2] = gz + sz * interval;
+}
+
+// adaptive LPF (closed form of the 24x9 least squares: M = P Q^T (Q Q^T)^-1,
+// (Q Q^T)^-1 = 0.5 I - 0.125 ones)
+__global__ void k_ada_lpf(int V, const float* __restrict__ samples, const int* __restrict__ valid, float lpf, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= V) return;
+  const float* base = samples + (size_t)i * 64 * 3;
+  float PQt[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+#pragma unroll
+  for (int col = 0; col < 8; col++) {
+    int idx = 0; float q[3] = {0.f, 0.f, 0.f};
+    if (col % 2 == 1) { q[0] = 1.0f; idx += 48; }
+    if ((col / 2) % 2 == 1) { q[1] = 1.0f; idx += 12; }
+    if ((col / 4) % 2 == 1) { q[2] = 1.0f; idx += 3; }
+    float p[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) p[r] = (base[idx * 3 + r] - base[r]) / 3.0f;
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) PQt[r][c] += p[r] * q[c];
+  }
+  float Mx[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    const float rs = PQt[r][0] + PQt[r][1] + PQt[r][2];
+#pragma unroll
+    for (int c = 0; c < 3; c++) Mx[r][c] = 0.5f * PQt[r][c] - 0.125f * rs;
+  }
+  float* o = out + (size_t)valid[i] * 9;
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      float s = 0.f;
+#pragma unroll
+      for (int t = 0; t < 3; t++) s += Mx[r][t] * Mx[c][t];
+      o[3 * r + c] = s * lpf;
+    }
+}
+
+// ------------------------------------------------------------------ field evaluation
+// forward3d_grid is EXTERNAL to the reference tree (XinhaoT/CudaRasterizer @
+// 96ea96c, source absent) — PARITY UNPINNED.  Implemented from the call-site
+// parameter list and the field definition:
+//   w_g(x) = alpha_g exp(-1/2 d^T (Sigma_g + LPF_cell)^-1 d),  feature = sum w_g SH_g,  opacity = sum w_g
+// One CTA per valid cell, one thread per sample; the cell's list is staged in
+// shared memory in chunks (inverse covariance, centre, alpha, cutoff, 48 SH
+// floats per Gaussian) and consumed in list order.
+constexpr int EV_CHUNK = 32;
+struct EvGauss { float px, py, pz, a, i00, i01, i02, i11, i12, i22, cut, ok; };
+
+__global__ void __launch_bounds__(64)
+k_grid_eval(const int* __restrict__ valid, const int* __restrict__ prefix, const int* __restrict__ lists,
+            const float* __restrict__ samples, const float* __restrict__ pos, const float* __restrict__ rot,
+            const float* __restrict__ scale, const float* __restrict__ opacity, const float* __restrict__ shs,
+            const float* __restrict__ ada_lpf, float* __restrict__ out_feature, float* __restrict__ out_opacity) {
+  __shared__ EvGauss s_g[EV_CHUNK];
+  __shared__ float s_sh[EV_CHUNK][48];
+  const int i = blockIdx.x;
+  const int c = valid[i];
+  const int beg = c ? prefix[c - 1] : 0, end = prefix[c];
+  const int tid = threadIdx.x;
+  const float* lp = ada_lpf + (size_t)c * 9;
+  const float* xs = samples + ((size_t)i * 64 + tid) * 3;
+  const float x0 = xs[0], x1 = xs[1], x2 = xs[2];
+  float acc[48];
+#pragma unroll
+  for (int u = 0; u < 48; u++) acc[u] = 0.f;
+  float opa = 0.f;
+  for (int base = beg; base < end; base += EV_CHUNK) {
+    const int nc = min(EV_CHUNK, end - base);
+    __syncthreads();
+    if (tid < nc) {
+      const int g = lists[base + tid];
+      EvGauss e; e.ok = 0.f;
+      const float a = opacity[g];
+      e.px = pos[3 * g]; e.py = pos[3 * g + 1]; e.pz = pos[3 * g + 2]; e.a = a;
+      e.i00 = e.i01 = e.i02 = e.i11 = e.i12 = e.i22 = 0.f; e.cut = 0.f;
+      if (a > 1.0f / 255.0f) {
+        const float4 r4 = ldg4(rot + 4 * g);
+        const Quat q = quat_normalized(Quat{r4.x, r4.y, r4.z, r4.w});
+        float R[3][3]; quat_to_matrix(q, R);
+        float Sg[3][3];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+          for (int cc = 0; cc < 3; cc++) {
+            float s = 0.f;
+#pragma unroll
+            for (int d = 0; d < 3; d++) s += R[r][d] * (scale[3 * g + d] * scale[3 * g + d]) * R[cc][d];
+            Sg[r][cc] = s + lp[3 * r + cc];
+          }
+        const float c00 = Sg[1][1] * Sg[2][2] - Sg[1][2] * Sg[2][1];
+        const float c01 = Sg[1][2] * Sg[2][0] - Sg[1][0] * Sg[2][2];
+        const float c02 = Sg[1][0] * Sg[2][1] - Sg[1][1] * Sg[2][0];
+        const float det = Sg[0][0] * c00 + Sg[0][1] * c01 + Sg[0][2] * c02;
+        if (det > 0.0f) {
+          const float id = 1.0f / det;
+          e.i00 = c00 * id; e.i01 = c01 * id; e.i02 = c02 * id;
+          e.i11 = (Sg[0][0] * Sg[2][2] - Sg[0][2] * Sg[2][0]) * id;
+          e.i12 = (Sg[0][2] * Sg[1][0] - Sg[0][0] * Sg[1][2]) * id;
+          e.i22 = (Sg[0][0] * Sg[1][1] - Sg[0][1] * Sg[1][0]) * id;
+          e.cut = logf(1.0f / 255.0f / a);
+          e.ok = 1.f;
+        }
+      }
+      s_g[tid] = e;
+    }
+    for (int v = tid; v < nc * 12; v += 64) {
+      const int r = v / 12, c4 = v - r * 12;
+      const float4 x = __ldg(reinterpret_cast<const float4*>(shs + (size_t)lists[base + r] * 48) + c4);
+      float* d = &s_sh[r][c4 * 4];
+      d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w;
+    }
+    __syncthreads();
+    for (int t = 0; t < nc; t++) {
+      const EvGauss e = s_g[t];
+      if (e.ok == 0.f) continue;
+      const float d0 = x0 - e.px, d1 = x1 - e.py, d2 = x2 - e.pz;
+      const float pw = -0.5f * (e.i00 * d0 * d0 + e.i11 * d1 * d1 + e.i22 * d2 * d2) - (e.i01 * d0 * d1 + e.i02 * d0 * d2 + e.i12 * d1 * d2);
+      if (pw > 0.0f || pw < e.cut) continue;
+      const float w = e.a * expf(pw);
+      opa += w;
+#pragma unroll
+      for (int u = 0; u < 48; u++) acc[u] += w * s_sh[t][u];
+    }
+  }
+  float* of = out_feature + ((size_t)i * 64 + tid) * 48;
+#pragma unroll
+  for (int u = 0; u < 48; u += 4) *reinterpret_cast<float4*>(of + u) = make_float4(acc[u], acc[u + 1], acc[u + 2], acc[u + 3]);
+  out_opacity[(size_t)i * 64 + tid] = opa;
+}
+
+}  // namespace arapgs
+
+using namespace arapgs;
+
+// scratch layout helper: [cnt G^3][fill G^3][scan sums][big list G^3 + 1][members N]
+extern "C" size_t arapk_grid_scratch_bytes(long long N, int G) {
+  const size_t gc = (size_t)G * G * G;
+  return (gc * 4 + 8192 + (size_t)N) * sizeof(int) + 1024;
+}
+
+namespace {
+struct GridScratch { int *cnt, *fill, *sums, *big, *members; };
+static GridScratch carve(void* scratch, int G, long long N) {
+  const size_t gc = (size_t)G * G * G;
+  GridScratch s; int* p = (int*)scratch;
+  s.cnt = p; p += gc; s.fill = p; p += gc; s.sums = p; p += 4096; s.big = p; p += gc + 4096; s.members = p;
+  (void)N; return s;
+}
+static int sort_segments(long long ncell, const int* prefix, int* data, int* big, cudaStream_t st) {
+  ARAP_CUDA_TRY(cudaMemsetAsync(big, 0, sizeof(int), st));
+  k_segsort_warp<<<(unsigned)((ncell + 7) / 8), 256, 0, st>>>(ncell, prefix, data, big, big + 1);
+  ARAP_KERNEL_CHECK();
+  int nbig = 0;
+  ARAP_CUDA_TRY(cudaMemcpyAsync(&nbig, big, sizeof(int), cudaMemcpyDeviceToHost, st));
+  ARAP_CUDA_TRY(cudaStreamSynchronize(st));
+  if (nbig > 0) { k_segsort_block<<<nbig, 512, 0, st>>>(big + 1, prefix, data); ARAP_KERNEL_CHECK(); }
+  return ARAP_OK;
+}
+}  // namespace
+
+extern "C" int arapk_cell_assign(const float* pos, long long N, const float* min3, float step, int G, int* cell_out,
+                                 int* prefix_out, int* new_idx_out, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+  if (scratch_bytes < arapk_grid_scratch_bytes(N, G)) { set_error("cell_assign: scratch too small"); return ARAP_ERR_INVALID; }
+  const long long gc = (long long)G * G * G;
+  GridScratch s = carve(scratch, G, N);
+  ARAP_CUDA_TRY(cudaMemsetAsync(s.cnt, 0, sizeof(int) * gc * 2, st));  // cnt + fill
+  const float3 mn = make_float3(min3[0], min3[1], min3[2]);
+  if (N > 0) { k_cell_hist<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, pos, mn, step, G, cell_out, s.cnt); ARAP_KERNEL_CHECK(); }
+  int rc = scan_inclusive(s.cnt, prefix_out, gc, s.sums, st); if (rc) return rc;
+  if (new_idx_out && N > 0) {
+    k_cell_fill<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, G, cell_out, prefix_out, s.fill, s.members); ARAP_KERNEL_CHECK();
+    rc = sort_segments(gc, prefix_out, s.members, s.big, st); if (rc) return rc;
+    k_invert_perm<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, s.members, new_idx_out); ARAP_KERNEL_CHECK();
+  }
+  return ARAP_OK;
+}
+
+extern "C" int arapk_permute_gaussians(long long N, const int* new_idx, const float* pos, const float* rot, const float* scale,
+                                       const float* opacity, const float* shs, float* pos_o, float* rot_o, float* scale_o,
+                                       float* opacity_o, float* shs_o, cudaStream_t st) {
+  if (N <= 0) return ARAP_OK;
+  const long long T = N * 12;
+  k_permute<<<(unsigned)((T + 255) / 256), 256, 0, st>>>(N, new_idx, pos, rot, scale, opacity, shs, pos_o, rot_o, scale_o, opacity_o, shs_o);
+  ARAP_KERNEL_CHECK();
+  return ARAP_OK;
+}
+
+extern "C" int arapk_gs_aabbs(long long N, const float* pos, const float* rot, const float* scale, const float* opacity,
+                              float* aabb, float* clip, float* smax, cudaStream_t st) {
+  if (N <= 0) return ARAP_OK;
+  k_gs_aabbs<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, pos, rot, scale, opacity, aabb, clip, smax);
+  ARAP_KERNEL_CHECK();
+  return ARAP_OK;
+}
+
+extern "C" int arapk_footprint_count(long long N, const float* aabb, const float* min3, float step, int G, int padding,
+                                     int* prefix_out, long long* total_host, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+  if (scratch_bytes < arapk_grid_scratch_bytes(0, G)) { set_error("footprint_count: scratch too small"); return ARAP_ERR_INVALID; }
+  const long long gc = (long long)G * G * G;
+  GridScratch s = carve(scratch, G, N);
+  ARAP_CUDA_TRY(cudaMemsetAsync(s.cnt, 0, sizeof(int) * gc, st));
+  const float3 mn = make_float3(min3[0], min3[1], min3[2]);
+  if (N > 0) { k_footprint<false><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, aabb, mn, step, G, padding, s.cnt, nullptr, nullptr); ARAP_KERNEL_CHECK(); }
+  int rc = scan_inclusive(s.cnt, prefix_out, gc, s.sums, st); if (rc) return rc;
+  if (total_host) {
+    int last = 0;
+    ARAP_CUDA_TRY(cudaMemcpyAsync(&last, prefix_out + gc - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ARAP_CUDA_TRY(cudaStreamSynchronize(st));
+    *total_host = last;
+  }
+  return ARAP_OK;
+}
+
+extern "C" int arapk_footprint_fill(long long N, const float* aabb, const float* min3, float step, int G, int padding,
+                                    const int* prefix, int* lists_out, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+  if (scratch_bytes < arapk_grid_scratch_bytes(0, G)) { set_error("footprint_fill: scratch too small"); return ARAP_ERR_INVALID; }
+  const long long gc = (long long)G * G * G;
+  GridScratch s = carve(scratch, G, N);
+  ARAP_CUDA_TRY(cudaMemsetAsync(s.fill, 0, sizeof(int) * gc, st));
+  const float3 mn = make_float3(min3[0], min3[1], min3[2]);
+  if (N > 0) { k_footprint<true><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, aabb, mn, step, G, padding, s.fill, prefix, lists_out); ARAP_KERNEL_CHECK(); }
+  return sort_segments(gc, prefix, lists_out, s.big, st);
+}
+
+extern "C" int arapk_valid_cells(const int* prefix, int G, int* valid_out, int* count_host, void* scratch, size_t scratch_bytes,
+                                 cudaStream_t st) {
+  if (scratch_bytes < arapk_grid_scratch_bytes(0, G)) { set_error("valid_cells: scratch too small"); return ARAP_ERR_INVALID; }
+  const long long gc = (long long)G * G * G;
+  GridScratch s = carve(scratch, G, 0);
+  k_valid_flags<<<(unsigned)((gc + 255) / 256), 256, 0, st>>>(gc, prefix, s.cnt); ARAP_KERNEL_CHECK();
+  int rc = scan_inclusive(s.cnt, s.fill, gc, s.sums, st); if (rc) return rc;
+  int V = 0;
+  ARAP_CUDA_TRY(cudaMemcpyAsync(&V, s.fill + gc - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  ARAP_CUDA_TRY(cudaStreamSynchronize(st));
+  if (count_host) *count_host = V;
+  if (valid_out && V > 0) { k_valid_compact<<<(unsigned)((gc + 255) / 256), 256, 0, st>>>(gc, s.cnt, s.fill, valid_out); ARAP_KERNEL_CHECK(); }
+  return ARAP_OK;
+}
+
+extern "C" int arapk_emit_samples(const int* valid, int V, const float* min3, float step, int G, float* out, cudaStream_t st) {
+  if (V <= 0) return ARAP_OK;
+  const long long T = (long long)V * 64;
+  k_emit_samples<<<(unsigned)((T + 255) / 256), 256, 0, st>>>(V, valid, make_float3(min3[0], min3[1], min3[2]), step, G, out);
+  ARAP_KERNEL_CHECK();
+  return ARAP_OK;
+}
+
+extern "C" int arapk_ada_lpf(const float* samples, const int* valid, int V, float lpf_parameter, float* out, cudaStream_t st) {
+  if (V <= 0) return ARAP_OK;
+  k_ada_lpf<<<(V + 127) / 128, 128, 0, st>>>(V, samples, valid, lpf_parameter, out);
+  ARAP_KERNEL_CHECK();
+  return ARAP_OK;
+}
+
+extern "C" int arapk_grid_eval(const int* valid, int V, const int* prefix, const int* lists, const float* samples, const float* pos,
+                               const float* rot, const float* scale, const float* opacity, const float* shs, const float* ada_lpf,
+                               float* out_feature, float* out_opacity, cudaStream_t st) {
+  if (V <= 0) return ARAP_OK;
+  k_grid_eval<<<V, 64, 0, st>>>(valid, prefix, lists, samples, pos, rot, scale, opacity, shs, ada_lpf, out_feature, out_opacity);
+  ARAP_KERNEL_CHECK();
+  return ARAP_OK;
+}

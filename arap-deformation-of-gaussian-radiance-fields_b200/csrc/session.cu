@@ -1,0 +1,809 @@
+// Session layer of libarapgs: the C++ host side that mirrors the deformation
+// API of the reference's GaussianView (control regions, aims, per-step driver,
+// graph / grid build) on top of the kernel layer (kernels.h).  All state is
+// device resident; the host keeps only graph topology and block bookkeeping.
+//
+// Reference call sites are cited per function (GV = GaussianView.cpp).
+#include <array>
+#include <cstdarg>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/arapgs.h"
+#include "common.cuh"
+#include "kernels.h"
+#include "session.h"
+
+namespace arapgs {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+
+// ------------------------------------------------------------------ small kernels (aims, bookkeeping)
+// UpdateAimPosition (GV:2920-2933): aim += delta once per (active block, node) entry.
+__global__ void k_aim_translate(int M, const int* __restrict__ active_mult, float3 d, float* __restrict__ aim) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  float a0 = aim[3 * i], a1 = aim[3 * i + 1], a2 = aim[3 * i + 2];
+  for (int t = 0; t < active_mult[i]; t++) { a0 += d.x; a1 += d.y; a2 += d.z; }
+  aim[3 * i] = a0; aim[3 * i + 1] = a1; aim[3 * i + 2] = a2;
+}
+
+// centre of the active entries: sequential float sum in block order, / count (GV:2938-2950, 2964-2974)
+__global__ void k_active_center(int n_entries, const int* __restrict__ entries, const float* __restrict__ node_pos,
+                                float* __restrict__ center_out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+  for (int t = 0; t < n_entries; t++) {
+    const int i = entries[t];
+    c0 += node_pos[3 * i]; c1 += node_pos[3 * i + 1]; c2 += node_pos[3 * i + 2];
+  }
+  const float cnt = (float)n_entries;  // Eigen: Vector3f / int -> float division
+  center_out[0] = c0 / cnt; center_out[1] = c1 / cnt; center_out[2] = c2 / cnt;
+}
+
+// PointRotateByAxis (helper.cpp:1077-1100) with host-evaluated cos/sin and unit axis
+struct TwistArgs { float cost, sint, x, y, z; };
+__device__ __forceinline__ void rotate_by_axis(const float* p, const float* c, const TwistArgs& a, float* o) {
+  const float cost = a.cost, sint = a.sint, x = a.x, y = a.y, z = a.z;
+  o[0] = (x * x * (1 - cost) + cost) * p[0] + (x * y * (1 - cost) - z * sint) * p[1] + (x * z * (1 - cost) + y * sint) * p[2];
+  o[1] = (y * x * (1 - cost) + z * sint) * p[0] + (y * y * (1 - cost) + cost) * p[1] + (y * z * (1 - cost) - x * sint) * p[2];
+  o[2] = (z * x * (1 - cost) - y * sint) * p[0] + (z * y * (1 - cost) + x * sint) * p[1] + (z * z * (1 - cost) + cost) * p[2];
+  const float ca = c[0], cb = c[1], cc = c[2];
+  o[0] += (ca * (y * y + z * z) - x * (cb * y + cc * z)) * (1 - cost) + (cb * z - cc * y) * sint;
+  o[1] += (cb * (x * x + z * z) - y * (ca * x + cc * z)) * (1 - cost) + (cc * x - ca * z) * sint;
+  o[2] += (cc * (x * x + y * y) - z * (ca * x + cb * y)) * (1 - cost) + (ca * y - cb * x) * sint;
+}
+__global__ void k_aim_twist(int M, const int* __restrict__ active_mult, const float* __restrict__ center, TwistArgs a,
+                            float* __restrict__ aim) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  float p[3] = {aim[3 * i], aim[3 * i + 1], aim[3 * i + 2]};
+  const float c[3] = {center[0], center[1], center[2]};
+  for (int t = 0; t < active_mult[i]; t++) { float o[3]; rotate_by_axis(p, c, a, o); p[0] = o[0]; p[1] = o[1]; p[2] = o[2]; }
+  aim[3 * i] = p[0]; aim[3 * i + 1] = p[1]; aim[3 * i + 2] = p[2];
+}
+__global__ void k_aim_scale(int M, const int* __restrict__ active_mult, const float* __restrict__ center, float s,
+                            float* __restrict__ aim) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  for (int t = 0; t < active_mult[i]; t++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) aim[3 * i + c] = center[c] + s * (aim[3 * i + c] - center[c]);
+}
+
+// constraint-group targets: per-node mode aim[node]; centre mode mean of the first nsel block nodes' aims
+// (SelectKeyControls, Deform.cpp:34-75: sequential float sum / nsel)
+__global__ void k_group_aims(int n_groups, const int* __restrict__ aim_off, const int* __restrict__ aim_nodes,
+                             const float* __restrict__ aim, float* __restrict__ grp_aim) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+  const int b = aim_off[g], e = aim_off[g + 1];
+  if (e - b == 1) { const int i = aim_nodes[b]; grp_aim[3 * g] = aim[3 * i]; grp_aim[3 * g + 1] = aim[3 * i + 1]; grp_aim[3 * g + 2] = aim[3 * i + 2]; return; }
+  for (int t = b; t < e; t++) { const int i = aim_nodes[t]; c0 += aim[3 * i]; c1 += aim[3 * i + 1]; c2 += aim[3 * i + 2]; }
+  const float n = (float)(e - b);
+  grp_aim[3 * g] = c0 / n; grp_aim[3 * g + 1] = c1 / n; grp_aim[3 * g + 2] = c2 / n;
+}
+
+__global__ void k_gather_points(int M, const int* __restrict__ idx, const float* __restrict__ src, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const long long s = idx[i];
+  dst[3 * i] = src[3 * s]; dst[3 * i + 1] = src[3 * s + 1]; dst[3 * i + 2] = src[3 * s + 2];
+}
+
+// plain rows (Q x k uint32 / double) -> blocked tables
+__global__ void k_rows_to_blocked(long long Q, int k, const uint32_t* __restrict__ idx, const double* __restrict__ w,
+                                  uint16_t* __restrict__ bidx, double* __restrict__ bw) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  const long long base = (q >> 5) * (long long)(k * 32) + (q & 31);
+  for (int j = 0; j < k; j++) { bidx[base + j * 32] = (uint16_t)idx[q * k + j]; bw[base + j * 32] = w[q * k + j]; }
+}
+__global__ void k_blocked_to_rows(long long Q, int k, const uint16_t* __restrict__ bidx, const double* __restrict__ bw,
+                                  uint32_t* __restrict__ idx, double* __restrict__ w) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  const long long base = (q >> 5) * (long long)(k * 32) + (q & 31);
+  for (int j = 0; j < k; j++) { idx[q * k + j] = bidx[base + j * 32]; w[q * k + j] = bw[base + j * 32]; }
+}
+
+// ------------------------------------------------------------------ device buffer helper
+template <typename T>
+struct DBuf {
+  T* p = nullptr; size_t n = 0;
+  ~DBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  int alloc(size_t count) {
+    if (count <= n && p) return ARAP_OK;
+    release();
+    if (count == 0) return ARAP_OK;
+    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+    if (e != cudaSuccess) { set_error(std::string("cudaMalloc(") + std::to_string(count * sizeof(T)) + "): " + cudaGetErrorString(e)); return ARAP_ERR_CUDA; }
+    n = count; return ARAP_OK;
+  }
+  void swap(DBuf& o) { std::swap(p, o.p); std::swap(n, o.n); }
+};
+
+struct RowTable {  // blocked skinning rows of one query family
+  long long rows = 0; int k = 0;
+  DBuf<uint16_t> idx; DBuf<double> w; DBuf<float> wf;
+  size_t entries() const { return (size_t)((rows + 31) / 32) * 32 * k; }
+};
+
+}  // namespace arapgs
+
+using namespace arapgs;
+
+struct arap_ctx {
+  int device = 0; cudaStream_t stream = nullptr; bool own_stream = false;
+  arap_params prm{};
+  // Gaussians
+  long long N = 0;
+  DBuf<float> pos, rot, scale, opacity, shs, scale_backup, ends;
+  DBuf<uint8_t> gs_static;
+  // grid
+  bool grid_ready = false;
+  int G = 0; float aabb[6] = {0}; float step = 0.f; int V = 0; long long S = 0, P = 0;
+  DBuf<int> cell_prefix, gs_init_grid_idx, fp_prefix, lists, valid;
+  DBuf<float> sample_pos, ada_lpf, aim_feature, aim_opacity, cur_feature, cur_opacity, gs_aabb;
+  DBuf<uint8_t> sample_static;
+  DBuf<char> grid_scratch;
+  // mesh points ("simplified_points")
+  int Mp = 0; bool nodes_on_mesh = false; DBuf<float> mesh_pts;
+  // graph
+  bool graph_ready = false;
+  int M = 0, k = 0;
+  std::vector<int> h_anchor, h_nbr, h_anc_idx;
+  DBuf<int> anchor, nbr, in_off, in_src, in_slot, anc_idx, static_in_cnt, active_mult, active_entries;
+  DBuf<double> anc_w;
+  DBuf<float> node_pos, node_next, node_rest, aim, center_tmp;
+  DBuf<uint8_t> node_free, node_static;
+  RowTable end_rows, sample_rows, mesh_rows, node_rows;
+  DBuf<char> knn_ws, knn_slow; std::vector<char> knn_index;
+  // blocks
+  std::vector<std::vector<uint32_t>> blocks; std::vector<int> block_types;
+  int n_active_entries = 0;
+  // constraints (two variants prepared at set_blocks: per-node and centre)
+  struct ConSet { int n_groups = 0; DBuf<int> grp_off, grp_member, aim_off, aim_nodes, cin_off, cin_grp, cin_member, cin_slot; DBuf<float> grp_aim; };
+  ConSet con[2];
+  // solve
+  DBuf<double> rot_d, trans_d, stats_d; DBuf<char> solve_ws; DBuf<char> node_xf; DBuf<float> node_q;
+  double* stats_h = nullptr;  // pinned
+  bool solved = false;
+  // timing
+  bool timing = false; cudaEvent_t ev[7] = {nullptr}; float last_ms[6] = {0};
+};
+
+#define CTX_CHECK(c) do { if (!(c)) { set_error("null ctx"); return ARAP_ERR_INVALID; } cudaSetDevice((c)->device); } while (0)
+#define TRY(x) do { int _rc = (x); if (_rc != ARAP_OK) return _rc; } while (0)
+
+extern "C" const char* arap_last_error(void) { return g_err.c_str(); }
+extern "C" int arap_version(void) { return 100; }
+
+extern "C" int arap_default_params(arap_params* p) {
+  if (!p) return ARAP_ERR_INVALID;
+  p->grid_num = 64; p->padding = 1; p->knn_k = 10; p->node_num = 150; p->high_quality = 0; p->lpf_parameter = 0.2f;
+  p->w_rot = 1.0; p->w_reg = 10.0; p->w_con = 100.0; p->max_gn_iters = 30; p->max_cg_iters = 4000; p->cg_tol = 1e-10;
+  p->skip_static_endpoints = 0;
+  return ARAP_OK;
+}
+
+extern "C" int arap_create(arap_ctx** out, int device, void* stream, const arap_params* params) {
+  if (!out) { set_error("arap_create: null out"); return ARAP_ERR_INVALID; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    set_error(std::string("arap_create: no CUDA device (libarapgs has no CPU fallback): ") + cudaGetErrorString(e));
+    return ARAP_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) { set_error("arap_create: bad device index"); return ARAP_ERR_INVALID; }
+  ARAP_CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  ARAP_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) { set_error("arap_create: libarapgs is built for sm_100a only"); return ARAP_ERR_UNSUPPORTED; }
+  std::unique_ptr<arap_ctx> c(new arap_ctx());
+  c->device = device;
+  if (stream) c->stream = (cudaStream_t)stream;
+  else { ARAP_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  if (params) c->prm = *params; else arap_default_params(&c->prm);
+  ARAP_CUDA_TRY(cudaMallocHost((void**)&c->stats_h, 16 * sizeof(double)));
+  for (auto& ev : c->ev) ARAP_CUDA_TRY(cudaEventCreate(&ev));
+  *out = c.release();
+  return ARAP_OK;
+}
+
+extern "C" int arap_destroy(arap_ctx* ctx) {
+  if (!ctx) return ARAP_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stats_h) cudaFreeHost(ctx->stats_h);
+  for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return ARAP_OK;
+}
+
+extern "C" int arap_set_params(arap_ctx* ctx, const arap_params* p) { CTX_CHECK(ctx); if (!p) return ARAP_ERR_INVALID; ctx->prm = *p; return ARAP_OK; }
+extern "C" int arap_sync(arap_ctx* ctx) { CTX_CHECK(ctx); ARAP_CUDA_TRY(cudaStreamSynchronize(ctx->stream)); return ARAP_OK; }
+extern "C" int arap_enable_timing(arap_ctx* ctx, int on) { CTX_CHECK(ctx); ctx->timing = on != 0; return ARAP_OK; }
+
+template <typename T>
+static int upload(DBuf<T>& d, const T* src, size_t n, bool src_dev, cudaStream_t st) {
+  TRY(d.alloc(n));
+  if (n) ARAP_CUDA_TRY(cudaMemcpyAsync(d.p, src, n * sizeof(T), src_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  return ARAP_OK;
+}
+template <typename T>
+static int download(T* dst, const T* src, size_t n, cudaStream_t st) {
+  if (dst && n) ARAP_CUDA_TRY(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, st));
+  return ARAP_OK;
+}
+
+// ------------------------------------------------------------------ Gaussians
+extern "C" int arap_set_gaussians(arap_ctx* ctx, long long n, const float* pos, const float* rot, const float* scale,
+                                  const float* opacity, const float* shs, int src_is_device) {
+  CTX_CHECK(ctx);
+  if (n <= 0 || !pos || !rot || !scale || !opacity || !shs) { set_error("set_gaussians: bad arguments"); return ARAP_ERR_INVALID; }
+  const bool d = src_is_device != 0; cudaStream_t st = ctx->stream;
+  ctx->N = n;
+  TRY(upload(ctx->pos, pos, (size_t)n * 3, d, st)); TRY(upload(ctx->rot, rot, (size_t)n * 4, d, st));
+  TRY(upload(ctx->scale, scale, (size_t)n * 3, d, st)); TRY(upload(ctx->opacity, opacity, (size_t)n, d, st));
+  TRY(upload(ctx->shs, shs, (size_t)n * 48, d, st));
+  TRY(upload(ctx->scale_backup, scale, (size_t)n * 3, d, st));
+  TRY(ctx->gs_static.alloc((size_t)n));
+  ARAP_CUDA_TRY(cudaMemsetAsync(ctx->gs_static.p, 0, (size_t)n, st));
+  ctx->grid_ready = false; ctx->graph_ready = false; ctx->solved = false;
+  if (!d) ARAP_CUDA_TRY(cudaStreamSynchronize(st));  // host buffers may be freed by the caller
+  return ARAP_OK;
+}
+
+extern "C" int arap_download_gaussians(arap_ctx* ctx, float* pos, float* rot, float* scale, float* opacity, float* shs) {
+  CTX_CHECK(ctx);
+  cudaStream_t st = ctx->stream; const size_t n = (size_t)ctx->N;
+  TRY(download(pos, ctx->pos.p, n * 3, st)); TRY(download(rot, ctx->rot.p, n * 4, st)); TRY(download(scale, ctx->scale.p, n * 3, st));
+  TRY(download(opacity, ctx->opacity.p, n, st)); TRY(download(shs, ctx->shs.p, n * 48, st));
+  ARAP_CUDA_TRY(cudaStreamSynchronize(st));
+  return ARAP_OK;
+}
+
+extern "C" int arap_get_device_view(arap_ctx* ctx, arap_device_view* o) {
+  CTX_CHECK(ctx); if (!o) return ARAP_ERR_INVALID;
+  memset(o, 0, sizeof(*o));
+  o->n_gaussians = ctx->N; o->pos = ctx->pos.p; o->rot = ctx->rot.p; o->scale = ctx->scale.p; o->opacity = ctx->opacity.p; o->shs = ctx->shs.p;
+  o->n_nodes = ctx->M; o->node_pos = ctx->node_pos.p; o->node_rot = ctx->rot_d.p; o->node_trans = ctx->trans_d.p;
+  o->n_samples = ctx->S; o->sample_pos = ctx->sample_pos.p; o->aim_feature = ctx->aim_feature.p; o->aim_opacity = ctx->aim_opacity.p;
+  o->valid_grid = ctx->valid.p; o->grid_gs_prefix_sum = ctx->fp_prefix.p; o->grided_gs_idx = ctx->lists.p;
+  o->gs_init_grid_idx = ctx->gs_init_grid_idx.p; o->ada_lpf_ratio = ctx->ada_lpf.p; o->end_points = ctx->ends.p;
+  return ARAP_OK;
+}
+
+// ------------------------------------------------------------------ grid
+// getOverallAABB (GV:3601-3631): min/max on device, the box arithmetic in host float
+// (Eigen float vectors x double literals evaluate in float).
+static int overall_aabb(arap_ctx* c) {
+  DBuf<float> mm; TRY(mm.alloc(8));
+  TRY(arapk_minmax(c->pos.p, c->N, mm.p, c->stream));
+  float h[6];
+  ARAP_CUDA_TRY(cudaMemcpyAsync(h, mm.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  ARAP_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  const float f11 = (float)1.1, fgrow = (float)(1.0 + (1.0) / 128);
+  for (int i = 0; i < 3; i++) {
+    volatile float mean = (h[3 + i] + h[i]) / 2.0f;
+    volatile float a = (h[i] - mean) * f11;
+    volatile float nmin = a + mean;
+    volatile float b = (h[3 + i] - mean) * f11;
+    volatile float b2 = b + mean;
+    volatile float b3 = b2 - nmin;
+    volatile float b4 = b3 * fgrow;
+    volatile float nmax = b4 + nmin;
+    c->aabb[i] = std::min((float)nmin, -0.75f);
+    c->aabb[3 + i] = std::max((float)nmax, 0.75f);
+  }
+  volatile float xs = (c->aabb[3] - c->aabb[0]) / c->G, ys = (c->aabb[4] - c->aabb[1]) / c->G, zs = (c->aabb[5] - c->aabb[2]) / c->G;
+  c->step = std::max(std::max((float)xs, (float)ys), (float)zs);
+  return ARAP_OK;
+}
+
+static int build_lists(arap_ctx* c) {  // boxes -> count -> fill (GV:3961-4100 / 3634-3743)
+  cudaStream_t st = c->stream;
+  TRY(c->gs_aabb.alloc((size_t)c->N * 6));
+  TRY(arapk_gs_aabbs(c->N, c->pos.p, c->rot.p, c->scale.p, c->opacity.p, c->gs_aabb.p, nullptr, nullptr, st));
+  const size_t gc = (size_t)c->G * c->G * c->G;
+  TRY(c->fp_prefix.alloc(gc));
+  long long P = 0;
+  TRY(arapk_footprint_count(c->N, c->gs_aabb.p, c->aabb, c->step, c->G, c->prm.padding, c->fp_prefix.p, &P, c->grid_scratch.p, c->grid_scratch.n, st));
+  c->P = P;
+  TRY(c->lists.alloc((size_t)std::max<long long>(P, 1)));
+  TRY(arapk_footprint_fill(c->N, c->gs_aabb.p, c->aabb, c->step, c->G, c->prm.padding, c->fp_prefix.p, c->lists.p, c->grid_scratch.p, c->grid_scratch.n, st));
+  return ARAP_OK;
+}
+
+extern "C" int arap_grid_build(arap_ctx* ctx) {
+  CTX_CHECK(ctx);
+  if (ctx->N <= 0) { set_error("grid_build: no Gaussians"); return ARAP_ERR_STATE; }
+  cudaStream_t st = ctx->stream;
+  ctx->G = ctx->prm.grid_num;
+  if (ctx->G < 1 || ctx->G > 256) { set_error("grid_build: grid_num out of range"); return ARAP_ERR_INVALID; }
+  const size_t gc = (size_t)ctx->G * ctx->G * ctx->G;
+  TRY(overall_aabb(ctx));
+  TRY(ctx->grid_scratch.alloc(arapk_grid_scratch_bytes(ctx->N, ctx->G)));
+  TRY(ctx->cell_prefix.alloc(gc)); TRY(ctx->gs_init_grid_idx.alloc((size_t)ctx->N));
+  // cell assignment + stable re-order (GV:3896-3953)
+  DBuf<int> new_idx; TRY(new_idx.alloc((size_t)ctx->N));
+  TRY(arapk_cell_assign(ctx->pos.p, ctx->N, ctx->aabb, ctx->step, ctx->G, ctx->gs_init_grid_idx.p, ctx->cell_prefix.p, new_idx.p,
+                        ctx->grid_scratch.p, ctx->grid_scratch.n, st));
+  {
+    DBuf<float> p2, r2, s2, o2, h2;
+    TRY(p2.alloc(ctx->pos.n)); TRY(r2.alloc(ctx->rot.n)); TRY(s2.alloc(ctx->scale.n)); TRY(o2.alloc(ctx->opacity.n)); TRY(h2.alloc(ctx->shs.n));
+    TRY(arapk_permute_gaussians(ctx->N, new_idx.p, ctx->pos.p, ctx->rot.p, ctx->scale.p, ctx->opacity.p, ctx->shs.p, p2.p, r2.p, s2.p, o2.p, h2.p, st));
+    ARAP_CUDA_TRY(cudaStreamSynchronize(st));
+    ctx->pos.swap(p2); ctx->rot.swap(r2); ctx->scale.swap(s2); ctx->opacity.swap(o2); ctx->shs.swap(h2);
+  }
+  ARAP_CUDA_TRY(cudaMemcpyAsync(ctx->scale_backup.p, ctx->scale.p, (size_t)ctx->N * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // gs_init_grid_idx in the new order (GV:4136-4145)
+  TRY(arapk_cell_assign(ctx->pos.p, ctx->N, ctx->aabb, ctx->step, ctx->G, ctx->gs_init_grid_idx.p, ctx->cell_prefix.p, nullptr,
+                        ctx->grid_scratch.p, ctx->grid_scratch.n, st));
+  TRY(build_lists(ctx));
+  // valid cells = non-empty padded lists (GV:4040-4053); 4^3 samples each (GV:4111-4133)
+  TRY(ctx->valid.alloc(gc));
+  int V = 0;
+  TRY(arapk_valid_cells(ctx->fp_prefix.p, ctx->G, ctx->valid.p, &V, ctx->grid_scratch.p, ctx->grid_scratch.n, st));
+  ctx->V = V; ctx->S = (long long)V * 64;
+  TRY(ctx->sample_pos.alloc((size_t)std::max<long long>(ctx->S, 1) * 3));
+  TRY(arapk_emit_samples(ctx->valid.p, V, ctx->aabb, ctx->step, ctx->G, ctx->sample_pos.p, st));
+  TRY(ctx->ada_lpf.alloc(gc * 9));
+  ARAP_CUDA_TRY(cudaMemsetAsync(ctx->ada_lpf.p, 0, gc * 9 * sizeof(float), st));
+  TRY(arapk_ada_lpf(ctx->sample_pos.p, ctx->valid.p, V, ctx->prm.lpf_parameter, ctx->ada_lpf.p, st));
+  TRY(ctx->sample_static.alloc((size_t)std::max<long long>(ctx->S, 1)));
+  ARAP_CUDA_TRY(cudaMemsetAsync(ctx->sample_static.p, 0, (size_t)std::max<long long>(ctx->S, 1), st));
+  // endpoints (GetEndPoints, GV:4643-4668)
+  TRY(ctx->ends.alloc((size_t)ctx->N * 18));
+  TRY(arapk_end_points(ctx->N, ctx->pos.p, ctx->rot.p, ctx->scale.p, ctx->ends.p, st));
+  ctx->aim_feature.release(); ctx->aim_opacity.release(); ctx->cur_feature.release(); ctx->cur_opacity.release();
+  ctx->grid_ready = true; ctx->graph_ready = false;
+  return ARAP_OK;
+}
+
+extern "C" int arap_grid_update_lists(arap_ctx* ctx) {
+  CTX_CHECK(ctx);
+  if (!ctx->grid_ready) { set_error("grid_update_lists: grid not built"); return ARAP_ERR_STATE; }
+  TRY(overall_aabb(ctx));  // UpdateContainingRelationship recomputes the scene box and step (GV:3636-3644)
+  return build_lists(ctx);
+}
+
+extern "C" int arap_grid_eval(arap_ctx* ctx, int which) {
+  CTX_CHECK(ctx);
+  if (!ctx->grid_ready) { set_error("grid_eval: grid not built"); return ARAP_ERR_STATE; }
+  DBuf<float>& f = which == 0 ? ctx->aim_feature : ctx->cur_feature;
+  DBuf<float>& o = which == 0 ? ctx->aim_opacity : ctx->cur_opacity;
+  TRY(f.alloc((size_t)std::max<long long>(ctx->S, 1) * 48)); TRY(o.alloc((size_t)std::max<long long>(ctx->S, 1)));
+  return arapk_grid_eval(ctx->valid.p, ctx->V, ctx->fp_prefix.p, ctx->lists.p, ctx->sample_pos.p, ctx->pos.p, ctx->rot.p, ctx->scale.p,
+                         ctx->opacity.p, ctx->shs.p, ctx->ada_lpf.p, f.p, o.p, ctx->stream);
+}
+
+extern "C" int arap_grid_info_get(arap_ctx* ctx, arap_grid_info* o) {
+  CTX_CHECK(ctx); if (!o) return ARAP_ERR_INVALID;
+  o->grid_num = ctx->G; o->padding = ctx->prm.padding; o->valid_cells = ctx->V; o->samples = ctx->S; o->pairs = ctx->P;
+  for (int i = 0; i < 3; i++) { o->aabb_min[i] = ctx->aabb[i]; o->aabb_max[i] = ctx->aabb[3 + i]; }
+  o->grid_step = ctx->step;
+  return ARAP_OK;
+}
+
+extern "C" int arap_download_grid(arap_ctx* ctx, int* valid, int* prefix, int* lists, float* sample_pos, int* gs_init) {
+  CTX_CHECK(ctx); cudaStream_t st = ctx->stream;
+  const size_t gc = (size_t)ctx->G * ctx->G * ctx->G;
+  TRY(download(valid, ctx->valid.p, (size_t)ctx->V, st)); TRY(download(prefix, ctx->fp_prefix.p, gc, st));
+  TRY(download(lists, ctx->lists.p, (size_t)ctx->P, st)); TRY(download(sample_pos, ctx->sample_pos.p, (size_t)ctx->S * 3, st));
+  TRY(download(gs_init, ctx->gs_init_grid_idx.p, (size_t)ctx->N, st));
+  ARAP_CUDA_TRY(cudaStreamSynchronize(st));
+  return ARAP_OK;
+}
+extern "C" int arap_download_features(arap_ctx* ctx, int which, float* feature, float* opacity) {
+  CTX_CHECK(ctx); cudaStream_t st = ctx->stream;
+  DBuf<float>& f = which == 0 ? ctx->aim_feature : ctx->cur_feature;
+  DBuf<float>& o = which == 0 ? ctx->aim_opacity : ctx->cur_opacity;
+  if (!f.p) { set_error("download_features: not evaluated"); return ARAP_ERR_STATE; }
+  TRY(download(feature, f.p, (size_t)ctx->S * 48, st)); TRY(download(opacity, o.p, (size_t)ctx->S, st));
+  ARAP_CUDA_TRY(cudaStreamSynchronize(st));
+  return ARAP_OK;
+}
+extern "C" int arap_download_samples(arap_ctx* ctx, float* sample_pos, float* aim_feature) {
+  CTX_CHECK(ctx); cudaStream_t st = ctx->stream;
+  TRY(download(sample_pos, ctx->sample_pos.p, (size_t)ctx->S * 3, st));
+  if (aim_feature) { if (!ctx->aim_feature.p) { set_error("download_samples: aim features not evaluated"); return ARAP_ERR_STATE; } TRY(download(aim_feature, ctx->aim_feature.p, (size_t)ctx->S * 48, st)); }
+  ARAP_CUDA_TRY(cudaStreamSynchronize(st));
+  return ARAP_OK;
+}
+
+// ------------------------------------------------------------------ graph
+static int knn_family(arap_ctx* c, const float* queries, long long Q, int k, RowTable& t, bool want_float) {
+  t.rows = Q; t.k = k;
+  TRY(t.idx.alloc(t.entries())); TRY(t.w.alloc(t.entries()));
+  if (want_float) TRY(t.wf.alloc(t.entries()));
+  if (Q <= 0) return ARAP_OK;
+  // queries are processed in chunks of whole 32-row blocks so the tie scratch stays bounded
+  const long long CH = 1LL << 23;
+  TRY(c->knn_slow.alloc((size_t)std::min(Q, CH) * 12 + 4096));
+  for (long long q0 = 0; q0 < Q; q0 += CH) {
+    const long long n = std::min(CH, Q - q0);
+    const size_t eo = (size_t)(q0 / 32) * 32 * k;
+    int nslow = 0;
+    TRY(arapk_knn_query(c->knn_index.data(), queries + 3 * q0, n, k, nullptr, nullptr, t.idx.p + eo, t.w.p + eo,
+                        want_float ? t.wf.p + eo : nullptr, nullptr, c->knn_slow.p, c->knn_slow.n, &nslow, c->stream));
+  }
+  return ARAP_OK;
+}
+
+static int finish_graph(arap_ctx* c, int k) {
+  cudaStream_t st = c->stream;
+  const int M = c->M;
+  if (M < k + 1) { set_error("graph_build: need at least k+1 nodes"); return ARAP_ERR_INVALID; }
+  if (M > 65536) { set_error("graph_build: more than 65536 nodes not supported by the uint16 skinning tables"); return ARAP_ERR_UNSUPPORTED; }
+  c->k = k;
+  // nodes = candidate points at the anchors; back_up_nodes = rest copy (DH:54-81)
+  TRY(upload(c->anchor, c->h_anchor.data(), (size_t)M, false, st));
+  TRY(c->node_pos.alloc((size_t)M * 3)); TRY(c->node_next.alloc((size_t)M * 3)); TRY(c->node_rest.alloc((size_t)M * 3)); TRY(c->aim.alloc((size_t)M * 3));
+  const float* cand = c->nodes_on_mesh ? c->mesh_pts.p : c->pos.p;
+  k_gather_points<<<(M + 127) / 128, 128, 0, st>>>(M, c->anchor.p, cand, c->node_pos.p);
+  ARAP_KERNEL_CHECK();
+  ARAP_CUDA_TRY(cudaMemcpyAsync(c->node_rest.p, c->node_pos.p, (size_t)M * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  ARAP_CUDA_TRY(cudaMemcpyAsync(c->aim.p, c->node_pos.p, (size_t)M * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));  // ReloadAimPositions
+  // kNN index over the rest positions (findNearestNodes always measures against back_up_nodes, DH:155-165)
+  TRY(c->knn_ws.alloc(arapk_knn_workspace_bytes(M)));
+  c->knn_index.resize(arapk_knn_index_struct_bytes());
+  TRY(arapk_knn_build(c->node_rest.p, M, c->knn_ws.p, c->knn_ws.n, c->knn_index.data(), st));
+  // node query: edges = idx[1..k] of the k+1 result (setupEdges, DH:84-95); anchor rows = cand_vertices[Vertex_index]
+  {
+    DBuf<uint32_t> idx_kq, idx_p; DBuf<double> w_p;
+    TRY(idx_kq.alloc((size_t)M * (k + 1))); TRY(idx_p.alloc((size_t)M * k)); TRY(w_p.alloc((size_t)M * k));
+    TRY(c->knn_slow.alloc((size_t)std::max(M, 1 << 16) * 12 + 4096));
+    int nslow = 0;
+    TRY(arapk_knn_query(c->knn_index.data(), c->node_rest.p, M, k, idx_p.p, w_p.p, nullptr, nullptr, nullptr, idx_kq.p, c->knn_slow.p, c->knn_slow.n, &nslow, st));
+    std::vector<uint32_t> h_kq((size_t)M * (k + 1)), h_idx((size_t)M * k);
+    ARAP_CUDA_TRY(cudaMemcpyAsync(h_kq.data(), idx_kq.p, h_kq.size() * 4, cudaMemcpyDeviceToHost, st));
+    ARAP_CUDA_TRY(cudaMemcpyAsync(h_idx.data(), idx_p.p, h_idx.size() * 4, cudaMemcpyDeviceToHost, st));
+    ARAP_CUDA_TRY(cudaStreamSynchronize(st));
+    c->h_nbr.assign((size_t)M * k, 0); c->h_anc_idx.assign((size_t)M * k, 0);
+    for (int i = 0; i < M; i++) for (int j = 0; j < k; j++) {
+      c->h_nbr[(size_t)i * k + j] = (int)h_kq[(size_t)i * (k + 1) + j + 1];
+      c->h_anc_idx[(size_t)i * k + j] = (int)h_idx[(size_t)i * k + j];
+    }
+    TRY(upload(c->nbr, c->h_nbr.data(), c->h_nbr.size(), false, st));
+    TRY(upload(c->anc_idx, c->h_anc_idx.data(), c->h_anc_idx.size(), false, st));
+    TRY(c->anc_w.alloc((size_t)M * k));
+    ARAP_CUDA_TRY(cudaMemcpyAsync(c->anc_w.p, w_p.p, (size_t)M * k * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    // node rows in blocked layout (node positions are skinned with their anchor's row, GV:3041-3046)
+    c->node_rows.rows = M; c->node_rows.k = k;
+    TRY(c->node_rows.idx.alloc(c->node_rows.entries())); TRY(c->node_rows.w.alloc(c->node_rows.entries()));
+    k_rows_to_blocked<<<(M + 127) / 128, 128, 0, st>>>(M, k, idx_p.p, w_p.p, c->node_rows.idx.p, c->node_rows.w.p);
+    ARAP_KERNEL_CHECK();
+    // in-edge CSR
+    std::vector<int> off(M + 1, 0), src((size_t)M * k), slot((size_t)M * k);
+    for (size_t e = 0; e < c->h_nbr.size(); e++) off[c->h_nbr[e] + 1]++;
+    for (int i = 0; i < M; i++) off[i + 1] += off[i];
+    std::vector<int> fill(off.begin(), off.end() - 1);
+    for (int i = 0; i < M; i++) for (int s = 0; s < k; s++) { const int q = c->h_nbr[(size_t)i * k + s]; src[fill[q]] = i; slot[fill[q]] = s; fill[q]++; }
+    TRY(upload(c->in_off, off.data(), off.size(), false, st)); TRY(upload(c->in_src, src.data(), src.size(), false, st));
+    TRY(upload(c->in_slot, slot.data(), slot.size(), false, st));
+    ARAP_CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  // skinning rows per query family (setupWeightsforEnds / forSamples / forMesh, GV:2833-2918)
+  TRY(knn_family(c, c->ends.p, c->N * 6, k, c->end_rows, false));
+  TRY(knn_family(c, c->sample_pos.p, c->S, k, c->sample_rows, true));
+  TRY(knn_family(c, c->mesh_pts.p, c->Mp, k, c->mesh_rows, false));
+  // solve outputs
+  TRY(c->rot_d.alloc((size_t)M * 9)); TRY(c->trans_d.alloc((size_t)M * 3)); TRY(c->stats_d.alloc(16));
+  TRY(c->node_xf.alloc((size_t)M * 112)); TRY(c->node_q.alloc((size_t)M * 4));
+  TRY(c->node_free.alloc((size_t)M)); TRY(c->node_static.alloc((size_t)M)); TRY(c->static_in_cnt.alloc((size_t)M)); TRY(c->active_mult.alloc((size_t)M));
+  TRY(c->center_tmp.alloc(4));
+  c->graph_ready = true; c->solved = false;
+  c->blocks.clear(); c->block_types.clear();
+  return arap_set_blocks(c, 0, nullptr, nullptr, nullptr);
+}
+
+extern "C" int arap_set_mesh_points(arap_ctx* ctx, const float* pts, int n, int nodes_on_mesh) {
+  CTX_CHECK(ctx);
+  if (n < 0 || (n > 0 && !pts)) { set_error("set_mesh_points: bad arguments"); return ARAP_ERR_INVALID; }
+  ctx->Mp = n; ctx->nodes_on_mesh = nodes_on_mesh != 0 && n > 0;
+  TRY(upload(ctx->mesh_pts, pts, (size_t)n * 3, false, ctx->stream));
+  ARAP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->graph_ready = false;
+  return ARAP_OK;
+}
+
+extern "C" int arap_graph_build_fps(arap_ctx* ctx, int node_num, int k) {
+  CTX_CHECK(ctx);
+  if (!ctx->grid_ready) { set_error("graph_build: call arap_grid_build first (the graph indexes the re-ordered Gaussians)"); return ARAP_ERR_STATE; }
+  if (k < 1 || k > ARAP_KNN_MAX) { set_error("graph_build: k must be in [1,12]"); return ARAP_ERR_INVALID; }
+  cudaStream_t st = ctx->stream;
+  const float* cand = ctx->nodes_on_mesh ? ctx->mesh_pts.p : ctx->pos.p;
+  const long long nc = ctx->nodes_on_mesh ? ctx->Mp : ctx->N;
+  if (ctx->nodes_on_mesh) node_num = ctx->Mp;  // LoadMeshForGraph: node_num = simplified_points.size() (GV:4952-4954)
+  const int m = (int)std::min<long long>(node_num, nc);
+  DBuf<int> out; TRY(out.alloc((size_t)std::max(m, 1)));
+  DBuf<char> scratch; TRY(scratch.alloc((size_t)nc * 4 + 65536 + 512));
+  int cnt = 0;
+  TRY(arapk_fps(cand, nc, node_num, out.p, scratch.p, scratch.n, &cnt, st));
+  ctx->h_anchor.resize(cnt);
+  ARAP_CUDA_TRY(cudaMemcpyAsync(ctx->h_anchor.data(), out.p, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, st));
+  ARAP_CUDA_TRY(cudaStreamSynchronize(st));
+  ctx->M = cnt;
+  return finish_graph(ctx, k);
+}
+
+extern "C" int arap_graph_build_anchors(arap_ctx* ctx, const int* anchor_idx, int m, int k) {
+  CTX_CHECK(ctx);
+  if (!ctx->grid_ready) { set_error("graph_build: call arap_grid_build first"); return ARAP_ERR_STATE; }
+  if (k < 1 || k > ARAP_KNN_MAX || m < 1 || !anchor_idx) { set_error("graph_build_anchors: bad arguments"); return ARAP_ERR_INVALID; }
+  const long long nc = ctx->nodes_on_mesh ? ctx->Mp : ctx->N;
+  for (int i = 0; i < m; i++) if (anchor_idx[i] < 0 || anchor_idx[i] >= nc) { set_error("graph_build_anchors: anchor index out of range"); return ARAP_ERR_INVALID; }
+  ctx->h_anchor.assign(anchor_idx, anchor_idx + m);
+  ctx->M = m;
+  return finish_graph(ctx, k);
+}
+
+extern "C" int arap_knn_weights(arap_ctx* ctx, const float* queries_dev, long long q, int k, uint32_t* idx_dev, double* w_dev) {
+  CTX_CHECK(ctx);
+  if (!ctx->graph_ready) { set_error("knn_weights: graph not built"); return ARAP_ERR_STATE; }
+  TRY(ctx->knn_slow.alloc((size_t)q * 12 + 4096));
+  int nslow = 0;
+  return arapk_knn_query(ctx->knn_index.data(), queries_dev, q, k, idx_dev, w_dev, nullptr, nullptr, nullptr, nullptr, ctx->knn_slow.p, ctx->knn_slow.n, &nslow, ctx->stream);
+}
+
+extern "C" int arap_download_graph(arap_ctx* ctx, int* anchor, float* node_pos, int* nbr) {
+  CTX_CHECK(ctx);
+  if (!ctx->graph_ready) { set_error("download_graph: graph not built"); return ARAP_ERR_STATE; }
+  if (anchor) memcpy(anchor, ctx->h_anchor.data(), sizeof(int) * ctx->M);
+  if (nbr) memcpy(nbr, ctx->h_nbr.data(), sizeof(int) * ctx->h_nbr.size());
+  TRY(download(node_pos, ctx->node_pos.p, (size_t)ctx->M * 3, ctx->stream));
+  ARAP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return ARAP_OK;
+}
+
+extern "C" int arap_download_rows(arap_ctx* ctx, int family, uint32_t* idx, double* w) {
+  CTX_CHECK(ctx);
+  if (!ctx->graph_ready) { set_error("download_rows: graph not built"); return ARAP_ERR_STATE; }
+  RowTable* t = family == 0 ? &ctx->end_rows : family == 1 ? &ctx->sample_rows : family == 2 ? &ctx->mesh_rows : &ctx->node_rows;
+  if (t->rows <= 0) return ARAP_OK;
+  DBuf<uint32_t> di; DBuf<double> dw;
+  TRY(di.alloc((size_t)t->rows * t->k)); TRY(dw.alloc((size_t)t->rows * t->k));
+  k_blocked_to_rows<<<(unsigned)((t->rows + 127) / 128), 128, 0, ctx->stream>>>(t->rows, t->k, t->idx.p, t->w.p, di.p, dw.p);
+  ARAP_KERNEL_CHECK();
+  TRY(download(idx, di.p, di.n, ctx->stream)); TRY(download(w, dw.p, dw.n, ctx->stream));
+  ARAP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return ARAP_OK;
+}
+
+// ------------------------------------------------------------------ blocks
+// UpdateIndicies + CheckStaticSamples (GV:1996-2087) and the index bookkeeping the Deform ctor /
+// SelectKeyControls do per step (DH:414-455, DC:6-75) — all value-free, so done once per block change.
+static int build_conset(arap_ctx* c, arap_ctx::ConSet& cs, bool on_center) {
+  const int M = c->M, k = c->k;
+  std::vector<int> grp_off{0}, grp_member, aim_off{0}, aim_nodes;
+  for (size_t b = 0; b < c->blocks.size(); b++) {
+    if (c->block_types[b] == -1) continue;
+    const auto& blk = c->blocks[b];
+    if (on_center) {
+      const int nsel = (int)std::min<size_t>(20, blk.size());  // CONTROL_NODE_NUM (DC:4); first nsel nodes (DC:57-61)
+      std::set<uint32_t> sel(blk.begin(), blk.begin() + nsel);
+      for (uint32_t v : sel) grp_member.push_back((int)v);
+      grp_off.push_back((int)grp_member.size());
+      for (int t = 0; t < nsel; t++) aim_nodes.push_back((int)blk[t]);
+      aim_off.push_back((int)aim_nodes.size());
+    } else {
+      for (uint32_t v : blk) {
+        grp_member.push_back((int)v); grp_off.push_back((int)grp_member.size());
+        aim_nodes.push_back((int)v); aim_off.push_back((int)aim_nodes.size());
+      }
+    }
+  }
+  cs.n_groups = (int)grp_off.size() - 1;
+  // entries touching each node, sorted by group
+  std::vector<std::vector<std::array<int, 3>>> per(M);
+  for (int g = 0; g < cs.n_groups; g++)
+    for (int t = grp_off[g]; t < grp_off[g + 1]; t++) {
+      const int m = grp_member[t];
+      for (int s = 0; s < k; s++) per[c->h_anc_idx[(size_t)m * k + s]].push_back({g, m, s});
+    }
+  std::vector<int> cin_off(M + 1, 0), cg, cm, csl;
+  for (int i = 0; i < M; i++) {
+    for (auto& e : per[i]) { cg.push_back(e[0]); cm.push_back(e[1]); csl.push_back(e[2]); }
+    cin_off[i + 1] = (int)cg.size();
+  }
+  auto up = [&](DBuf<int>& d, std::vector<int>& v) { if (v.empty()) v.push_back(0); return upload(d, v.data(), v.size(), false, c->stream); };
+  TRY(up(cs.grp_off, grp_off)); TRY(up(cs.grp_member, grp_member)); TRY(up(cs.aim_off, aim_off)); TRY(up(cs.aim_nodes, aim_nodes));
+  TRY(up(cs.cin_off, cin_off)); TRY(up(cs.cin_grp, cg)); TRY(up(cs.cin_member, cm)); TRY(up(cs.cin_slot, csl));
+  TRY(cs.grp_aim.alloc((size_t)std::max(cs.n_groups, 1) * 3));
+  ARAP_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return ARAP_OK;
+}
+
+extern "C" int arap_set_blocks(arap_ctx* ctx, int n_blocks, const int* block_off, const uint32_t* block_nodes, const int* block_types) {
+  CTX_CHECK(ctx);
+  if (!ctx->graph_ready) { set_error("set_blocks: graph not built"); return ARAP_ERR_STATE; }
+  const int M = ctx->M, k = ctx->k; cudaStream_t st = ctx->stream;
+  ctx->blocks.clear(); ctx->block_types.clear();
+  for (int b = 0; b < n_blocks; b++) {
+    std::vector<uint32_t> v(block_nodes + block_off[b], block_nodes + block_off[b + 1]);
+    for (uint32_t x : v) if ((int)x >= M) { set_error("set_blocks: node index out of range"); return ARAP_ERR_INVALID; }
+    ctx->blocks.push_back(std::move(v)); ctx->block_types.push_back(block_types[b]);
+  }
+  std::vector<uint8_t> is_static(M, 0), is_free(M, 1);
+  std::vector<int> mult(M, 0), entries;
+  for (size_t b = 0; b < ctx->blocks.size(); b++) {
+    if (ctx->block_types[b] < 0) for (uint32_t v : ctx->blocks[b]) { is_static[v] = 1; is_free[v] = 0; }
+    if (ctx->block_types[b] == 1) for (uint32_t v : ctx->blocks[b]) { mult[v]++; entries.push_back((int)v); }
+  }
+  std::vector<int> sic(M, 0);
+  for (int i = 0; i < M; i++) if (is_static[i]) for (int s = 0; s < k; s++) sic[ctx->h_nbr[(size_t)i * k + s]]++;
+  ctx->n_active_entries = (int)entries.size();
+  if (entries.empty()) entries.push_back(0);
+  TRY(upload(ctx->node_static, is_static.data(), (size_t)M, false, st)); TRY(upload(ctx->node_free, is_free.data(), (size_t)M, false, st));
+  TRY(upload(ctx->static_in_cnt, sic.data(), (size_t)M, false, st)); TRY(upload(ctx->active_mult, mult.data(), (size_t)M, false, st));
+  TRY(upload(ctx->active_entries, entries.data(), entries.size(), false, st));
+  ARAP_CUDA_TRY(cudaStreamSynchronize(st));
+  TRY(build_conset(ctx, ctx->con[0], false));
+  TRY(build_conset(ctx, ctx->con[1], true));
+  // static flags (GV:2024-2059); without any block the reference leaves static_gaussians all true but never
+  // deforms — flags are only consulted by the apply, so "no blocks" keeps everything non-static here.
+  if (ctx->S > 0) TRY(arapk_static_flags(ctx->S, 1, k, ctx->sample_rows.idx.p, ctx->node_static.p, ctx->sample_static.p, st));
+  TRY(arapk_static_flags(ctx->N, 6, k, ctx->end_rows.idx.p, ctx->node_static.p, ctx->gs_static.p, st));
+  return ARAP_OK;
+}
+
+extern "C" int arap_download_static_flags(arap_ctx* ctx, uint8_t* gaussians, uint8_t* samples) {
+  CTX_CHECK(ctx);
+  TRY(download(gaussians, ctx->gs_static.p, (size_t)ctx->N, ctx->stream)); TRY(download(samples, ctx->sample_static.p, (size_t)ctx->S, ctx->stream));
+  ARAP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return ARAP_OK;
+}
+
+// ------------------------------------------------------------------ aims
+#define GRAPH_CHECK(c) do { CTX_CHECK(c); if (!(c)->graph_ready) { set_error("graph not built"); return ARAP_ERR_STATE; } } while (0)
+
+extern "C" int arap_aim_translate(arap_ctx* ctx, const float delta[3]) {
+  GRAPH_CHECK(ctx);
+  k_aim_translate<<<(ctx->M + 127) / 128, 128, 0, ctx->stream>>>(ctx->M, ctx->active_mult.p, make_float3(delta[0], delta[1], delta[2]), ctx->aim.p);
+  ARAP_KERNEL_CHECK();
+  return ARAP_OK;
+}
+extern "C" int arap_aim_twist(arap_ctx* ctx, const float axis[4], int y) {
+  GRAPH_CHECK(ctx);
+  if (ctx->n_active_entries == 0) return ARAP_OK;
+  const float radian = 0.005f * (float)y;  // GV:2936
+  TwistArgs a;
+  a.cost = std::cos(radian); a.sint = std::sin(radian);
+  const float norm = std::sqrt(axis[0] * axis[0] + axis[1] * axis[1] + axis[2] * axis[2]);
+  a.x = axis[0] / norm; a.y = axis[1] / norm; a.z = axis[2] / norm;
+  k_active_center<<<1, 32, 0, ctx->stream>>>(ctx->n_active_entries, ctx->active_entries.p, ctx->node_pos.p, ctx->center_tmp.p);
+  k_aim_twist<<<(ctx->M + 127) / 128, 128, 0, ctx->stream>>>(ctx->M, ctx->active_mult.p, ctx->center_tmp.p, a, ctx->aim.p);
+  ARAP_KERNEL_CHECK();
+  return ARAP_OK;
+}
+extern "C" int arap_aim_scale(arap_ctx* ctx, int y) {
+  GRAPH_CHECK(ctx);
+  if (ctx->n_active_entries == 0) return ARAP_OK;
+  const float s = 0.002f * (float)y + 1.0f;  // GV:2962
+  k_active_center<<<1, 32, 0, ctx->stream>>>(ctx->n_active_entries, ctx->active_entries.p, ctx->node_pos.p, ctx->center_tmp.p);
+  k_aim_scale<<<(ctx->M + 127) / 128, 128, 0, ctx->stream>>>(ctx->M, ctx->active_mult.p, ctx->center_tmp.p, s, ctx->aim.p);
+  ARAP_KERNEL_CHECK();
+  return ARAP_OK;
+}
+extern "C" int arap_aim_set(arap_ctx* ctx, const float* aim) {
+  GRAPH_CHECK(ctx);
+  ARAP_CUDA_TRY(cudaMemcpyAsync(ctx->aim.p, aim, (size_t)ctx->M * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  return ARAP_OK;
+}
+extern "C" int arap_aim_get(arap_ctx* ctx, float* aim) {
+  GRAPH_CHECK(ctx);
+  TRY(download(aim, ctx->aim.p, (size_t)ctx->M * 3, ctx->stream));
+  ARAP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return ARAP_OK;
+}
+extern "C" int arap_aim_reload(arap_ctx* ctx) {
+  GRAPH_CHECK(ctx);
+  ARAP_CUDA_TRY(cudaMemcpyAsync(ctx->aim.p, ctx->node_pos.p, (size_t)ctx->M * 3 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  return ARAP_OK;
+}
+
+// ------------------------------------------------------------------ solve + apply
+extern "C" int arap_solve(arap_ctx* ctx, int on_center) {
+  GRAPH_CHECK(ctx);
+  cudaStream_t st = ctx->stream;
+  arap_ctx::ConSet& cs = ctx->con[on_center ? 1 : 0];
+  if (cs.n_groups > 0) {
+    k_group_aims<<<(cs.n_groups + 127) / 128, 128, 0, st>>>(cs.n_groups, cs.aim_off.p, cs.aim_nodes.p, ctx->aim.p, cs.grp_aim.p);
+    ARAP_KERNEL_CHECK();
+  }
+  ArapSolveGraph G;
+  G.M = ctx->M; G.k = ctx->k; G.n_groups = cs.n_groups;
+  G.node_pos = ctx->node_pos.p; G.nbr = ctx->nbr.p; G.in_off = ctx->in_off.p; G.in_src = ctx->in_src.p; G.in_slot = ctx->in_slot.p;
+  G.anc_idx = ctx->anc_idx.p; G.anc_w = ctx->anc_w.p; G.node_free = ctx->node_free.p; G.static_in_cnt = ctx->static_in_cnt.p;
+  G.grp_off = cs.grp_off.p; G.grp_member = cs.grp_member.p; G.grp_aim = cs.grp_aim.p;
+  G.cin_off = cs.cin_off.p; G.cin_grp = cs.cin_grp.p; G.cin_member = cs.cin_member.p; G.cin_slot = cs.cin_slot.p;
+  ArapSolveParams P{ctx->prm.w_rot, ctx->prm.w_reg, ctx->prm.w_con, ctx->prm.max_gn_iters, ctx->prm.max_cg_iters, ctx->prm.cg_tol};
+  TRY(ctx->solve_ws.alloc(arapk_solve_workspace_bytes(G.M, G.k, G.n_groups)));
+  TRY(arapk_solve(&G, &P, ctx->solve_ws.p, ctx->solve_ws.n, ctx->rot_d.p, ctx->trans_d.p, ctx->stats_d.p, st));
+  ctx->solved = true;
+  return ARAP_OK;
+}
+
+extern "C" int arap_solve_stats_get(arap_ctx* ctx, arap_solve_stats* o) {
+  GRAPH_CHECK(ctx); if (!o) return ARAP_ERR_INVALID;
+  ARAP_CUDA_TRY(cudaMemcpyAsync(ctx->stats_h, ctx->stats_d.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  ARAP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  const double* s = ctx->stats_h;
+  o->gn_iters = (int)s[0]; o->energy = s[1]; o->halvings = (int)s[2]; o->normh = s[3]; o->cg_iters = (int)s[4];
+  o->last_rel_residual = s[5]; o->flags = (int)s[6];
+  return ARAP_OK;
+}
+
+// The per-step update, in the reference's order (GV:1499-1522): samples first (they use the pre-update node
+// positions), then mesh points, endpoints, node positions (double-buffered), the six-point fit, sample SH.
+extern "C" int arap_apply(arap_ctx* ctx) {
+  GRAPH_CHECK(ctx);
+  if (!ctx->solved) { set_error("apply: no solve result"); return ARAP_ERR_STATE; }
+  cudaStream_t st = ctx->stream; const int M = ctx->M, k = ctx->k;
+  const bool tm = ctx->timing;
+  if (tm) cudaEventRecord(ctx->ev[1], st);
+  TRY(arapk_node_xf(M, ctx->rot_d.p, ctx->trans_d.p, ctx->node_pos.p, ctx->node_xf.p, st));
+  if (ctx->S > 0) TRY(arapk_lbs_points(ctx->sample_pos.p, ctx->sample_pos.p, ctx->S, k, ctx->sample_rows.idx.p, ctx->sample_rows.w.p, ctx->node_xf.p, ctx->sample_static.p, 1, st));
+  if (tm) cudaEventRecord(ctx->ev[2], st);
+  if (ctx->Mp > 0) TRY(arapk_lbs_points(ctx->mesh_pts.p, ctx->mesh_pts.p, ctx->Mp, k, ctx->mesh_rows.idx.p, ctx->mesh_rows.w.p, ctx->node_xf.p, nullptr, 1, st));
+  TRY(arapk_lbs_points(ctx->ends.p, ctx->ends.p, ctx->N * 6, k, ctx->end_rows.idx.p, ctx->end_rows.w.p, ctx->node_xf.p,
+                       ctx->prm.skip_static_endpoints ? ctx->gs_static.p : nullptr, 6, st));
+  TRY(arapk_lbs_points(ctx->node_pos.p, ctx->node_next.p, M, k, ctx->node_rows.idx.p, ctx->node_rows.w.p, ctx->node_xf.p, nullptr, 1, st));
+  if (tm) cudaEventRecord(ctx->ev[3], st);
+  TRY(arapk_fit_gaussians(ctx->N, ctx->ends.p, ctx->scale_backup.p, ctx->gs_static.p, ctx->pos.p, ctx->rot.p, ctx->scale.p, ctx->shs.p, st));
+  if (tm) cudaEventRecord(ctx->ev[4], st);
+  if (ctx->S > 0 && ctx->aim_feature.p) {
+    TRY(arapk_node_quats(M, ctx->rot_d.p, ctx->node_q.p, st));
+    TRY(arapk_rotate_sample_shs(ctx->S, k, ctx->sample_rows.wf.p, ctx->sample_rows.idx.p, ctx->node_q.p, ctx->sample_static.p, ctx->aim_feature.p, st));
+  }
+  if (tm) cudaEventRecord(ctx->ev[5], st);
+  ctx->node_pos.swap(ctx->node_next);
+  ARAP_CUDA_TRY(cudaMemcpyAsync(ctx->aim.p, ctx->node_pos.p, (size_t)M * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));  // ReloadAimPositions
+  ctx->solved = false;  // resetRT: transforms are per-step increments (GV:1522)
+  return ARAP_OK;
+}
+
+extern "C" int arap_step(arap_ctx* ctx, int on_center) {
+  GRAPH_CHECK(ctx);
+  if (ctx->timing) cudaEventRecord(ctx->ev[0], ctx->stream);
+  TRY(arap_solve(ctx, on_center));
+  TRY(arap_apply(ctx));
+  if (ctx->timing) cudaEventRecord(ctx->ev[6], ctx->stream);
+  return ARAP_OK;
+}
+
+extern "C" int arap_last_step_timing(arap_ctx* ctx, float* ms6) {
+  CTX_CHECK(ctx);
+  if (!ctx->timing) { set_error("timing not enabled"); return ARAP_ERR_STATE; }
+  ARAP_CUDA_TRY(cudaEventSynchronize(ctx->ev[6]));
+  for (int i = 0; i < 5; i++) ARAP_CUDA_TRY(cudaEventElapsedTime(&ms6[i], ctx->ev[i], ctx->ev[i + 1]));
+  ARAP_CUDA_TRY(cudaEventElapsedTime(&ms6[5], ctx->ev[0], ctx->ev[6]));
+  return ARAP_OK;
+}
+
+extern "C" int arap_download_nodes(arap_ctx* ctx, float* node_pos, double* rot, double* trans) {
+  GRAPH_CHECK(ctx);
+  TRY(download(node_pos, ctx->node_pos.p, (size_t)ctx->M * 3, ctx->stream));
+  TRY(download(rot, ctx->rot_d.p, (size_t)ctx->M * 9, ctx->stream)); TRY(download(trans, ctx->trans_d.p, (size_t)ctx->M * 3, ctx->stream));
+  ARAP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return ARAP_OK;
+}
+
+// accessors used by the replay driver (host_io.cpp)
+namespace arapgs {
+int session_num_nodes(arap_ctx* c) { return c->M; }
+int session_k(arap_ctx* c) { return c->k; }
+const std::vector<std::vector<uint32_t>>& session_blocks(arap_ctx* c) { return c->blocks; }
+const std::vector<int>& session_block_types(arap_ctx* c) { return c->block_types; }
+}  // namespace arapgs

@@ -1,0 +1,206 @@
+/* arapgs.h — C ABI of libarapgs: B200-native (sm_100a) ARAP deformation of
+ * Gaussian radiance fields.
+ *
+ * Drop-in boundary for the deformation path of the reference viewer
+ * (XinhaoT/ARAP-Deformation-of-Gaussian-Radiance-Fields, SIBR gaussianViewer).
+ * The reference has no plugin / FFI layer: its deformation API is the set of
+ * C++ entry points GaussianView calls.  Each function below names the reference
+ * call site(s) it replaces, relative to
+ *   src/projects/gaussianviewer/renderer/   (GV = GaussianView.cpp, DH = Deform.hpp,
+ *   DC = Deform.cpp, HC = helper.cpp, CK = cudakdtree.cu).
+ *
+ * Conventions:
+ *   - plain pointers and sizes only; all functions return an int status
+ *     (ARAP_OK = 0) and never exit(); arap_last_error() gives the message.
+ *   - an arap_ctx owns every device buffer; the caller may borrow the SoA
+ *     pointers for the rasteriser (arap_device_view).
+ *   - one explicit CUDA stream per ctx; calls are not re-entrant per ctx and
+ *     only synchronise where the host reads a result.
+ *   - there is NO CPU fallback: every entry point needs the CUDA device.
+ */
+#ifndef ARAPGS_H
+#define ARAPGS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARAP_OK 0
+#define ARAP_ERR_INVALID 1
+#define ARAP_ERR_CUDA 2
+#define ARAP_ERR_STATE 3
+#define ARAP_ERR_IO 4
+#define ARAP_ERR_KNN_TIES 5
+#define ARAP_ERR_UNSUPPORTED 6
+#define ARAP_ERR_NUMERIC 7
+
+#define ARAP_KNN_MAX 12 /* helper.hpp:48 */
+
+typedef struct arap_ctx arap_ctx;
+
+/* Tunables the reference keeps as GaussianView members / ImGui widgets
+ * (GV.hpp:322, 446, 455-457, 482, 598; DC:3-4). */
+typedef struct arap_params {
+  int grid_num;        /* 64 (paper default) .. 128; <ply>_config.txt field 0 (GV:459-487) */
+  int padding;         /* 1  (GV.hpp:446) */
+  int knn_k;           /* 10 (GV.hpp:598; README: 8 to reproduce the paper) */
+  int node_num;        /* 150 (GV.hpp:322) */
+  int high_quality;    /* config field 2; forwarded to the evaluator only */
+  float lpf_parameter; /* 0.2 (GV.hpp:482) */
+  double w_rot, w_reg, w_con; /* 1, 10, 100 (DH:56-58) */
+  int max_gn_iters;    /* 30 (DC:3) */
+  int max_cg_iters;    /* PCG iteration cap per linear system */
+  double cg_tol;       /* relative residual of the first linear system of a step */
+  int skip_static_endpoints; /* 0 = reference behaviour (all endpoints skinned) */
+} arap_params;
+
+typedef struct arap_solve_stats {
+  int gn_iters;        /* Gauss-Newton iterations taken */
+  int cg_iters;        /* total PCG iterations */
+  int halvings;        /* step-halving count */
+  int flags;           /* bit0: numeric breakdown, bit1: PCG hit the iteration cap */
+  double energy;       /* f.f at the last linearisation point (Deform::optimize return) */
+  double normh;        /* |h| of the last accepted step */
+  double last_rel_residual;
+} arap_solve_stats;
+
+typedef struct arap_grid_info {
+  int grid_num, padding;
+  int valid_cells;          /* valid_grid_num */
+  long long samples;        /* 64 * valid_cells */
+  long long pairs;          /* grid_gs_prefix_sum[G^3-1] */
+  float aabb_min[3], aabb_max[3];
+  float grid_step;
+} arap_grid_info;
+
+/* Borrowed device pointers: exactly the Rasterizer::forward /
+ * forward3d_grid argument arrays (GV:1106-1112, 4159-4186). */
+typedef struct arap_device_view {
+  long long n_gaussians;
+  float* pos;      /* N x 3 */
+  float* rot;      /* N x 4 (w,x,y,z) */
+  float* scale;    /* N x 3, linear */
+  float* opacity;  /* N, post-sigmoid */
+  float* shs;      /* N x 48, 16 coefficients x RGB interleaved */
+  int n_nodes;
+  float* node_pos; /* M x 3 */
+  double* node_rot;   /* M x 9 column-major (DeformGraph::rot) of the last solve */
+  double* node_trans; /* M x 3 */
+  long long n_samples;
+  float* sample_pos;     /* S x 3 */
+  float* aim_feature;    /* S x 48 */
+  float* aim_opacity;    /* S */
+  int* valid_grid;       /* V */
+  int* grid_gs_prefix_sum; /* G^3, inclusive */
+  int* grided_gs_idx;    /* pairs */
+  int* gs_init_grid_idx; /* N */
+  float* ada_lpf_ratio;  /* G^3 x 9 */
+  float* end_points;     /* N x 6 x 3 */
+} arap_device_view;
+
+/* ---- lifecycle ----------------------------------------------------------- */
+const char* arap_last_error(void);
+int arap_version(void);
+int arap_default_params(arap_params* p);
+/* stream: a cudaStream_t (or NULL for a ctx-owned stream). Replaces the cudaMalloc block of GaussianView::init (GV:611-841). */
+int arap_create(arap_ctx** out, int device, void* stream, const arap_params* params);
+int arap_destroy(arap_ctx* ctx);
+int arap_set_params(arap_ctx* ctx, const arap_params* params);
+int arap_sync(arap_ctx* ctx);
+
+/* ---- Gaussians ----------------------------------------------------------- */
+/* SoA upload (post-activation values, as loadPly_Origin produces: GV:43-153). Host or device source. */
+int arap_set_gaussians(arap_ctx* ctx, long long n, const float* pos, const float* rot, const float* scale,
+                       const float* opacity, const float* shs, int src_is_device);
+int arap_download_gaussians(arap_ctx* ctx, float* pos, float* rot, float* scale, float* opacity, float* shs);
+int arap_get_device_view(arap_ctx* ctx, arap_device_view* out);
+
+/* ---- stage (a): density grid ---------------------------------------------- */
+/* getOverallAABB + getGridSamples + GetAdaLpfRatio (GV:3601-3631, 3870-4149, 4670-4751).
+ * Re-orders the Gaussians into cell order exactly like GV:3938-3953. */
+int arap_grid_build(arap_ctx* ctx);
+/* UpdateContainingRelationship (GV:3634-3743): rebuild boxes/lists for the current Gaussians, keeping samples. */
+int arap_grid_update_lists(arap_ctx* ctx);
+/* Rasterizer::forward3d_grid call sites (GV:4159-4186 cur, 4222-4249 aim). which: 0 = aim, 1 = current. */
+int arap_grid_eval(arap_ctx* ctx, int which);
+int arap_grid_info_get(arap_ctx* ctx, arap_grid_info* out);
+int arap_download_grid(arap_ctx* ctx, int* valid, int* prefix, int* lists, float* sample_pos, int* gs_init_grid_idx);
+int arap_download_features(arap_ctx* ctx, int which, float* feature, float* opacity);
+int arap_download_samples(arap_ctx* ctx, float* sample_pos, float* aim_feature);
+
+/* ---- stage (b): graph, kNN, weights --------------------------------------- */
+/* farthest_control_points_sampling over the Gaussian centres + DeformGraph ctor + setupWeights* (GV:698-754, HC:139-195, DH:54-95). */
+int arap_graph_build_fps(arap_ctx* ctx, int node_num, int k);
+/* LoadDeformation: nodes given as Gaussian (or mesh point) indices (GV:4961-5010). */
+int arap_graph_build_anchors(arap_ctx* ctx, const int* anchor_idx, int m, int k);
+/* LoadMeshForGraph + "Build Graph on Mesh" + RebuildGraph (GV:4939-4959, 4825-4856): mesh points become the
+ * candidate points; nodes = FPS over them with node_num = all. on_mesh=0 keeps nodes on Gaussians but still skins the mesh points. */
+int arap_set_mesh_points(arap_ctx* ctx, const float* pts, int n, int nodes_on_mesh);
+/* DeformGraph::computeWeights for arbitrary device queries (DH:187-208): idx Q x k (uint32), w Q x k (double), device outputs. */
+int arap_knn_weights(arap_ctx* ctx, const float* queries_dev, long long q, int k, uint32_t* idx_dev, double* w_dev);
+int arap_download_graph(arap_ctx* ctx, int* anchor, float* node_pos, int* nbr /* M x k */);
+int arap_download_rows(arap_ctx* ctx, int family /*0 ends,1 samples,2 mesh,3 nodes*/, uint32_t* idx, double* w);
+
+/* ---- control regions (GV:1169-1387, 1996-2109) ---------------------------- */
+/* blocks as CSR over node ids; types: 1 active, 0 pinned, -1 excluded. Absorbs UpdateIndicies + CheckStaticSamples. */
+int arap_set_blocks(arap_ctx* ctx, int n_blocks, const int* block_off, const uint32_t* block_nodes, const int* block_types);
+int arap_download_static_flags(arap_ctx* ctx, uint8_t* gaussians, uint8_t* samples);
+
+/* ---- aims (GV:2920-2983, 5240-5247) ---------------------------------------- */
+int arap_aim_translate(arap_ctx* ctx, const float delta[3]);                 /* UpdateAimPosition */
+int arap_aim_twist(arap_ctx* ctx, const float axis[4], int y);               /* UpdateAimPositionTwist */
+int arap_aim_scale(arap_ctx* ctx, int y);                                    /* UpdateAimPositionScale */
+int arap_aim_set(arap_ctx* ctx, const float* aim /* M x 3 host */);          /* script aims (GV:1924-1937) */
+int arap_aim_get(arap_ctx* ctx, float* aim);
+int arap_aim_reload(arap_ctx* ctx);                                          /* ReloadAimPositions */
+
+/* ---- stage (c) + (d): one drag step (GV:1481-1522) ------------------------- */
+/* Deform deform(...); real_time_deform(); putFreeInputs  (DC:77-169, DH:140-151) */
+int arap_solve(arap_ctx* ctx, int constraints_on_center);
+int arap_solve_stats_get(arap_ctx* ctx, arap_solve_stats* out); /* synchronises */
+/* UpdatePositionforSamples; UpdatePosition; UpdateAsSixPointsWithdrawBad; FastUpdateSamplesSH; ReloadAimPositions; resetRT */
+int arap_apply(arap_ctx* ctx);
+/* solve + apply */
+int arap_step(arap_ctx* ctx, int constraints_on_center);
+int arap_download_nodes(arap_ctx* ctx, float* node_pos, double* rot, double* trans);
+/* per-stage device time of the last arap_step in ms: [0] solve [1] samples lbs [2] endpoints+mesh+nodes lbs [3] fit [4] sample SH [5] total */
+int arap_last_step_timing(arap_ctx* ctx, float* ms6);
+int arap_enable_timing(arap_ctx* ctx, int on);
+
+/* ---- deform.txt / graph.obj / config / scripts (host IO, byte-compatible) -- */
+typedef struct arap_history arap_history;
+int arap_history_load(const char* path, arap_history** out);                 /* LoadDeformation grammar (GV:4961-5095) */
+int arap_history_save(const arap_history* h, const char* path);              /* RecordDeformation (GV:4859-4935) */
+int arap_history_free(arap_history* h);
+int arap_history_new(arap_history** out, int nodes_on_mesh, const int* node_anchor, int n_nodes);
+int arap_history_add_block(arap_history* h, const uint32_t* nodes, int n);
+int arap_history_add_move(arap_history* h, int op_type, const float* movements /* n x 3 */, int n, const int* block_types,
+                          int n_types, int energy_on_center, const float twist_axis[4]);
+/* summary: [0] nodes_on_mesh [1] n_nodes [2] total_ops [3] move_ops [4] n_blocks [5] n_moves */
+int arap_history_summary(const arap_history* h, int* out6);
+int arap_history_nodes(const arap_history* h, int* out);
+int arap_history_ops(const arap_history* h, int* out);
+int arap_history_block(const arap_history* h, int i, uint32_t* nodes_out, int* n);
+int arap_history_move(const arap_history* h, int i, float* movements_out, int* n, int* block_types_out, int* n_types,
+                      int* energy_on_center, float* twist_axis4);
+/* LoadMeshPoints: `v x y z` lines only (HC:264-282). Two-call pattern: pts==NULL returns the count. */
+int arap_graph_obj_load(const char* path, float* pts, int* n);
+int arap_graph_obj_save(const char* path, const float* pts, int n);          /* writeVectorToObj (HC:1111-1126) */
+/* <ply>_config.txt: grid_num is_synthetic conf2 (GV:459-487) */
+int arap_config_load(const char* path, int* grid_num, int* is_synthetic, int* has_soup, int* high_quality);
+/* Run a loaded history through the state machine of GV:1757-1916 (blocks added/deleted, per-move block types,
+ * op types 1..4).  Rebuilds the graph from the recorded anchors first when rebuild != 0 (LoadDeformation) or keeps the
+ * current graph (LoadDeformation_wo_rebuild).  Returns the number of drag steps run. */
+int arap_replay(arap_ctx* ctx, const arap_history* h, int rebuild_graph, int* steps_run);
+/* LoadDeformScript0/1 (GV:2512-2600) on the current graph + the script loop of GV:1918-1993. */
+int arap_run_script(arap_ctx* ctx, int script_id, int* steps_run);
+/* PointRotateByAxis (HC:1077-1100), exposed for tests */
+int arap_point_rotate_by_axis(const float point[3], const float center[3], const float axis[4], float radian, float out[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARAPGS_H */
