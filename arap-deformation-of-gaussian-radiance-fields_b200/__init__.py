@@ -380,6 +380,12 @@ class Session:
         check(lib().arap_last_step_timing(self._ctx, _ptr(ms)))
         return dict(solve=float(ms[0]), samples_lbs=float(ms[1]), points_lbs=float(ms[2]), fit=float(ms[3]), sample_sh=float(ms[4]), total=float(ms[5]))
 
+    def step_timings(self, max_steps=128):
+        ms = np.zeros((max_steps, 6), f32)
+        n = C.c_int()
+        check(lib().arap_step_timings(self._ctx, _ptr(ms), int(max_steps), C.byref(n)))
+        return ms[:n.value]   # columns: solve, samples_lbs, points_lbs, fit, sample_sh, total
+
     # -- replay
     def replay(self, history: History, rebuild_graph=True) -> int:
         n = C.c_int()

@@ -178,7 +178,9 @@ struct arap_ctx {
   double* stats_h = nullptr;  // pinned
   bool solved = false;
   // timing
-  bool timing = false; cudaEvent_t ev[7] = {nullptr}; float last_ms[6] = {0};
+  // timing: a ring of per-step event sets so a whole timed region can be read back afterwards
+  static constexpr int TRING = 128;
+  bool timing = false; cudaEvent_t evr[TRING][7] = {{nullptr}}; cudaEvent_t* ev = evr[0]; long long tsteps = 0;
 };
 
 #define CTX_CHECK(c) do { if (!(c)) { set_error("null ctx"); return ARAP_ERR_INVALID; } cudaSetDevice((c)->device); } while (0)
@@ -214,7 +216,7 @@ extern "C" int arap_create(arap_ctx** out, int device, void* stream, const arap_
   else { ARAP_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
   if (params) c->prm = *params; else arap_default_params(&c->prm);
   ARAP_CUDA_TRY(cudaMallocHost((void**)&c->stats_h, 16 * sizeof(double)));
-  for (auto& ev : c->ev) ARAP_CUDA_TRY(cudaEventCreate(&ev));
+  for (auto& row : c->evr) for (auto& ev : row) ARAP_CUDA_TRY(cudaEventCreate(&ev));
   *out = c.release();
   return ARAP_OK;
 }
@@ -224,7 +226,7 @@ extern "C" int arap_destroy(arap_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->stats_h) cudaFreeHost(ctx->stats_h);
-  for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  for (auto& row : ctx->evr) for (auto& ev : row) if (ev) cudaEventDestroy(ev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return ARAP_OK;
@@ -232,7 +234,7 @@ extern "C" int arap_destroy(arap_ctx* ctx) {
 
 extern "C" int arap_set_params(arap_ctx* ctx, const arap_params* p) { CTX_CHECK(ctx); if (!p) return ARAP_ERR_INVALID; ctx->prm = *p; return ARAP_OK; }
 extern "C" int arap_sync(arap_ctx* ctx) { CTX_CHECK(ctx); ARAP_CUDA_TRY(cudaStreamSynchronize(ctx->stream)); return ARAP_OK; }
-extern "C" int arap_enable_timing(arap_ctx* ctx, int on) { CTX_CHECK(ctx); ctx->timing = on != 0; return ARAP_OK; }
+extern "C" int arap_enable_timing(arap_ctx* ctx, int on) { CTX_CHECK(ctx); ctx->timing = on != 0; ctx->tsteps = 0; ctx->ev = ctx->evr[0]; return ARAP_OK; }
 
 template <typename T>
 static int upload(DBuf<T>& d, const T* src, size_t n, bool src_dev, cudaStream_t st) {
@@ -776,10 +778,10 @@ extern "C" int arap_apply(arap_ctx* ctx) {
 
 extern "C" int arap_step(arap_ctx* ctx, int on_center) {
   GRAPH_CHECK(ctx);
-  if (ctx->timing) cudaEventRecord(ctx->ev[0], ctx->stream);
+  if (ctx->timing) { ctx->ev = ctx->evr[ctx->tsteps % arap_ctx::TRING]; cudaEventRecord(ctx->ev[0], ctx->stream); }
   TRY(arap_solve(ctx, on_center));
   TRY(arap_apply(ctx));
-  if (ctx->timing) cudaEventRecord(ctx->ev[6], ctx->stream);
+  if (ctx->timing) { cudaEventRecord(ctx->ev[6], ctx->stream); ctx->tsteps++; }
   return ARAP_OK;
 }
 
@@ -789,6 +791,22 @@ extern "C" int arap_last_step_timing(arap_ctx* ctx, float* ms6) {
   ARAP_CUDA_TRY(cudaEventSynchronize(ctx->ev[6]));
   for (int i = 0; i < 5; i++) ARAP_CUDA_TRY(cudaEventElapsedTime(&ms6[i], ctx->ev[i], ctx->ev[i + 1]));
   ARAP_CUDA_TRY(cudaEventElapsedTime(&ms6[5], ctx->ev[0], ctx->ev[6]));
+  return ARAP_OK;
+}
+
+// per-step stage timings of the last min(n_steps_recorded, max_steps, 128) steps, oldest first; 6 floats each
+extern "C" int arap_step_timings(arap_ctx* ctx, float* ms, int max_steps, int* n_out) {
+  CTX_CHECK(ctx);
+  if (!ctx->timing) { set_error("timing not enabled"); return ARAP_ERR_STATE; }
+  const long long have = std::min<long long>(ctx->tsteps, arap_ctx::TRING);
+  const int n = (int)std::min<long long>(have, max_steps);
+  for (int t = 0; t < n; t++) {
+    cudaEvent_t* e = ctx->evr[(ctx->tsteps - n + t) % arap_ctx::TRING];
+    ARAP_CUDA_TRY(cudaEventSynchronize(e[6]));
+    for (int i = 0; i < 5; i++) ARAP_CUDA_TRY(cudaEventElapsedTime(&ms[6 * t + i], e[i], e[i + 1]));
+    ARAP_CUDA_TRY(cudaEventElapsedTime(&ms[6 * t + 5], e[0], e[6]));
+  }
+  if (n_out) *n_out = n;
   return ARAP_OK;
 }
 

@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py — ms per ARAP drag-update on the BASELINE.json workload.
+
+Own arm (default):   python bench.py --gpus N --steps K --warmup W
+Reference arm:       python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" is one drag update of the reference's per-frame body (GaussianView.cpp:1481-1522):
+aim update -> Gauss-Newton solve -> sample advect -> endpoint/mesh/node LBS -> six-point fit ->
+sample SH rotation.  Workload at N=1: configs[3] of BASELINE.json (the configuration the
+north_star target is quoted on): synthetic 6M-Gaussian scene, 128^3 grid, 16k nodes, k=10,
+per-node constraints on two box-selected caps, constant (0,0,0.002) drag.  With N>1 ranks the
+Gaussian-indexed stages are sharded (each rank owns a 6M-Gaussian shard, weak scaling), the node
+solve is replicated, and each step ends with an NCCL all-gather of the deformed SoA.
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+import __graft_entry__ as ge  # noqa: E402
+
+METRIC = "ms_per_drag_update"
+UNIT = "ms"
+WORKLOADS = {
+    "shells6m": "synthetic 6M-Gaussian scene, 128^3 grid, high_quality=1, 16k nodes, k=10, solve+samples+apply per drag step",
+    "sphere1m": "synthetic 1M-Gaussian cloud, 64^3 grid, 4k graph nodes, k=10, drag replay",
+}
+DRAG = np.array([0.0, 0.0, 0.002], np.float32)
+
+
+def hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
+
+
+class DevArray:
+    """Expose a raw device pointer owned by the ctx to torch (for NCCL) via __cuda_array_interface__."""
+
+    def __init__(self, ptr, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=2)
+
+
+def setup_session(pkg, scenes, workload, n, rank, world, stream):
+    cfg = scenes.CONFIGS[workload]
+    sc = scenes.make_scene(workload, n=n, seed_offset=rank)
+    s = pkg.Session(device=int(os.environ.get("LOCAL_RANK", 0)), stream=stream, grid_num=cfg["grid"], knn_k=cfg["k"],
+                    node_num=cfg["nodes"], high_quality=1 if workload == "shells6m" else 0)
+    t0 = time.perf_counter()
+    s.set_gaussians(sc["pos"], sc["rot"], sc["scale"], sc["opacity"], sc["shs"])
+    gi = s.grid_build()
+    s.grid_eval(0)
+    s.sync(); t_grid = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    if world > 1:
+        # replicated solve: every rank uses the same node set (FPS over a common seeded cloud of the same law)
+        common = scenes.make_scene(workload, n=max(cfg["nodes"] * 25, 100000), seed_offset=7777)
+        tmp = pkg.Session(device=int(os.environ.get("LOCAL_RANK", 0)), grid_num=16, knn_k=cfg["k"], node_num=cfg["nodes"])
+        tmp.set_gaussians(common["pos"], common["rot"], common["scale"], common["opacity"], common["shs"])
+        tmp.grid_build()
+        nodes = tmp.graph_build_fps()["node_pos"]
+        tmp.close()
+        s.set_mesh_points(nodes, True)
+    g = s.graph_build_fps()
+    s.sync(); t_graph = time.perf_counter() - t0
+    blocks, types = scenes.cap_blocks(g["node_pos"])
+    s.set_blocks(blocks, types)
+    return s, sc, gi, dict(t_grid_s=t_grid, t_graph_s=t_graph, n_active=len(blocks[0]), n_pinned=len(blocks[1]), active=blocks[0])
+
+
+def run_own(args):
+    import torch
+    import torch.distributed as dist
+
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = ge.load_package()
+    scenes = importlib.import_module(ge.PKG + ".scenes")
+    cfg = scenes.CONFIGS[args.workload]
+    n = args.gaussians or cfg["n"]
+    # a dedicated (non-default) torch stream: the ctx launches every kernel on it, so torch.cuda.Event sees the work
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
+    s, sc, gi, setup = setup_session(pkg, scenes, args.workload, n, rank, world, stream)
+    M, k, N, S = s.M, cfg["k"], s.N, gi["samples"]
+
+    gather = None
+    if world > 1:   # all-gather of the deformed SoA (232 B / Gaussian): pos 12 + rot 16 + scale 12 + SH 192
+        v = s.device_view()
+        parts = [torch.as_tensor(DevArray(p, (N * w,)), device="cuda") for p, w in ((v.pos, 3), (v.rot, 4), (v.scale, 3), (v.shs, 48))]
+        outs = [torch.empty(world * t.numel(), dtype=torch.float32, device="cuda") for t in parts]
+
+        def gather():
+            for t, o in zip(parts, outs):
+                dist.all_gather_into_tensor(o, t)
+
+    def one_step():
+        s.aim_translate(DRAG)
+        s.step(False)
+        if gather:
+            gather()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    barrier()
+    s.enable_timing(True)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        one_step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    stages = s.step_timings(min(args.steps, 128))
+    st = s.solve_stats()
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+
+    # ---- e2e: host-driven drag loop through the C ABI: host aims in, node positions + solve stats out, every step
+    s.enable_timing(False)
+    aim = s.aim_get()
+    active = setup["active"]
+    e2e_steps = max(3, min(args.steps, 10))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        aim[active] += DRAG
+        s.aim_set(aim)              # H2D M x 3 floats (+ sync)
+        s.step(False)
+        if gather:
+            gather()
+        aim, _, _ = s.download_nodes()  # D2H node positions (+ rot/trans), synchronises
+        s.solve_stats()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    te = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = hbm_peak()
+    mean = stages.mean(0) if len(stages) else np.zeros(6)
+    apply_ms = float(mean[2] + mean[3])      # endpoint/mesh/node LBS + six-point fit  (stage (d))
+    sample_ms = float(mean[1] + mean[4])     # sample advect + sample SH rotate       (a9 + a10)
+    apply_bytes = (596 + 48 * k) * N          # algorithmic bytes per non-static Gaussian
+    sample_bytes = (408 + 8 * k) * S
+    apply_gbs = apply_bytes / (apply_ms * 1e-3) / 1e9 if apply_ms > 0 else 0.0
+    sample_gbs = sample_bytes / (sample_ms * 1e-3) / 1e9 if sample_ms > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": round(ms_step, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": round(ms_step, 4), "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 storage, f64 solve/LBS arithmetic", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload], "gaussians_per_gpu": N, "gaussians_total": N * world, "nodes": M, "k": k,
+                   "grid": cfg["grid"], "samples_per_gpu": S, "valid_cells": gi["valid_cells"], "list_pairs": gi["pairs"],
+                   "constraints": "per-node, two caps (|z|>0.4)", "active_nodes": setup["n_active"], "pinned_nodes": setup["n_pinned"],
+                   "l2": "inputs (>1.4 GB SoA + tables per step) exceed the 126 MB L2",
+                   "parallelism": "replicated solve, Gaussians/samples sharded by index, NCCL all-gather of deformed SoA" if world > 1 else "single GPU"},
+        "stages_ms": {"solve": round(float(mean[0]), 4), "sample_advect": round(float(mean[1]), 4), "endpoint_lbs": round(float(mean[2]), 4),
+                      "six_point_fit": round(float(mean[3]), 4), "sample_sh_rotate": round(float(mean[4]), 4)},
+        "solve": {"gn_iters": st["gn_iters"], "cg_iters": st["cg_iters"], "flags": st["flags"]},
+        "apply_gaussians_per_s": round(N / (apply_ms * 1e-3), 1) if apply_ms > 0 else None,
+        "setup_s": {"grid_build_eval": round(setup["t_grid_s"], 3), "graph_knn": round(setup["t_graph_s"], 3)},
+        "roofline": {"bound": "hbm", "kernel": "apply pass (d): k_lbs_points<endpoints> + k_fit_gaussians", "achieved": round(apply_gbs, 1),
+                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(apply_gbs / peak, 4), "traffic": None,
+                     "algorithmic_bytes_per_launch": apply_bytes, "ms_per_launch": round(apply_ms, 4)},
+        "roofline_samples": {"bound": "hbm", "kernel": "sample pass (a9+a10): k_lbs_points<samples> + k_rotate_sample_shs",
+                             "achieved": round(sample_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(sample_gbs / peak, 4),
+                             "algorithmic_bytes_per_launch": sample_bytes, "ms_per_launch": round(sample_ms, 4)},
+        "e2e": {"value": round(e2e_ms, 4), "unit": UNIT, "h2d_bytes_per_step": M * 12, "d2h_bytes_per_step": M * (12 + 72 + 24) + 64,
+                "what": "arap_aim_set(host aims) + arap_step + arap_download_nodes + arap_solve_stats_get per step"},
+        "gpu_launches": 11 * args.steps,
+        "clocks": clk,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(scenes, args.workload, sc, N, S, M, k, cfg)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_sample_step(scenes, workload, full_n, cfg, sample_n, sample_nodes, steps=2):
+    """One bounded CPU sample of the workload through the oracle (the OpenMP restatement of the reference path)."""
+    import oracle
+    from oracle.session import OracleSession
+    threads = min(16, os.cpu_count() or 1)     # the reference pins 16 OpenMP threads (main.cpp:102-104)
+    oracle.set_threads(threads)
+    sc = scenes.make_scene(workload, n=sample_n)
+    o = OracleSession(sc, grid_num=cfg["grid"], knn_k=cfg["k"], node_num=sample_nodes)
+    gi = o.grid_build()
+    o.grid_eval(0)
+    o.graph_build_fps()
+    blocks, types = scenes.cap_blocks(o.node_pos)
+    o.set_blocks(blocks, types)
+    acc = dict(solve=0.0, samples_lbs=0.0, points_lbs=0.0, fit=0.0, sample_sh=0.0)
+    for _ in range(steps):
+        o.aim_translate(DRAG)
+        o.step(False)
+        for kk in acc:
+            acc[kk] += o.timing[kk] / steps
+    return acc, gi, threads
+
+
+def cpu_baseline(scenes, workload, sc, N, S, M, k, cfg):
+    sample_n, sample_nodes = min(N, 200_000), min(M, 1000)
+    acc, gi, threads = cpu_sample_step(scenes, workload, N, cfg, sample_n, sample_nodes)
+    gauss_ms = (acc["points_lbs"] + acc["fit"]) * 1e3 * (N / sample_n)
+    samp_ms = (acc["samples_lbs"] + acc["sample_sh"]) * 1e3 * (S / max(gi["samples"], 1))
+    solve_ms = acc["solve"] * 1e3
+    return {"value": round(gauss_ms + samp_ms + solve_ms, 1), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"oracle (OpenMP port of the reference CPU path) on {sample_n} Gaussians / {gi['samples']} samples / {sample_nodes} nodes; "
+                      f"Gaussian and sample stages scaled linearly to {N} / {S}; solve measured at {sample_nodes} nodes and NOT scaled "
+                      f"(sparse Cholesky grows super-linearly: the value is a lower bound)",
+            "parts_ms": {"gaussian_stages_scaled": round(gauss_ms, 1), "sample_stages_scaled": round(samp_ms, 1), "solve_unscaled": round(solve_ms, 1)}}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    ge.load_package()
+    scenes = importlib.import_module(ge.PKG + ".scenes")
+    cfg = scenes.CONFIGS[args.workload]
+    N = args.gaussians or cfg["n"]
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    sample_n, sample_nodes = min(N, 200_000), min(cfg["nodes"], 1000)
+    vals = []
+    parts = None
+    for i in range(max(1, min(args.steps, 3))):
+        acc, gi, threads = cpu_sample_step(scenes, args.workload, N, cfg, sample_n, sample_nodes, steps=1 + (1 if i == 0 and args.warmup else 0))
+        S_full = gi["samples"] * (N / sample_n)   # sample count grows with the occupied volume; linear stand-in
+        ms = (acc["points_lbs"] + acc["fit"]) * 1e3 * (N / sample_n) + (acc["samples_lbs"] + acc["sample_sh"]) * 1e3 * (N / sample_n) + acc["solve"] * 1e3
+        vals.append(ms)
+        parts = acc
+    v = float(np.median(vals))
+    sample = (f"oracle (OpenMP port; the reference cannot be built here: no Eigen/GL, CudaRasterizer fetched from the network) on {sample_n} Gaussians, "
+              f"{sample_nodes} nodes, {threads} threads; Gaussian/sample stages scaled linearly to {N} Gaussians, solve at {sample_nodes} nodes unscaled (lower bound)")
+    line = {"impl": "reference", "metric": METRIC, "value": round(v, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(v, 1), "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f32 storage, f64 solve/LBS arithmetic",
+            "data": "synthetic", "config": {"workload": WORKLOADS[args.workload], "gaussians_total": N, "nodes": cfg["nodes"], "k": cfg["k"], "grid": cfg["grid"]},
+            "cpu_baseline": {"value": round(v, 1), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                             "parts_s_on_sample": {k2: round(v2, 4) for k2, v2 in parts.items()}},
+            "e2e": {"value": round(v, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--workload", default="shells6m", choices=list(WORKLOADS))
+    ap.add_argument("--gaussians", type=int, default=0, help="override the Gaussian count per GPU (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

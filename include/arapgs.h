@@ -169,6 +169,8 @@ int arap_download_nodes(arap_ctx* ctx, float* node_pos, double* rot, double* tra
 /* per-stage device time of the last arap_step in ms: [0] solve [1] samples lbs [2] endpoints+mesh+nodes lbs [3] fit [4] sample SH [5] total */
 int arap_last_step_timing(arap_ctx* ctx, float* ms6);
 int arap_enable_timing(arap_ctx* ctx, int on);
+/* stage timings (6 floats per step, same order) of the most recent steps since timing was enabled, oldest first (ring of 128) */
+int arap_step_timings(arap_ctx* ctx, float* ms, int max_steps, int* n_out);
 
 /* ---- deform.txt / graph.obj / config / scripts (host IO, byte-compatible) -- */
 typedef struct arap_history arap_history;

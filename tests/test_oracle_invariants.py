@@ -1,0 +1,176 @@
+"""Analytic invariants that pin the oracle where the reference has no tests. CPU only."""
+import numpy as np
+import pytest
+from scipy.spatial.transform import Rotation
+
+from oracle.session import OracleSession
+
+
+def sh_basis(d):
+    """3DGS real SH basis (degree 3) at unit direction d — the basis the rasteriser evaluates."""
+    x, y, z = d
+    C0, C1 = 0.28209479177387814, 0.4886025119029199
+    C2 = [1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792, 0.5462742152960396]
+    C3 = [-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154, -0.4570457994644658,
+          1.445305721320277, -0.5900435899266435]
+    xx, yy, zz, xy, yz, xz = x * x, y * y, z * z, x * y, y * z, x * z
+    return np.array([C0, -C1 * y, C1 * z, -C1 * x, C2[0] * xy, C2[1] * yz, C2[2] * (2 * zz - xx - yy), C2[3] * xz,
+                     C2[4] * (xx - yy), C3[0] * y * (3 * xx - yy), C3[1] * xy * z, C3[2] * y * (4 * zz - xx - yy),
+                     C3[3] * z * (2 * zz - 3 * xx - 3 * yy), C3[4] * x * (4 * zz - xx - yy), C3[5] * z * (xx - yy),
+                     C3[6] * x * (xx - 3 * yy)])
+
+
+def test_sh_rotation_rotates_the_radiance_function(orc):
+    """f'(R d) == f(d): pins the rotation matrices (and the odd-index sign flips) against the 3DGS basis."""
+    rng = np.random.default_rng(1)
+    for seed in range(4):
+        R = Rotation.random(random_state=seed).as_matrix().astype(np.float32)
+        sh = rng.normal(size=(16, 3)).astype(np.float32)
+        sh2 = orc.sh_rotate(R, sh.reshape(-1)).reshape(16, 3)
+        for _ in range(10):
+            d = rng.normal(size=3); d /= np.linalg.norm(d)
+            assert np.allclose(sh_basis(d) @ sh, sh_basis(R.astype(np.float64) @ d) @ sh2, atol=3e-6)
+
+
+def test_sh_rotation_inverse_and_composition(orc):
+    rng = np.random.default_rng(2)
+    R1 = Rotation.random(random_state=5).as_matrix().astype(np.float32)
+    R2 = Rotation.random(random_state=6).as_matrix().astype(np.float32)
+    sh = rng.normal(size=48).astype(np.float32)
+    assert np.allclose(orc.sh_rotate(R1.T.copy(), orc.sh_rotate(R1, sh)), sh, atol=2e-6)
+    assert np.allclose(orc.sh_rotate(R2, orc.sh_rotate(R1, sh)), orc.sh_rotate((R2 @ R1).astype(np.float32), sh), atol=3e-6)
+    b1, b2, b3 = orc.sh_matrices(R1)
+    for b in (b1, b2, b3):
+        assert np.allclose(b @ b.T, np.eye(len(b)), atol=2e-6)
+
+
+def test_polar_matches_svd(orc):
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        M = rng.normal(size=(3, 3)) * np.array([1.0, 0.1, 0.01])
+        U, s, Vt = np.linalg.svd(M)
+        R, S = orc.polar(M)
+        assert np.allclose(R, U @ Vt, atol=1e-9) and np.allclose(S, Vt.T @ np.diag(s) @ Vt, atol=1e-12)
+
+
+def test_knn_selection_sort_semantics(orc):
+    """Without ties the partial selection sort is a plain ascending order; weights follow (1-d/dmax)^2 normalised."""
+    rng = np.random.default_rng(4)
+    nodes = rng.normal(size=(300, 3)).astype(np.float32)
+    q = rng.normal(size=(500, 3)).astype(np.float32)
+    k = 10
+    idx, w = orc.knn_weights(nodes, q, k)
+    t = q[:, None, :] - nodes[None]
+    d = np.sqrt(((t[..., 0] * t[..., 0] + t[..., 1] * t[..., 1]) + t[..., 2] * t[..., 2]).astype(np.float32)).astype(np.float32)
+    order = np.argsort(d, axis=1, kind="stable")[:, :k + 1]
+    ties = np.array([len(np.unique(np.sort(d[i])[:k + 2])) < k + 2 for i in range(len(q))])
+    assert np.array_equal(idx[~ties], order[~ties].astype(np.uint32))
+    dd = np.take_along_axis(d, idx.astype(np.int64), 1).astype(np.float64)
+    u = (1.0 - dd[:, :k] / dd[:, k:k + 1]) ** 2
+    assert np.allclose(w, u / u.sum(1, keepdims=True), rtol=1e-15, atol=0)
+    assert np.allclose(w.sum(1), 1.0)
+
+
+def test_knn_tie_break_is_position_based(orc):
+    """position i keeps a tie against later positions; among later positions the highest wins."""
+    nodes = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [-1, 0, 0], [0, -1, 0], [0, 0, -1], [3, 3, 3]], np.float32)
+    idx, _ = orc.knn_weights(nodes, np.zeros((1, 3), np.float32), 3, weights=False)
+    # step 0: position 0 ties with everyone -> stays (node 0). step 1: position 1 holds d=1 -> node 1. ...
+    assert idx[0].tolist() == [0, 1, 2, 3]
+    nodes2 = np.array([[3, 3, 3], [0, 1, 0], [0, 0, 1], [-1, 0, 0], [0, -1, 0], [0, 0, -1], [1, 0, 0]], np.float32)
+    idx2, _ = orc.knn_weights(nodes2, np.zeros((1, 3), np.float32), 3, weights=False)
+    # step 0: d[0] is large; scanning from the end, the LAST position with the minimum (6) wins; node 0 moves to position 6.
+    # step 1: position 1 holds the minimum -> node 1; etc.
+    assert idx2[0].tolist() == [6, 1, 2, 3]
+
+
+def _session(scenes, n=3000, nodes=60, k=6, **kw):
+    sc = scenes.make_scene("sphere1m", n=n)
+    o = OracleSession(sc, grid_num=16, knn_k=k, node_num=nodes, with_samples=kw.pop("with_samples", False), **kw)
+    o.grid_build()
+    o.graph_build_fps()
+    return o
+
+
+def test_identity_aims_give_identity_solve_and_noop_apply(scenes):
+    o = _session(scenes)
+    o.set_blocks([np.arange(o.M, dtype=np.uint32)], [1])
+    before = {k: v.copy() for k, v in o.g.items()}
+    st = o.step(False)
+    assert st["iters"] == 1 and st["energy"] < 1e-20
+    assert np.allclose(o.last_rot, np.tile(np.eye(3).reshape(-1), (o.M, 1)), atol=1e-12) and np.allclose(o.last_trans, 0, atol=1e-12)
+    assert np.allclose(o.g["pos"], before["pos"], atol=2e-7)
+    assert np.allclose(o.g["scale"], before["scale"], rtol=2e-4)   # (s+1e-3)*2 end-point round trip in float
+    assert np.allclose(o.g["shs"], before["shs"], atol=2e-6)
+
+
+def test_rigid_aims_give_rigid_motion(scenes):
+    """Rigid aims on all nodes => every Gaussian follows the rigid motion; scales unchanged; SH rotated by R."""
+    o = _session(scenes)
+    o.set_blocks([np.arange(o.M, dtype=np.uint32)], [1])
+    R = Rotation.from_rotvec([0.02, -0.03, 0.05]).as_matrix()
+    t = np.array([0.01, -0.02, 0.005])
+    before = {k: v.copy() for k, v in o.g.items()}
+    o.aim_set((o.node_pos.astype(np.float64) @ R.T + t).astype(np.float32))
+    st = o.step(False)
+    assert st["energy"] < 1e-10
+    assert np.allclose(o.g["pos"], before["pos"].astype(np.float64) @ R.T + t, atol=5e-7)
+    assert np.allclose(o.g["scale"], before["scale"], rtol=5e-4)
+    q0 = Rotation.from_quat(before["rot"][:, [1, 2, 3, 0]]); q1 = Rotation.from_quat(o.g["rot"][:, [1, 2, 3, 0]])
+    assert np.allclose((q1 * q0.inv()).as_matrix(), R[None], atol=2e-4)
+    expect = np.stack([__import__("oracle").sh_rotate(R.astype(np.float32), s) for s in before["shs"][:50]])
+    assert np.allclose(o.g["shs"][:50], expect, atol=2e-4)
+
+
+def test_solve_first_step_matches_scipy_direct_solve(orc, scenes):
+    """(J^T J) h = -J^T f solved by scipy's sparse LU equals the oracle's block LDL^T step."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    o = _session(scenes, n=4000, nodes=150, k=8)
+    blocks, types = scenes.cap_blocks(o.node_pos, lo=-0.3, hi=0.3)
+    o.set_blocks(blocks, types)
+    o.aim_translate([0.0, 0.0, 0.02])
+    I = np.tile(np.eye(3).reshape(-1), (o.M, 1)); Z = np.zeros((o.M, 3))
+    R, Cc, V, f, (m, n) = orc.jacobian(o.node_pos, o.nbr, o.anc_idx, o.anc_w, o.node_static, o.blocks, o.block_types, o.aim, False, I, Z)
+    J = sp.coo_matrix((V, (R, Cc)), shape=(m, n)).tocsc()
+    h = spl.spsolve((J.T @ J).tocsc(), -(J.T @ f))
+    rot, trans, st = orc.solve(o.node_pos, o.nbr, o.anc_idx, o.anc_w, o.node_static, o.blocks, o.block_types, o.aim, False, max_iters=1)
+    x1 = np.concatenate([rot, trans], 1).reshape(-1)
+    x0 = np.concatenate([I, Z], 1).reshape(-1)
+    assert np.allclose(x1 - x0, h, atol=1e-9)
+    assert np.isclose(f @ f, orc.energy(o.node_pos, o.nbr, o.anc_idx, o.anc_w, o.node_static, o.blocks, o.block_types, o.aim, False, I, Z))
+
+
+def test_excluded_nodes_keep_identity_and_static_flags(scenes):
+    o = _session(scenes, with_samples=True)
+    lo = np.nonzero(o.node_pos[:, 2] < -0.2)[0].astype(np.uint32)
+    hi = np.nonzero(o.node_pos[:, 2] > 0.3)[0].astype(np.uint32)
+    o.set_blocks([hi, lo], [1, -1])
+    assert o.gs_static.sum() > 0 and o.sample_static.sum() > 0 and o.gs_static.sum() < o.N
+    before = o.g["pos"].copy()
+    o.aim_translate([0, 0, 0.01])
+    o.step(False)
+    assert np.allclose(o.last_rot[lo], np.eye(3).reshape(-1)) and np.allclose(o.last_trans[lo], 0)
+    st = o.gs_static.astype(bool)
+    assert np.array_equal(o.g["pos"][st], before[st]) and not np.array_equal(o.g["pos"][~st], before[~st])
+
+
+def test_grid_invariants(scenes):
+    o = _session(scenes, with_samples=True)
+    G = o.G
+    assert o.cell_prefix[-1] == o.N and np.all(np.diff(o.gs_init_grid_idx) >= 0)      # Gaussians are in cell order
+    cnt = np.diff(np.concatenate([[0], o.fp_prefix]))
+    assert np.array_equal(np.nonzero(cnt)[0], o.valid) and len(o.sample_pos) == 64 * len(o.valid)
+    for c in o.valid[:50]:
+        b, e = (o.fp_prefix[c - 1] if c else 0), o.fp_prefix[c]
+        assert np.all(np.diff(o.lists[b:e]) > 0)                                       # ascending Gaussian index per cell
+    # every Gaussian sits in its own cell's list (padding >= 0)
+    for g in range(0, o.N, 97):
+        c = o.gs_init_grid_idx[g]; b, e = (o.fp_prefix[c - 1] if c else 0), o.fp_prefix[c]
+        assert g in o.lists[b:e]
+    # samples of a cell lie inside the cell
+    c = o.valid[0]; x, y, z = c // (G * G), (c // G) % G, c % G
+    lo = o.aabb[:3] + np.array([x, y, z]) * o.gstep
+    assert np.all(o.sample_pos[:64] > lo) and np.all(o.sample_pos[:64] < lo + o.gstep)
+    # undeformed adaptive LPF = (step/4)^2 * 0.2 * I  (GaussianView.cpp:3881)
+    assert np.allclose(o.ada_lpf[c].reshape(3, 3), np.eye(3) * (o.gstep / 4) ** 2 * 0.2, rtol=1e-3, atol=1e-12)
