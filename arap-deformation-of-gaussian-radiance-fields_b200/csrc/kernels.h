@@ -55,6 +55,7 @@ typedef struct ArapSolveGraph {
   const int* cin_grp;
   const int* cin_member;
   const int* cin_slot;
+  long long n_cin_entries;    // cin_off[M]
 } ArapSolveGraph;
 
 typedef struct ArapSolveParams {

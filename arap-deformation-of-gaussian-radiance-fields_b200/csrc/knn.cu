@@ -285,7 +285,7 @@ k_knn_fast(const float* __restrict__ queries, long long Q, int k, BucketGrid bg,
 #pragma unroll
             for (int j = 0; j < KQ; j++) {
               if (j < kq) {
-                if (cd == d[j]) tie = true;
+                if (cd == d[j] && cd != FLT_MAX) tie = true;  // empty slots hold FLT_MAX and must not count as ties
                 if (cd < d[j]) { const float td = d[j]; const int ti = id[j]; d[j] = cd; id[j] = ci; cd = td; ci = ti; }
               }
             }

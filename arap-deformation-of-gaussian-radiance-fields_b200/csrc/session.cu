@@ -171,7 +171,7 @@ struct arap_ctx {
   std::vector<std::vector<uint32_t>> blocks; std::vector<int> block_types;
   int n_active_entries = 0;
   // constraints (two variants prepared at set_blocks: per-node and centre)
-  struct ConSet { int n_groups = 0; DBuf<int> grp_off, grp_member, aim_off, aim_nodes, cin_off, cin_grp, cin_member, cin_slot; DBuf<float> grp_aim; };
+  struct ConSet { int n_groups = 0; long long n_entries = 0; DBuf<int> grp_off, grp_member, aim_off, aim_nodes, cin_off, cin_grp, cin_member, cin_slot; DBuf<float> grp_aim; };
   ConSet con[2];
   // solve
   DBuf<double> rot_d, trans_d, stats_d; DBuf<char> solve_ws; DBuf<char> node_xf; DBuf<float> node_q;
@@ -619,6 +619,7 @@ static int build_conset(arap_ctx* c, arap_ctx::ConSet& cs, bool on_center) {
     for (auto& e : per[i]) { cg.push_back(e[0]); cm.push_back(e[1]); csl.push_back(e[2]); }
     cin_off[i + 1] = (int)cg.size();
   }
+  cs.n_entries = (long long)cg.size();
   auto up = [&](DBuf<int>& d, std::vector<int>& v) { if (v.empty()) v.push_back(0); return upload(d, v.data(), v.size(), false, c->stream); };
   TRY(up(cs.grp_off, grp_off)); TRY(up(cs.grp_member, grp_member)); TRY(up(cs.aim_off, aim_off)); TRY(up(cs.aim_nodes, aim_nodes));
   TRY(up(cs.cin_off, cin_off)); TRY(up(cs.cin_grp, cg)); TRY(up(cs.cin_member, cm)); TRY(up(cs.cin_slot, csl));
@@ -729,7 +730,7 @@ extern "C" int arap_solve(arap_ctx* ctx, int on_center) {
   G.node_pos = ctx->node_pos.p; G.nbr = ctx->nbr.p; G.in_off = ctx->in_off.p; G.in_src = ctx->in_src.p; G.in_slot = ctx->in_slot.p;
   G.anc_idx = ctx->anc_idx.p; G.anc_w = ctx->anc_w.p; G.node_free = ctx->node_free.p; G.static_in_cnt = ctx->static_in_cnt.p;
   G.grp_off = cs.grp_off.p; G.grp_member = cs.grp_member.p; G.grp_aim = cs.grp_aim.p;
-  G.cin_off = cs.cin_off.p; G.cin_grp = cs.cin_grp.p; G.cin_member = cs.cin_member.p; G.cin_slot = cs.cin_slot.p;
+  G.cin_off = cs.cin_off.p; G.cin_grp = cs.cin_grp.p; G.cin_member = cs.cin_member.p; G.cin_slot = cs.cin_slot.p; G.n_cin_entries = cs.n_entries;
   ArapSolveParams P{ctx->prm.w_rot, ctx->prm.w_reg, ctx->prm.w_con, ctx->prm.max_gn_iters, ctx->prm.max_cg_iters, ctx->prm.cg_tol};
   TRY(ctx->solve_ws.alloc(arapk_solve_workspace_bytes(G.M, G.k, G.n_groups)));
   TRY(arapk_solve(&G, &P, ctx->solve_ws.p, ctx->solve_ws.n, ctx->rot_d.p, ctx->trans_d.p, ctx->stats_d.p, st));
