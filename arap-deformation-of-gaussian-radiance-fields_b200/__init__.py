@@ -40,7 +40,8 @@ class Params(C.Structure):
 
 class SolveStats(C.Structure):
     _fields_ = [("gn_iters", C.c_int), ("cg_iters", C.c_int), ("halvings", C.c_int), ("flags", C.c_int),
-                ("energy", C.c_double), ("normh", C.c_double), ("last_rel_residual", C.c_double)]
+                ("energy", C.c_double), ("normh", C.c_double), ("last_rel_residual", C.c_double),
+                ("phase_ns", C.c_double * 4), ("grid_blocks", C.c_int)]
 
 
 class GridInfo(C.Structure):
@@ -359,7 +360,7 @@ class Session:
         s = SolveStats()
         check(lib().arap_solve_stats_get(self._ctx, C.byref(s)))
         return dict(gn_iters=s.gn_iters, cg_iters=s.cg_iters, halvings=s.halvings, flags=s.flags, energy=s.energy,
-                    normh=s.normh, last_rel_residual=s.last_rel_residual)
+                    normh=s.normh, last_rel_residual=s.last_rel_residual, phase_ns=list(s.phase_ns), grid_blocks=s.grid_blocks)
 
     def apply(self):
         check(lib().arap_apply(self._ctx))

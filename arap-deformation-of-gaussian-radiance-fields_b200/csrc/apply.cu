@@ -15,6 +15,7 @@
 // so a warp reading neighbour j of 32 consecutive rows issues one 64 B and one
 // 256 B fully-coalesced request.
 #include "device_math.cuh"
+#include "sh_fast.cuh"
 #include "kernels.h"
 
 namespace arapgs {
@@ -205,7 +206,7 @@ k_fit_gaussians(long long N, const float* __restrict__ ends, const float* __rest
     }
     const Quat rq = quat_normalized(quat_mul(q, quat_inverse(oq)));
     float Rs[3][3]; quat_to_matrix(rq, Rs);
-    sh_rotate_flipped(Rs, s_sh + tid * SH_PITCH);
+    sh_rotate_flipped_fast(Rs, s_sh + tid * SH_PITCH);
   }
   __syncthreads();
   float* osh = shs + g0 * SH_FLOATS;
@@ -297,29 +298,33 @@ k_rotate_sample_shs(long long S, int k, const float* __restrict__ w, const uint1
     float last = 0.0f;
     const long long base = (s >> 5) * (long long)(k * 32) + (s & 31);
     for (int j = 0; j < k; j++) {
+      // Q_SlerpCUDA (cudakdtree.cu:113-148).  The reference mixes double ratios with float quaternions; here the
+      // common lerp branch (incremental steps: cos > 0.99995) runs in float, the sin branch keeps double ratios.
+      // Quaternions agree with the reference's to ~1e-7, far inside the sample-SH tolerance.
       const float cw = w[base + j * 32];
-      const float t = cw / (cw + last);
+      const float t = __fdividef(cw, cw + last);
       const float4 e = __ldg(q_xyzw + idx[base + j * 32]);
       Quat eq{e.w, e.x, e.y, e.z};
-      const float cf = wq.x * eq.x + wq.y * eq.y + wq.z * eq.z + wq.w * eq.w;
-      double cosa = (double)cf;
-      if (cosa < 0) { eq.x = -eq.x; eq.y = -eq.y; eq.z = -eq.z; eq.w = -eq.w; cosa = -cosa; }
-      double rA, rB; const double td = (double)t;
-      if (cosa > (double)0.99995f) { rA = 1.0 - td; rB = td; }
+      float cf = wq.x * eq.x + wq.y * eq.y + wq.z * eq.z + wq.w * eq.w;
+      if (cf < 0.0f) { eq.x = -eq.x; eq.y = -eq.y; eq.z = -eq.z; eq.w = -eq.w; cf = -cf; }
+      float rA, rB;
+      if (cf > 0.99995f) { rA = 1.0f - t; rB = t; }
       else {
+        const double cosa = (double)cf, td = (double)t;
         const double sina = sqrt(1.0 - cosa * cosa);
         const double ang = atan2(sina, cosa);
-        rA = sin((1.0 - td) * ang) / sina;
-        rB = sin(td * ang) / sina;
+        rA = (float)(sin((1.0 - td) * ang) / sina);
+        rB = (float)(sin(td * ang) / sina);
       }
       Quat l;
-      l.x = (float)(rA * wq.x + rB * eq.x); l.y = (float)(rA * wq.y + rB * eq.y);
-      l.z = (float)(rA * wq.z + rB * eq.z); l.w = (float)(rA * wq.w + rB * eq.w);
-      wq = quat_normalized(l);
+      l.x = fmaf(rA, wq.x, rB * eq.x); l.y = fmaf(rA, wq.y, rB * eq.y);
+      l.z = fmaf(rA, wq.z, rB * eq.z); l.w = fmaf(rA, wq.w, rB * eq.w);
+      const float inv = rsqrtf(quat_n2(l));
+      wq = Quat{l.w * inv, l.x * inv, l.y * inv, l.z * inv};
       last += cw;
     }
     float R[3][3]; quat_to_matrix(quat_normalized(wq), R);
-    sh_rotate_flipped(R, s_sh + tid * SH_PITCH);
+    sh_rotate_flipped_fast(R, s_sh + tid * SH_PITCH);
   }
   __syncthreads();
   float* osh = feature + s0 * SH_FLOATS;
@@ -369,6 +374,10 @@ static int ensure_sh_tables() {
   fill(2, h.u2, h.v2, h.w2);
   fill(3, h.u3, h.v3, h.w3);
   ARAP_CUDA_TRY(cudaMemcpyToSymbol(c_sh, &h, sizeof(h)));
+  ShCoefF f;
+  for (int i = 0; i < 25; i++) { const int m = i / 5 - 2; f.u2[i] = (float)h.u2[i]; f.v2[i] = (float)(h.v2[i] * ((m == 1 || m == -1) ? 1.4142135623730951 : 1.0)); f.w2[i] = (float)h.w2[i]; }
+  for (int i = 0; i < 49; i++) { const int m = i / 7 - 3; f.u3[i] = (float)h.u3[i]; f.v3[i] = (float)(h.v3[i] * ((m == 1 || m == -1) ? 1.4142135623730951 : 1.0)); f.w3[i] = (float)h.w3[i]; }
+  ARAP_CUDA_TRY(cudaMemcpyToSymbol(c_shf, &f, sizeof(f)));
   g_sh_ready = true;
   return ARAP_OK;
 }
@@ -444,17 +453,17 @@ extern "C" int arapk_static_flags(long long G, int group, int k, const uint16_t*
   return ARAP_OK;
 }
 
-extern "C" int arapk_sh_rotate_test(const float* R9, float* shs48_dev, cudaStream_t st);
 namespace arapgs {
-__global__ void k_sh_rotate_test(const float* R9, float* shs) {
+__global__ void k_sh_rotate_test(const float* R9, float* shs, int fast) {
   float R[3][3];
   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) R[i][j] = R9[3 * i + j];
-  sh_rotate_flipped(R, shs);
+  if (fast) sh_rotate_flipped_fast(R, shs); else sh_rotate_flipped(R, shs);
 }
 }  // namespace arapgs
-extern "C" int arapk_sh_rotate_test(const float* R9, float* shs48_dev, cudaStream_t st) {
+// fast = 0: the reference's exact rounding (double coefficient products); fast = 1: the float version the per-step kernels use
+extern "C" int arapk_sh_rotate_test(const float* R9, float* shs48_dev, int fast, cudaStream_t st) {
   int rc = ensure_sh_tables(); if (rc) return rc;
-  k_sh_rotate_test<<<1, 1, 0, st>>>(R9, shs48_dev);
+  k_sh_rotate_test<<<1, 1, 0, st>>>(R9, shs48_dev, fast);
   ARAP_KERNEL_CHECK();
   return ARAP_OK;
 }

@@ -38,7 +38,9 @@ __host__ __device__ __forceinline__ void static_for(F&& f) {
 
 // Per-node transform record consumed by the LBS kernels (built once per step
 // from the solver's x and the current node positions).  112 B, 16-B aligned:
-// seven LDG.128 per (point, neighbour) pair.
+// seven LDG.128 per (point, neighbour) pair.  The pitch is deliberately NOT a power
+// of two: with a 128-B pitch every lane of a gather hits the same L1 data banks
+// (measured: 2x slower LBS); 112 B spreads neighbouring node ids across banks.
 //   A : column-major 3x3 (reference DeformGraph::rot layout, Deform.hpp:29-36)
 //   c : trans + (double)pos        g : node position (float, for the float
 //                                      subtraction `cur - position`, Deform.hpp:240)

@@ -23,7 +23,7 @@ int arapk_rotate_sample_shs(long long S, int k, const float* w, const uint16_t* 
                             const uint8_t* is_static, float* feature, cudaStream_t st);
 int arapk_static_flags(long long G, int group, int k, const uint16_t* idx, const uint8_t* node_static, uint8_t* out,
                        cudaStream_t st);
-int arapk_sh_rotate_test(const float* R9, float* shs48_dev, cudaStream_t st);
+int arapk_sh_rotate_test(const float* R9, float* shs48_dev, int fast, cudaStream_t st);
 
 // ---- stage (b) FPS + kNN (knn.cu) -------------------------------------------
 int arapk_minmax(const float* pts, long long N, float* out6_dev, cudaStream_t st);
@@ -41,9 +41,8 @@ typedef struct ArapSolveGraph {
   int M, k, n_groups;
   const float* node_pos;      // M x 3, current node positions (device)
   const int* nbr;             // M x k out-neighbours (Node.Neighbor)
-  const int* in_off;          // M + 1: CSR of in-edges
-  const int* in_src;          // source node of each in-edge
-  const int* in_slot;         // slot of this node in the source's row
+  const int* in_off;          // M + 1: in-edges whose source node is free (row values land in u_in[in_off[q] ..])
+  const int* out_to_in;       // M x k: for edge (i, s) its slot in the destination's in-edge range, -1 if i is excluded
   const int* anc_idx;         // M x k: anchor vertex kNN row of each node
   const double* anc_w;        // M x k
   const uint8_t* node_free;   // M: 1 = unknown, 0 = excluded (identity)

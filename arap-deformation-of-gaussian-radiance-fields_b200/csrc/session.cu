@@ -161,7 +161,7 @@ struct arap_ctx {
   bool graph_ready = false;
   int M = 0, k = 0;
   std::vector<int> h_anchor, h_nbr, h_anc_idx;
-  DBuf<int> anchor, nbr, in_off, in_src, in_slot, anc_idx, static_in_cnt, active_mult, active_entries;
+  DBuf<int> anchor, nbr, in_off, out_to_in, anc_idx, static_in_cnt, active_mult, active_entries;
   DBuf<double> anc_w;
   DBuf<float> node_pos, node_next, node_rest, aim, center_tmp;
   DBuf<uint8_t> node_free, node_static;
@@ -486,14 +486,6 @@ static int finish_graph(arap_ctx* c, int k) {
     TRY(c->node_rows.idx.alloc(c->node_rows.entries())); TRY(c->node_rows.w.alloc(c->node_rows.entries()));
     k_rows_to_blocked<<<(M + 127) / 128, 128, 0, st>>>(M, k, idx_p.p, w_p.p, c->node_rows.idx.p, c->node_rows.w.p);
     ARAP_KERNEL_CHECK();
-    // in-edge CSR
-    std::vector<int> off(M + 1, 0), src((size_t)M * k), slot((size_t)M * k);
-    for (size_t e = 0; e < c->h_nbr.size(); e++) off[c->h_nbr[e] + 1]++;
-    for (int i = 0; i < M; i++) off[i + 1] += off[i];
-    std::vector<int> fill(off.begin(), off.end() - 1);
-    for (int i = 0; i < M; i++) for (int s = 0; s < k; s++) { const int q = c->h_nbr[(size_t)i * k + s]; src[fill[q]] = i; slot[fill[q]] = s; fill[q]++; }
-    TRY(upload(c->in_off, off.data(), off.size(), false, st)); TRY(upload(c->in_src, src.data(), src.size(), false, st));
-    TRY(upload(c->in_slot, slot.data(), slot.size(), false, st));
     ARAP_CUDA_TRY(cudaStreamSynchronize(st));
   }
   // skinning rows per query family (setupWeightsforEnds / forSamples / forMesh, GV:2833-2918)
@@ -646,6 +638,15 @@ extern "C" int arap_set_blocks(arap_ctx* ctx, int n_blocks, const int* block_off
   }
   std::vector<int> sic(M, 0);
   for (int i = 0; i < M; i++) if (is_static[i]) for (int s = 0; s < k; s++) sic[ctx->h_nbr[(size_t)i * k + s]]++;
+  // in-edges from free sources: E_reg rows of edge (i, s) are also delivered to slot out_to_in[i*k+s] of node nbr[i][s]
+  {
+    std::vector<int> off(M + 1, 0), o2i((size_t)M * k, -1);
+    for (int i = 0; i < M; i++) if (is_free[i]) for (int s = 0; s < k; s++) off[ctx->h_nbr[(size_t)i * k + s] + 1]++;
+    for (int i = 0; i < M; i++) off[i + 1] += off[i];
+    std::vector<int> fill(off.begin(), off.end() - 1);
+    for (int i = 0; i < M; i++) if (is_free[i]) for (int s = 0; s < k; s++) o2i[(size_t)i * k + s] = fill[ctx->h_nbr[(size_t)i * k + s]]++;
+    TRY(upload(ctx->in_off, off.data(), off.size(), false, st)); TRY(upload(ctx->out_to_in, o2i.data(), o2i.size(), false, st));
+  }
   ctx->n_active_entries = (int)entries.size();
   if (entries.empty()) entries.push_back(0);
   TRY(upload(ctx->node_static, is_static.data(), (size_t)M, false, st)); TRY(upload(ctx->node_free, is_free.data(), (size_t)M, false, st));
@@ -727,7 +728,7 @@ extern "C" int arap_solve(arap_ctx* ctx, int on_center) {
   }
   ArapSolveGraph G;
   G.M = ctx->M; G.k = ctx->k; G.n_groups = cs.n_groups;
-  G.node_pos = ctx->node_pos.p; G.nbr = ctx->nbr.p; G.in_off = ctx->in_off.p; G.in_src = ctx->in_src.p; G.in_slot = ctx->in_slot.p;
+  G.node_pos = ctx->node_pos.p; G.nbr = ctx->nbr.p; G.in_off = ctx->in_off.p; G.out_to_in = ctx->out_to_in.p;
   G.anc_idx = ctx->anc_idx.p; G.anc_w = ctx->anc_w.p; G.node_free = ctx->node_free.p; G.static_in_cnt = ctx->static_in_cnt.p;
   G.grp_off = cs.grp_off.p; G.grp_member = cs.grp_member.p; G.grp_aim = cs.grp_aim.p;
   G.cin_off = cs.cin_off.p; G.cin_grp = cs.cin_grp.p; G.cin_member = cs.cin_member.p; G.cin_slot = cs.cin_slot.p; G.n_cin_entries = cs.n_entries;
@@ -740,11 +741,13 @@ extern "C" int arap_solve(arap_ctx* ctx, int on_center) {
 
 extern "C" int arap_solve_stats_get(arap_ctx* ctx, arap_solve_stats* o) {
   GRAPH_CHECK(ctx); if (!o) return ARAP_ERR_INVALID;
-  ARAP_CUDA_TRY(cudaMemcpyAsync(ctx->stats_h, ctx->stats_d.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  ARAP_CUDA_TRY(cudaMemcpyAsync(ctx->stats_h, ctx->stats_d.p, 16 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   ARAP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   const double* s = ctx->stats_h;
   o->gn_iters = (int)s[0]; o->energy = s[1]; o->halvings = (int)s[2]; o->normh = s[3]; o->cg_iters = (int)s[4];
   o->last_rel_residual = s[5]; o->flags = (int)s[6];
+  for (int t = 0; t < 4; t++) o->phase_ns[t] = s[8 + t];
+  o->grid_blocks = (int)s[12];
   return ARAP_OK;
 }
 

@@ -4,23 +4,25 @@
 // CalcEnergyFunc  (reference Deform.cpp:77-581) and putFreeInputs
 // (Deform.hpp:140-151).  Same energy, same Jacobian, same Gauss-Newton loop
 // (start from identity, <= 30 iterations, step halving, |h| < (|x|+1e-6)1e-6
-// stop) — the sparse Cholesky of J^T J is replaced by a matrix-free,
-// block-Jacobi (12x12) preconditioned conjugate gradient in double, run to a
-// residual that makes every iterate agree with the direct solve.
+// stop) — the sparse Cholesky of J^T J is replaced by a matrix-free, Jacobi
+// preconditioned conjugate gradient in double, run to a residual that makes
+// every iterate agree with the direct solve.
 //
-// One persistent cooperative kernel runs the whole solve.  J is never stored:
-//   * E_reg and E_con rows act identically on the three components j of a node's
-//     unknowns, each on the 4-vector q_ij = (A[j,0], A[j,1], A[j,2], t_j); only
-//     E_rot couples the components.  Vectors are therefore stored as
-//     [node][component][4] and one QUAD of lanes (3 active) owns a node.
-//   * J^T J p runs in two phases with one grid barrier each: u = J p by the row
-//     owner (rows of an edge live with its source node), y = J^T u gathered by the
-//     column owner.  The barriers also carry the CG dot products (p.Hp = |Jp|^2).
-//   * per-edge constants (float position differences, Deform.cpp:254-256) and
-//     constraint coefficients are computed once per solve.
+// One persistent cooperative kernel runs the whole solve.  The work per PCG
+// iteration is tiny (a few MFLOP), so the design goal is latency: every phase
+// is "one thread per row" or "one thread per unknown" with short, independent
+// load chains, and there are exactly two grid barriers per iteration, which
+// also carry the dot products:
+//   phase A  u = J p     one thread per E_reg row (node, slot, component), per node (E_rot), per constraint row
+//   phase B  y = J^T u   one thread per unknown; + x/r/z updates (Jacobi: z = r / diag)
+// J is never stored.  E_reg / E_con rows act identically on the three components j of a node's unknowns, each
+// on the 4-vector (A[j,0], A[j,1], A[j,2], t_j); vectors are stored [node][component][4].  Row values of an edge
+// are written twice: at the source (u_reg, its own gather) and into the destination's in-edge slot (u_in), so
+// both gathers are contiguous.  Per-edge constants (float position differences, Deform.cpp:254-256) and
+// constraint coefficients are computed once per solve.
 //
-// Reference unknown layout (Deform.hpp:29-36): x[0..8] = A column-major, x[9..11] = t,
-// i.e. A[j,c] = x[j + 3c].  Non-free (excluded) nodes keep identity.
+// Reference unknown layout (Deform.hpp:29-36): x[0..8] = A column-major, x[9..11] = t, i.e. A[j,c] = x[j + 3c].
+// Non-free (excluded) nodes keep identity and carry no unknowns.
 #include <cooperative_groups.h>
 #include "common.cuh"
 #include "kernels.h"
@@ -29,19 +31,15 @@ namespace cg = cooperative_groups;
 
 namespace arapgs {
 
-constexpr int SOLVE_THREADS = 256;
-constexpr int QUADS_PER_BLOCK = SOLVE_THREADS / 4;
-constexpr int TILE = 16;                              // D-block build / inversion
-constexpr int TILES_PER_BLOCK = SOLVE_THREADS / TILE;
+constexpr int SOLVE_THREADS = 1024;
 constexpr int NRED = 3;
 
 struct SolveDev {
-  int M, k, n_groups, n_entries;
+  int M, k, n_groups;
   const float* node_pos;      // M x 3
   const int* nbr;             // M x k
-  const int* in_off;          // M + 1
-  const int* in_src;
-  const int* in_slot;
+  const int* in_off;          // M + 1: in-edges from FREE sources
+  const int* out_to_in;       // M x k: slot of edge (i,s) in u_in, or -1
   const int* anc_idx;         // M x k
   const double* anc_w;        // M x k
   const uint8_t* node_free;   // M
@@ -49,7 +47,7 @@ struct SolveDev {
   const int* grp_off;         // n_groups + 1 -> members
   const int* grp_member;
   const float* grp_aim;       // n_groups x 3
-  const int* cin_off;         // M + 1 -> (group, member, slot) entries touching the node, sorted by group
+  const int* cin_off;         // M + 1 -> constraint entries touching the node, sorted by group
   const int* cin_grp;
   const int* cin_member;
   const int* cin_slot;
@@ -57,11 +55,13 @@ struct SolveDev {
   int max_gn, max_cg;
   double cg_tol;
   // work (double).  Vectors: [M][3][4]
-  double *x, *h, *r, *z, *p0, *p1, *dinv /* M x 144, quad ordering */, *bedge /* M x k x 4 */, *ccoef /* cin entries x 4 */;
-  double *u_reg /* M x k x 3 */, *u_con /* groups x 3 */;
+  double *x, *h, *r, *z, *p0, *p1, *dinv, *bedge /* M x k x 4 */, *ccoef /* cin entries x 4 */;
+  double *u_reg /* M x k x 3 */, *u_in /* in-edges x 3 */, *u_con /* groups x 3 */;
   double* partial;             // 2 x gridDim x NRED
   double *rot_out, *trans_out, *stats;
 };
+
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
 // ---- grid-wide deterministic sum of NRED scalars; doubles as the phase barrier
 __device__ __forceinline__ void grid_reduce(cg::grid_group& grid, const SolveDev& S, int& phase, double (&v)[NRED]) {
@@ -124,11 +124,10 @@ __device__ __forceinline__ double ldcomb1(const double* va, const double* vb, do
   return vb ? fma(s, vb[o], va[o]) : va[o];
 }
 
-// E_rot rows for a node with rows A0,A1,A2 (current x) applied to direction rows P0,P1,P2:
-// u0..2 = w (c_a . pc_b + c_b . pc_a) for column pairs (0,1),(0,2),(1,2); u3+c = 2 w (c_c . pc_c)   (Deform.cpp:186-220)
+// E_rot rows for a node with rows A0,A1,A2 (current x) applied to direction rows P0,P1,P2 (Deform.cpp:186-220):
+// u0..2 = w (c_a . pc_b + c_b . pc_a) for column pairs (0,1),(0,2),(1,2); u3+c = 2 w (c_c . pc_c).  D4 fields a,b,c = columns.
 __device__ __forceinline__ void rot_rows_lin(const D4& A0, const D4& A1, const D4& A2, const D4& P0, const D4& P1, const D4& P2,
                                              double w, double (&u)[6]) {
-  // column c of A = (A0.c, A1.c, A2.c); D4 fields a,b,c = columns 0,1,2
   const double a0p1 = fma(A0.a, P0.b, fma(A1.a, P1.b, A2.a * P2.b)), a1p0 = fma(A0.b, P0.a, fma(A1.b, P1.a, A2.b * P2.a));
   const double a0p2 = fma(A0.a, P0.c, fma(A1.a, P1.c, A2.a * P2.c)), a2p0 = fma(A0.c, P0.a, fma(A1.c, P1.a, A2.c * P2.a));
   const double a1p2 = fma(A0.b, P0.c, fma(A1.b, P1.c, A2.b * P2.c)), a2p1 = fma(A0.c, P0.b, fma(A1.c, P1.b, A2.c * P2.b));
@@ -146,331 +145,200 @@ __device__ __forceinline__ void rot_rows_res(const D4& A0, const D4& A1, const D
   f[4] = w * (fma(A0.b, A0.b, fma(A1.b, A1.b, A2.b * A2.b)) - 1.0);
   f[5] = w * (fma(A0.c, A0.c, fma(A1.c, A1.c, A2.c * A2.c)) - 1.0);
 }
-// (Jrot^T u) restricted to row j of A: needs only the node's own row Aj
-__device__ __forceinline__ void rot_rows_t(const D4& Aj, double w, const double (&u)[6], D4& y) {
-  y.a = fma(w, fma(u[0], Aj.b, fma(u[1], Aj.c, 2.0 * u[3] * Aj.a)), y.a);
-  y.b = fma(w, fma(u[0], Aj.a, fma(u[2], Aj.c, 2.0 * u[4] * Aj.b)), y.b);
-  y.c = fma(w, fma(u[1], Aj.a, fma(u[2], Aj.b, 2.0 * u[5] * Aj.c)), y.c);
+// entry c (< 3) of (Jrot^T u) on row j of A, whose own row is Aj
+__device__ __forceinline__ double rot_rows_t(const D4& Aj, double w, const double (&u)[6], int c) {
+  if (c == 0) return w * fma(u[0], Aj.b, fma(u[1], Aj.c, 2.0 * u[3] * Aj.a));
+  if (c == 1) return w * fma(u[0], Aj.a, fma(u[2], Aj.c, 2.0 * u[4] * Aj.b));
+  return w * fma(u[1], Aj.a, fma(u[2], Aj.b, 2.0 * u[5] * Aj.c));
 }
 
 // ---------------------------------------------------------------------------
-// Row phases (one quad per item; lanes 0..2 = component j)
+// Row phase.  MODE 0: nonlinear residual f(va + sc*vb)  (CalcEnergyFunc, Deform.cpp:378-581)
+//             MODE 1: u = J v, v = va + sc*vb, Jrot at S.x; v is also stored to vstore (the new search direction)
+// Returns this thread's sum of squares.
 // ---------------------------------------------------------------------------
-// LIN: u = J v with v = va + sc*vb (Jrot at S.x); own v stored to vstore.  Returns this lane's sum of squares.
-// K > 0: compile-time neighbour count, so the k neighbour gathers are issued as one batch (latency, not bandwidth,
-// bounds this kernel).
-template <int K>
-__device__ __forceinline__ double rows_lin(const SolveDev& S, int gquad, int nquads, int j, const double* va, const double* vb,
-                                           double sc, double* vstore) {
-  constexpr int KK = K > 0 ? K : KNN_MAX;
+template <int K, int MODE>
+__device__ __forceinline__ double row_phase(const SolveDev& S, int gthread, int nthreads, const double* va, const double* vb,
+                                            double sc, double* vstore) {
   const int M = S.M, k = K > 0 ? K : S.k;
+  const int k3 = 3 * k;
   double sq = 0.0;
-  for (int item = gquad; item < M + S.n_groups; item += nquads) {
-    if (j > 2) continue;
-    if (item < M) {
-      const int i = item;
-      if (!S.node_free[i]) continue;
-      const size_t o = ((size_t)i * 3 + j) * 4;
-      const D4 v = ldcomb(va, vb, sc, o);
-      if (vstore) st4(vstore + o, v);
-      const double* be = S.bedge + (size_t)i * k * 4;
-      double* ur = S.u_reg + (size_t)i * k * 3 + j;
-      int q[KK]; double tqa[KK], tqb[KK]; uint8_t fr[KK];
-#pragma unroll
-      for (int s = 0; s < KK; s++) q[s] = (s < k) ? S.nbr[i * k + s] : i;
-#pragma unroll
-      for (int s = 0; s < KK; s++) {
-        const size_t oq = ((size_t)q[s] * 3 + j) * 4 + 3;
-        fr[s] = S.node_free[q[s]];
-        tqa[s] = va[oq];
-        tqb[s] = vb ? vb[oq] : 0.0;
-      }
-#pragma unroll
-      for (int s = 0; s < KK; s++) {
-        if (s < k) {
-          const D4 b = ld4(be + 4 * s);
-          const double tq = fr[s] ? fma(sc, tqb[s], tqa[s]) : 0.0;
-          const double val = S.w_reg * ((fma(v.c, b.c, fma(v.b, b.b, v.a * b.a)) + v.d) - tq);
-          ur[3 * s] = val;
-          sq = fma(val, val, sq);
-        }
-      }
-      {  // static-side rows: one per (excluded node, slot) pointing here (Deform.cpp:268-297)
-        const double val = S.w_reg * v.d;
-        sq = fma((double)S.static_in_cnt[i] * val, val, sq);
-      }
-      if (j == 0) {
-        const size_t ob = (size_t)i * 12;
-        const D4 A0 = ld4(S.x + ob), A1 = ld4(S.x + ob + 4), A2 = ld4(S.x + ob + 8);
-        const D4 P0 = v, P1 = ldcomb(va, vb, sc, ob + 4), P2 = ldcomb(va, vb, sc, ob + 8);
-        double u[6]; rot_rows_lin(A0, A1, A2, P0, P1, P2, S.w_rot, u);
-#pragma unroll
-        for (int t = 0; t < 6; t++) sq = fma(u[t], u[t], sq);
-      }
+  // --- E_reg rows: (i, s, j)
+  for (int t = gthread; t < M * k3; t += nthreads) {
+    const int i = t / k3, rem = t - i * k3, s = rem / 3, j = rem - 3 * s;
+    if (!S.node_free[i]) continue;
+    const int e = i * k + s;
+    const int q = S.nbr[e];
+    const int slot = S.out_to_in[e];
+    const size_t o = ((size_t)i * 3 + j) * 4;
+    const D4 v = ldcomb(va, vb, sc, o);
+    double tq = 0.0;
+    if (S.node_free[q]) tq = ldcomb1(va, vb, sc, ((size_t)q * 3 + j) * 4 + 3);
+    double val;
+    if (MODE == 1) {
+      const D4 b = ld4(S.bedge + (size_t)e * 4);
+      val = S.w_reg * ((fma(v.c, b.c, fma(v.b, b.b, v.a * b.a)) + v.d) - tq);
+      if (s == 0 && vstore) st4(vstore + o, v);
     } else {
-      const int g = item - M;
+      // mat*(gk-gj) + gj + tj - gk - tk with double differences (Deform.cpp:444-448)
+      const double gi0 = S.node_pos[3 * i], gi1 = S.node_pos[3 * i + 1], gi2 = S.node_pos[3 * i + 2];
+      const double gq0 = S.node_pos[3 * q], gq1 = S.node_pos[3 * q + 1], gq2 = S.node_pos[3 * q + 2];
+      const double gij = j == 0 ? gi0 : j == 1 ? gi1 : gi2, gqj = j == 0 ? gq0 : j == 1 ? gq1 : gq2;
+      val = S.w_reg * ((((fma(v.c, gq2 - gi2, fma(v.b, gq1 - gi1, v.a * (gq0 - gi0))) + gij) + v.d) - gqj) - tq);
+    }
+    S.u_reg[(size_t)e * 3 + j] = val;
+    if (slot >= 0) S.u_in[(size_t)slot * 3 + j] = val;
+    sq = fma(val, val, sq);
+    if (s == 0) {  // static-side rows: one per (excluded node, slot) pointing here (Deform.cpp:268-297, 458-482)
+      const double sv = S.w_reg * v.d;
+      sq = fma((double)S.static_in_cnt[i] * sv, sv, sq);
+    }
+  }
+  // --- E_rot rows: one thread per node.  The short extra loops are dealt from the far end of the grid so they do
+  // not pile onto the blocks that also own the constraint rows (barrier wait = slowest block).
+  for (int i = nthreads - 1 - gthread; i < M; i += nthreads) {
+    if (!S.node_free[i]) continue;
+    const size_t ob = (size_t)i * 12;
+    double u[6];
+    if (MODE == 1) {
+      const D4 A0 = ld4(S.x + ob), A1 = ld4(S.x + ob + 4), A2 = ld4(S.x + ob + 8);
+      const D4 P0 = ldcomb(va, vb, sc, ob), P1 = ldcomb(va, vb, sc, ob + 4), P2 = ldcomb(va, vb, sc, ob + 8);
+      rot_rows_lin(A0, A1, A2, P0, P1, P2, S.w_rot, u);
+    } else {
+      const D4 A0 = ldcomb(va, vb, sc, ob), A1 = ldcomb(va, vb, sc, ob + 4), A2 = ldcomb(va, vb, sc, ob + 8);
+      rot_rows_res(A0, A1, A2, S.w_rot, u);
+    }
+#pragma unroll
+    for (int t = 0; t < 6; t++) sq = fma(u[t], u[t], sq);
+  }
+  // --- constraint rows: one 16-lane team per (group, component); lane = neighbour slot of the member's anchor row
+  {
+    const int l16 = threadIdx.x & 15;
+    const unsigned tmask = 0xFFFFu << (threadIdx.x & 16);
+    const int nteams = nthreads >> 4;
+    int team = (gthread >> 4) + (nteams >> 1);   // start in the middle of the grid (see E_rot note)
+    if (team >= nteams) team -= nteams;
+    for (int t = team; t < 3 * S.n_groups; t += nteams) {
+      const int g = t / 3, j = t - 3 * g;
+      const int mb = S.grp_off[g], me = S.grp_off[g + 1];
       double acc = 0.0;
-      for (int m = S.grp_off[g]; m < S.grp_off[g + 1]; m++) {
+      for (int m = mb; m < me; m++) {
         const int c = S.grp_member[m];
-        const float vc0 = S.node_pos[3 * c], vc1 = S.node_pos[3 * c + 1], vc2 = S.node_pos[3 * c + 2];
-        int q[KK]; double wv[KK];
-#pragma unroll
-        for (int s = 0; s < KK; s++) { q[s] = (s < k) ? S.anc_idx[c * k + s] : c; wv[s] = (s < k) ? S.w_con * S.anc_w[c * k + s] : 0.0; }
-#pragma unroll
-        for (int s = 0; s < KK; s++) {
-          if (s < k && S.node_free[q[s]]) {
-            const double e0 = (double)(vc0 - S.node_pos[3 * q[s]]), e1 = (double)(vc1 - S.node_pos[3 * q[s] + 1]), e2 = (double)(vc2 - S.node_pos[3 * q[s] + 2]);  // Deform.cpp:325-327
-            const D4 v = ldcomb(va, vb, sc, ((size_t)q[s] * 3 + j) * 4);
-            acc = fma(wv[s], fma(v.c, e2, fma(v.b, e1, v.a * e0)) + v.d, acc);
+        if (l16 < k) {
+          const int q = S.anc_idx[c * k + l16];
+          const double wei = S.anc_w[c * k + l16];
+          const float vc0 = S.node_pos[3 * c], vc1 = S.node_pos[3 * c + 1], vc2 = S.node_pos[3 * c + 2];
+          if (!S.node_free[q]) {
+            if (MODE == 0) acc = fma(wei, j == 0 ? (double)vc0 : j == 1 ? (double)vc1 : (double)vc2, acc);
+          } else {
+            const float gq0 = S.node_pos[3 * q], gq1 = S.node_pos[3 * q + 1], gq2 = S.node_pos[3 * q + 2];
+            const D4 v = ldcomb(va, vb, sc, ((size_t)q * 3 + j) * 4);
+            if (MODE == 1) {
+              const double e0 = (double)(vc0 - gq0), e1 = (double)(vc1 - gq1), e2 = (double)(vc2 - gq2);  // float differences, Deform.cpp:325-327
+              acc = fma(S.w_con * wei, fma(v.c, e2, fma(v.b, e1, v.a * e0)) + v.d, acc);
+            } else {
+              const double gqj = j == 0 ? (double)gq0 : j == 1 ? (double)gq1 : (double)gq2;
+              acc = fma(wei, (fma(v.c, (double)vc2 - (double)gq2, fma(v.b, (double)vc1 - (double)gq1, v.a * ((double)vc0 - (double)gq0))) + gqj) + v.d, acc);
+            }
           }
         }
       }
-      S.u_con[(size_t)g * 3 + j] = acc;
-      sq = fma(acc, acc, sq);
-    }
-  }
-  return sq;
-}
-
-// RES: nonlinear residual f(xa + sc*xb) (CalcEnergyFunc, Deform.cpp:378-581) into the row buffers.
-__device__ __forceinline__ double rows_res(const SolveDev& S, int gquad, int nquads, int j, const double* va, const double* vb, double sc) {
-  const int M = S.M, k = S.k;
-  double sq = 0.0;
-  for (int item = gquad; item < M + S.n_groups; item += nquads) {
-    if (j > 2) continue;
-    if (item < M) {
-      const int i = item;
-      if (!S.node_free[i]) continue;
-      const size_t o = ((size_t)i * 3 + j) * 4;
-      const D4 v = ldcomb(va, vb, sc, o);
-      const double gi0 = S.node_pos[3 * i], gi1 = S.node_pos[3 * i + 1], gi2 = S.node_pos[3 * i + 2];
-      const double gij = j == 0 ? gi0 : j == 1 ? gi1 : gi2;
-      double* ur = S.u_reg + (size_t)i * k * 3 + j;
-      for (int s = 0; s < k; s++) {
-        const int q = S.nbr[i * k + s];
-        const double gq0 = S.node_pos[3 * q], gq1 = S.node_pos[3 * q + 1], gq2 = S.node_pos[3 * q + 2];
-        const double gqj = j == 0 ? gq0 : j == 1 ? gq1 : gq2;
-        double tq = 0.0;
-        if (S.node_free[q]) tq = ldcomb1(va, vb, sc, ((size_t)q * 3 + j) * 4 + 3);
-        // mat*(gk-gj) + gj + tj - gk - tk with double differences (Deform.cpp:444-448)
-        const double val = S.w_reg * ((((fma(v.c, gq2 - gi2, fma(v.b, gq1 - gi1, v.a * (gq0 - gi0))) + gij) + v.d) - gqj) - tq);
-        ur[3 * s] = val;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(tmask, acc, o, 16);
+      if (l16 == 0) {
+        const double val = MODE == 1 ? acc : S.w_con * (acc - (double)(me - mb) * (double)S.grp_aim[3 * g + j]);
+        S.u_con[t] = val;
         sq = fma(val, val, sq);
       }
-      {
-        const double val = S.w_reg * v.d;
-        sq = fma((double)S.static_in_cnt[i] * val, val, sq);
-      }
-      if (j == 0) {
-        const size_t ob = (size_t)i * 12;
-        const D4 A1 = ldcomb(va, vb, sc, ob + 4), A2 = ldcomb(va, vb, sc, ob + 8);
-        double f[6]; rot_rows_res(v, A1, A2, S.w_rot, f);
-#pragma unroll
-        for (int t = 0; t < 6; t++) sq = fma(f[t], f[t], sq);
-      }
-    } else {
-      const int g = item - M;
-      double acc = 0.0;
-      const int mb = S.grp_off[g], me = S.grp_off[g + 1];
-      for (int m = mb; m < me; m++) {
-        const int c = S.grp_member[m];
-        const double vc0 = S.node_pos[3 * c], vc1 = S.node_pos[3 * c + 1], vc2 = S.node_pos[3 * c + 2];
-        const double vcj = j == 0 ? vc0 : j == 1 ? vc1 : vc2;
-        for (int s = 0; s < k; s++) {
-          const int q = S.anc_idx[c * k + s];
-          const double wei = S.anc_w[c * k + s];
-          if (!S.node_free[q]) { acc = fma(wei, vcj, acc); continue; }
-          const double gq0 = S.node_pos[3 * q], gq1 = S.node_pos[3 * q + 1], gq2 = S.node_pos[3 * q + 2];
-          const double gqj = j == 0 ? gq0 : j == 1 ? gq1 : gq2;
-          const D4 v = ldcomb(va, vb, sc, ((size_t)q * 3 + j) * 4);
-          acc = fma(wei, (fma(v.c, vc2 - gq2, fma(v.b, vc1 - gq1, v.a * (vc0 - gq0))) + gqj) + v.d, acc);
-        }
-      }
-      const double val = S.w_con * (acc - (double)(me - mb) * (double)S.grp_aim[3 * g + j]);
-      S.u_con[(size_t)g * 3 + j] = val;
-      sq = fma(val, val, sq);
     }
   }
   return sq;
 }
 
-// y = (J^T u) for (node i, component j).  urot: the node's six E_rot row values; vt: t_j of the vector J was applied to
-// (static-side rows).
+// (J^T u) for unknown (i, j, c).  urot: the node's six E_rot row values; vt: this unknown's own value in the vector J
+// was applied to (only used for c == 3: static-side rows).
 template <int K>
-__device__ __forceinline__ D4 gather_jt(const SolveDev& S, int i, int j, const double (&urot)[6], double vt) {
+__device__ __forceinline__ double gather_jt(const SolveDev& S, int i, int j, int c, const D4& Aj, const double (&urot)[6], double vt) {
   constexpr int KK = K > 0 ? K : KNN_MAX;
   const int k = K > 0 ? K : S.k;
-  D4 y{0.0, 0.0, 0.0, 0.0};
-  const D4 Aj = ld4(S.x + ((size_t)i * 3 + j) * 4);
-  rot_rows_t(Aj, S.w_rot, urot, y);
-  const double* be = S.bedge + (size_t)i * k * 4;
   const double* ur = S.u_reg + (size_t)i * k * 3 + j;
-  const int ib = S.in_off[i], ie = S.in_off[i + 1];
+  double y = 0.0;
+  if (c < 3) {
+    y = rot_rows_t(Aj, S.w_rot, urot, c);
+    const double* be = S.bedge + (size_t)i * k * 4 + c;
+    double acc = 0.0;
 #pragma unroll
-  for (int s = 0; s < KK; s++) {
-    if (s < k) {
-      const double wu = S.w_reg * ur[3 * s];
-      const D4 b = ld4(be + 4 * s);
-      y.a = fma(b.a, wu, y.a); y.b = fma(b.b, wu, y.b); y.c = fma(b.c, wu, y.c); y.d += wu;
-    }
+    for (int s = 0; s < KK; s++) if (s < k) acc = fma(be[4 * s], ur[3 * s], acc);
+    y = fma(S.w_reg, acc, y);
+  } else {
+    double acc = 0.0;
+#pragma unroll
+    for (int s = 0; s < KK; s++) if (s < k) acc += ur[3 * s];
+    const double* ui = S.u_in + j;
+    const int ib = S.in_off[i], ie = S.in_off[i + 1];
+    double acc2 = 0.0;
+    for (int t = ib; t < ie; t++) acc2 += ui[(size_t)t * 3];
+    y = S.w_reg * (acc - acc2);
+    y = fma((double)S.static_in_cnt[i] * S.w_reg * S.w_reg, vt, y);
   }
-  for (int t0 = ib; t0 < ie; t0 += 8) {   // in-edges, 8 at a time so the dependent gathers overlap
-    int src[8], sl[8]; double uu[8];
+  const int cb = S.cin_off[i], ce = S.cin_off[i + 1];
+  for (int t0 = cb; t0 < ce; t0 += 4) {   // 4 at a time so the dependent u_con gathers overlap
+    double cc[4], uu[4]; int gg[4];
 #pragma unroll
-    for (int t = 0; t < 8; t++) { const bool ok = t0 + t < ie; src[t] = ok ? S.in_src[t0 + t] : -1; sl[t] = ok ? S.in_slot[t0 + t] : 0; }
+    for (int t = 0; t < 4; t++) { const bool ok = t0 + t < ce; gg[t] = ok ? S.cin_grp[t0 + t] : -1; cc[t] = ok ? S.ccoef[(size_t)(t0 + t) * 4 + c] : 0.0; }
 #pragma unroll
-    for (int t = 0; t < 8; t++) uu[t] = (src[t] >= 0 && S.node_free[src[t]]) ? S.u_reg[((size_t)src[t] * k + sl[t]) * 3 + j] : 0.0;
+    for (int t = 0; t < 4; t++) uu[t] = gg[t] >= 0 ? S.u_con[(size_t)gg[t] * 3 + j] : 0.0;
 #pragma unroll
-    for (int t = 0; t < 8; t++) y.d = fma(-S.w_reg, uu[t], y.d);
-  }
-  y.d = fma((double)S.static_in_cnt[i] * S.w_reg * S.w_reg, vt, y.d);
-  for (int t = S.cin_off[i]; t < S.cin_off[i + 1]; t++) {
-    const D4 c = ld4(S.ccoef + (size_t)t * 4);
-    const double u = S.u_con[(size_t)S.cin_grp[t] * 3 + j];
-    y.a = fma(c.a, u, y.a); y.b = fma(c.b, u, y.b); y.c = fma(c.c, u, y.c); y.d = fma(c.d, u, y.d);
+    for (int t = 0; t < 4; t++) y = fma(cc[t], uu[t], y);
   }
   return y;
 }
 
-// z = Dinv r for one node; each lane holds its component's 4 residual entries.
-__device__ __forceinline__ D4 apply_dinv(const SolveDev& S, int i, int j, unsigned qmask, const D4& r) {
-  D4 z{0.0, 0.0, 0.0, 0.0};
-  const double* Di = S.dinv + (size_t)i * 144 + (size_t)(j < 3 ? j : 0) * 48;  // rows 4j..4j+3
+// diagonal of J^T J for unknown (i, j, c)
+template <int K>
+__device__ __forceinline__ double diag_jtj(const SolveDev& S, int i, int j, int c, const D4& A0, const D4& A1, const D4& A2) {
+  constexpr int KK = K > 0 ? K : KNN_MAX;
+  const int k = K > 0 ? K : S.k;
+  double d = 0.0;
+  if (c < 3) {
+    // E_rot column of A[j][c]: two pair rows (entries A[j][other columns]) and the norm row of column c (2 A[j][c])
+    const D4 Aj = j == 0 ? A0 : j == 1 ? A1 : A2;
+    const double w2 = S.w_rot * S.w_rot;
+    const double o1 = c == 0 ? Aj.b : Aj.a, o2 = c == 2 ? Aj.b : Aj.c, own = c == 0 ? Aj.a : c == 1 ? Aj.b : Aj.c;
+    d = w2 * (o1 * o1 + o2 * o2 + 4.0 * own * own);
+    const double* be = S.bedge + (size_t)i * k * 4 + c;
+    double acc = 0.0;
 #pragma unroll
-  for (int jj = 0; jj < 3; jj++) {
-    const double ra = __shfl_sync(qmask, r.a, jj, 4), rb = __shfl_sync(qmask, r.b, jj, 4);
-    const double rc = __shfl_sync(qmask, r.c, jj, 4), rd = __shfl_sync(qmask, r.d, jj, 4);
-    const D4 d0 = ld4(Di + 0 * 12 + 4 * jj), d1 = ld4(Di + 1 * 12 + 4 * jj), d2 = ld4(Di + 2 * 12 + 4 * jj), d3 = ld4(Di + 3 * 12 + 4 * jj);
-    z.a = fma(d0.a, ra, fma(d0.b, rb, fma(d0.c, rc, fma(d0.d, rd, z.a))));
-    z.b = fma(d1.a, ra, fma(d1.b, rb, fma(d1.c, rc, fma(d1.d, rd, z.b))));
-    z.c = fma(d2.a, ra, fma(d2.b, rb, fma(d2.c, rc, fma(d2.d, rd, z.c))));
-    z.d = fma(d3.a, ra, fma(d3.b, rb, fma(d3.c, rc, fma(d3.d, rd, z.d))));
+    for (int s = 0; s < KK; s++) if (s < k) acc = fma(be[4 * s], be[4 * s], acc);
+    d = fma(S.w_reg * S.w_reg, acc, d);
+  } else {
+    // own rows (w each), in-edges from free sources (-w each), static-side rows (-w each)
+    d = S.w_reg * S.w_reg * (double)(k + (S.in_off[i + 1] - S.in_off[i]) + S.static_in_cnt[i]);
   }
-  return z;
-}
-
-// ---- 12x12 diagonal block of J^T J for node i (reference index order in shared memory), Cholesky inverse stored in
-// quad order: index (j,c) -> 4j + c, reference index of (j,c) = (c < 3) ? j + 3c : 9 + j.
-__device__ __forceinline__ int ref_index(int qi) { const int j = qi >> 2, c = qi & 3; return c < 3 ? j + 3 * c : 9 + j; }
-
-__device__ __forceinline__ double jrot_ref(const double* x12 /* [3][4] quad layout */, int r, int c, double w) {
-  // reference column index c = 3*col + t  (entry A[t][col]); a(col,t) = x12[t*4 + col]
-  const int col = c / 3, t = c - 3 * col;
-  if (r < 3) {
-    const int ca = (r == 2) ? 1 : 0, cb = (r == 0) ? 1 : 2;
-    if (col == ca) return x12[t * 4 + cb] * w;
-    if (col == cb) return x12[t * 4 + ca] * w;
-    return 0.0;
+  int cur = -1; double sa = 0.0;
+  for (int t = S.cin_off[i]; t < S.cin_off[i + 1]; t++) {   // per group the node's aggregated entry (setFromTriplets sums duplicates)
+    const int g = S.cin_grp[t];
+    if (g != cur) { d = fma(sa, sa, d); sa = 0.0; cur = g; }
+    sa += S.ccoef[(size_t)t * 4 + c];
   }
-  return (col == r - 3) ? 2.0 * x12[t * 4 + col] * w : 0.0;
-}
-
-__device__ __forceinline__ void build_dinv(const SolveDev& S, cg::thread_block_tile<TILE>& T, int i, double* D /*144*/, double* Jr /*54*/) {
-  const int k = S.k, lane = T.thread_rank();
-  const double* a = S.x + (size_t)i * 12;
-  for (int t = lane; t < 144; t += TILE) D[t] = 0.0;
-  for (int t = lane; t < 54; t += TILE) Jr[t] = jrot_ref(a, t / 9, t % 9, S.w_rot);
-  T.sync();
-  if (lane < 9) {
-    for (int cp = 0; cp < 9; cp++) {
-      double s = 0.0;
-#pragma unroll
-      for (int r = 0; r < 6; r++) s = fma(Jr[r * 9 + cp], Jr[r * 9 + lane], s);
-      D[cp * 12 + lane] += s;
-    }
-  }
-  T.sync();
-  {
-    const int pa = lane >> 2, pb = lane & 3;
-    double val = 0.0;
-    const double* be = S.bedge + (size_t)i * k * 4;
-    for (int s = 0; s < k; s++) {
-      const double ba = pa < 3 ? S.w_reg * be[4 * s + pa] : S.w_reg;
-      const double bb = pb < 3 ? S.w_reg * be[4 * s + pb] : S.w_reg;
-      val = fma(ba, bb, val);
-    }
-    // in-edges: a free source has -w in its row, an excluded source contributes a static-side row -w: w^2 each on t_j
-    if (pa == 3 && pb == 3) val = fma((double)(S.in_off[i + 1] - S.in_off[i]) * S.w_reg, S.w_reg, val);
-    // constraints: per group the node's aggregated entry (setFromTriplets sums duplicates, Deform.cpp:374)
-    int cur = -1; double sa = 0.0, sb = 0.0;
-    for (int t = S.cin_off[i]; t < S.cin_off[i + 1]; t++) {
-      const int g = S.cin_grp[t];
-      if (g != cur) { val = fma(sa, sb, val); sa = 0.0; sb = 0.0; cur = g; }
-      sa += S.ccoef[(size_t)t * 4 + pa]; sb += S.ccoef[(size_t)t * 4 + pb];
-    }
-    val = fma(sa, sb, val);
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-      const int ia = pa < 3 ? j + 3 * pa : 9 + j, ib = pb < 3 ? j + 3 * pb : 9 + j;
-      D[ia * 12 + ib] += val;
-    }
-  }
-  T.sync();
-  for (int j = 0; j < 12; j++) {  // Cholesky, lower, in place
-    if (lane == j) {
-      double s = D[j * 12 + j];
-      for (int t = 0; t < j; t++) s = fma(-D[j * 12 + t], D[j * 12 + t], s);
-      D[j * 12 + j] = sqrt(s);
-    }
-    T.sync();
-    if (lane > j && lane < 12) {
-      double s = D[lane * 12 + j];
-      for (int t = 0; t < j; t++) s = fma(-D[lane * 12 + t], D[j * 12 + t], s);
-      D[lane * 12 + j] = s / D[j * 12 + j];
-    }
-    T.sync();
-  }
-  if (lane < 12) {  // inverse column for quad index `lane`
-    const int rc = ref_index(lane);
-    double y[12];
-#pragma unroll
-    for (int r = 0; r < 12; r++) {
-      double s = (r == rc) ? 1.0 : 0.0;
-#pragma unroll
-      for (int t = 0; t < 12; t++) if (t < r) s = fma(-D[r * 12 + t], y[t], s);
-      y[r] = s / D[r * 12 + r];
-    }
-#pragma unroll
-    for (int r = 11; r >= 0; r--) {
-      double s = y[r];
-#pragma unroll
-      for (int t = 0; t < 12; t++) if (t > r) s = fma(-D[t * 12 + r], y[t], s);
-      y[r] = s / D[r * 12 + r];
-    }
-    // y is indexed by reference index; store row-wise in quad order (matrix is symmetric)
-#pragma unroll
-    for (int qi = 0; qi < 12; qi++) {
-      double v = 0.0;
-      const int rr = ref_index(qi);
-#pragma unroll
-      for (int t = 0; t < 12; t++) if (t == rr) v = y[t];
-      S.dinv[(size_t)i * 144 + (size_t)qi * 12 + lane] = v;
-    }
-  }
-  T.sync();
+  d = fma(sa, sa, d);
+  return d;
 }
 
 template <int K>
-__global__ void __launch_bounds__(SOLVE_THREADS, 3) k_solve(SolveDev S) {
+__global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveDev S) {
   cg::grid_group grid = cg::this_grid();
-  cg::thread_block block = cg::this_thread_block();
-  cg::thread_block_tile<TILE> T = cg::tiled_partition<TILE>(block);
-  __shared__ double s_D[TILES_PER_BLOCK][144 + 54];
-  const int gquad = blockIdx.x * QUADS_PER_BLOCK + (threadIdx.x >> 2), nquads = gridDim.x * QUADS_PER_BLOCK;
-  const int j = threadIdx.x & 3;
-  const unsigned qmask = 0xFu << (threadIdx.x & 28);
-  const int gtile = blockIdx.x * TILES_PER_BLOCK + threadIdx.x / TILE, ntiles = gridDim.x * TILES_PER_BLOCK;
   const int gthread = blockIdx.x * SOLVE_THREADS + threadIdx.x, nthreads = gridDim.x * SOLVE_THREADS;
-  const int M = S.M, k = S.k;
+  const int M = S.M, k = K > 0 ? K : S.k;
+  const int NU = M * 12;
   int phase = 0;
   double red[NRED];
 
   // ---- per-solve constants + x = identity (setIdentityRots, Deform.cpp:83-93)
-  for (int t = gthread; t < M * 12; t += nthreads) {
-    const int c = t & 3;
-    const int jj = (t >> 2) % 3;
-    S.x[t] = (c == jj) ? 1.0 : 0.0;   // A[j][c] = delta, t_j = 0
-    S.h[t] = 0.0; S.p0[t] = 0.0; S.p1[t] = 0.0; S.z[t] = 0.0; S.r[t] = 0.0;
+  for (int t = gthread; t < NU; t += nthreads) {
+    const int c = t & 3, jj = (t >> 2) % 3;
+    S.x[t] = (c == jj) ? 1.0 : 0.0;
+    S.h[t] = 0.0; S.p0[t] = 0.0; S.p1[t] = 0.0; S.z[t] = 0.0; S.r[t] = 0.0; S.dinv[t] = 0.0;
   }
   for (int t = gthread; t < M * k; t += nthreads) {  // float differences g_q - g_i (Deform.cpp:254-256)
     const int i = t / k, q = S.nbr[t];
@@ -495,41 +363,32 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 3) k_solve(SolveDev S) {
   int gn_iters = 0, halvings = 0, total_cg = 0, flag = 0;
   double energy = 0.0, normh = 0.0, last_rel = 0.0, abs_target = -1.0, E0 = 0.0;
   bool have_f = false;
+  double tphase[4] = {0.0, 0.0, 0.0, 0.0};  // ns spent in: rows, barrier 1, gather/update, barrier 2 (this thread's view)
 
   for (int gn = 0; gn < S.max_gn; gn++) {
     gn_iters = gn + 1;
     if (!have_f) {
-      red[0] = rows_res(S, gquad, nquads, j, S.x, nullptr, 0.0);
+      red[0] = row_phase<K, 0>(S, gthread, nthreads, S.x, nullptr, 0.0, nullptr);
       red[1] = red[2] = 0.0;
       grid_reduce(grid, S, phase, red);
       E0 = red[0];
     }
     energy = E0;
-    // ---- block-Jacobi preconditioner
-    for (int i = gtile; i < M; i += ntiles)
-      if (S.node_free[i]) build_dinv(S, T, i, s_D[threadIdx.x / TILE], s_D[threadIdx.x / TILE] + 144);
-    __syncthreads();
-    // ---- gradient g = -J^T f, z = Dinv g
+    // ---- gradient g = -J^T f, Jacobi preconditioner, z = g / diag
     double rz_l = 0.0, gg_l = 0.0, xx_l = 0.0;
-    for (int i = gquad; i < M; i += nquads) {
+    for (int t = gthread; t < NU; t += nthreads) {
+      const int i = t / 12, qi = t - 12 * i, j = qi >> 2, c = qi & 3;
       if (!S.node_free[i]) continue;
-      D4 g4{0.0, 0.0, 0.0, 0.0}, x4{0.0, 0.0, 0.0, 0.0};
-      if (j < 3) {
-        const size_t ob = (size_t)i * 12;
-        const D4 A0 = ld4(S.x + ob), A1 = ld4(S.x + ob + 4), A2 = ld4(S.x + ob + 8);
-        double f[6]; rot_rows_res(A0, A1, A2, S.w_rot, f);
-        x4 = j == 0 ? A0 : j == 1 ? A1 : A2;
-        const D4 y = gather_jt<K>(S, i, j, f, x4.d);
-        g4 = D4{-y.a, -y.b, -y.c, -y.d};
-      }
-      const D4 z4 = apply_dinv(S, i, j, qmask, g4);
-      if (j < 3) {
-        const size_t o = ((size_t)i * 3 + j) * 4;
-        st4(S.r + o, g4); st4(S.z + o, z4); st4(S.h + o, D4{0.0, 0.0, 0.0, 0.0});
-        rz_l += g4.a * z4.a + g4.b * z4.b + g4.c * z4.c + g4.d * z4.d;
-        gg_l += g4.a * g4.a + g4.b * g4.b + g4.c * g4.c + g4.d * g4.d;
-        xx_l += x4.a * x4.a + x4.b * x4.b + x4.c * x4.c + x4.d * x4.d;
-      }
+      const size_t ob = (size_t)i * 12;
+      const D4 A0 = ld4(S.x + ob), A1 = ld4(S.x + ob + 4), A2 = ld4(S.x + ob + 8);
+      double f[6]; rot_rows_res(A0, A1, A2, S.w_rot, f);
+      const D4 Aj = j == 0 ? A0 : j == 1 ? A1 : A2;
+      const double xv = c == 0 ? Aj.a : c == 1 ? Aj.b : c == 2 ? Aj.c : Aj.d;
+      const double g = -gather_jt<K>(S, i, j, c, Aj, f, xv);
+      const double di = 1.0 / diag_jtj<K>(S, i, j, c, A0, A1, A2);
+      const double zv = g * di;
+      S.dinv[t] = di; S.r[t] = g; S.z[t] = zv; S.h[t] = 0.0;
+      rz_l = fma(g, zv, rz_l); gg_l = fma(g, g, gg_l); xx_l = fma(xv, xv, xx_l);
     }
     red[0] = rz_l; red[1] = gg_l; red[2] = xx_l;
     grid_reduce(grid, S, phase, red);
@@ -542,37 +401,40 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 3) k_solve(SolveDev S) {
       for (int it = 0; it < S.max_cg; it++) {
         double* pnew = cur ? S.p1 : S.p0;
         const double* pold = cur ? S.p0 : S.p1;
-        red[0] = rows_lin<K>(S, gquad, nquads, j, S.z, pold, beta, pnew);   // p = z + beta p_old; u = J p
+        const unsigned long long t0 = gtime();
+        red[0] = row_phase<K, 1>(S, gthread, nthreads, S.z, pold, beta, pnew);   // p = z + beta p_old; u = J p
         red[1] = red[2] = 0.0;
+        const unsigned long long t1 = gtime();
         grid_reduce(grid, S, phase, red);
+        const unsigned long long t2 = gtime();
         const double pHp = red[0];
         const double alpha = rz / pHp;
         double rzn_l = 0.0, rr_l = 0.0;
-        for (int i = gquad; i < M; i += nquads) {
+        for (int t = gthread; t < NU; t += nthreads) {
+          const int i = t / 12, qi = t - 12 * i, j = qi >> 2, c = qi & 3;
           if (!S.node_free[i]) continue;
-          D4 r4{0.0, 0.0, 0.0, 0.0};
-          const size_t o = ((size_t)i * 3 + (j < 3 ? j : 0)) * 4;
-          if (j < 3) {
-            const size_t ob = (size_t)i * 12;
+          const size_t ob = (size_t)i * 12;
+          const D4 Aj = ld4(S.x + ob + 4 * j);
+          double u[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+          if (c < 3) {
             const D4 A0 = ld4(S.x + ob), A1 = ld4(S.x + ob + 4), A2 = ld4(S.x + ob + 8);
             const D4 P0 = ld4(pnew + ob), P1 = ld4(pnew + ob + 4), P2 = ld4(pnew + ob + 8);
-            double u[6]; rot_rows_lin(A0, A1, A2, P0, P1, P2, S.w_rot, u);
-            const D4 p4 = j == 0 ? P0 : j == 1 ? P1 : P2;
-            const D4 y = gather_jt<K>(S, i, j, u, p4.d);
-            D4 h4 = ld4(S.h + o); r4 = ld4(S.r + o);
-            h4.a = fma(alpha, p4.a, h4.a); h4.b = fma(alpha, p4.b, h4.b); h4.c = fma(alpha, p4.c, h4.c); h4.d = fma(alpha, p4.d, h4.d);
-            r4.a = fma(-alpha, y.a, r4.a); r4.b = fma(-alpha, y.b, r4.b); r4.c = fma(-alpha, y.c, r4.c); r4.d = fma(-alpha, y.d, r4.d);
-            st4(S.h + o, h4); st4(S.r + o, r4);
+            rot_rows_lin(A0, A1, A2, P0, P1, P2, S.w_rot, u);
           }
-          const D4 z4 = apply_dinv(S, i, j, qmask, r4);
-          if (j < 3) {
-            st4(S.z + o, z4);
-            rzn_l += r4.a * z4.a + r4.b * z4.b + r4.c * z4.c + r4.d * z4.d;
-            rr_l += r4.a * r4.a + r4.b * r4.b + r4.c * r4.c + r4.d * r4.d;
-          }
+          const double pv = pnew[t];
+          const double y = gather_jt<K>(S, i, j, c, Aj, u, pv);
+          S.h[t] = fma(alpha, pv, S.h[t]);
+          const double rv = fma(-alpha, y, S.r[t]);
+          S.r[t] = rv;
+          const double zv = rv * S.dinv[t];
+          S.z[t] = zv;
+          rzn_l = fma(rv, zv, rzn_l); rr_l = fma(rv, rv, rr_l);
         }
         red[0] = rzn_l; red[1] = rr_l; red[2] = 0.0;
+        const unsigned long long t3 = gtime();
         grid_reduce(grid, S, phase, red);
+        const unsigned long long t4 = gtime();
+        tphase[0] += (double)(t1 - t0); tphase[1] += (double)(t2 - t1); tphase[2] += (double)(t3 - t2); tphase[3] += (double)(t4 - t3);
         total_cg++;
         const double rzn = red[0], rr = red[1];
         last_rel = sqrt(rr / gg);
@@ -587,19 +449,19 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 3) k_solve(SolveDev S) {
     // ---- step halving (Deform.cpp:144-156)
     bool accepted = false;
     for (double alpha_ls = 1.0; alpha_ls > 1e-15; alpha_ls *= 0.5) {
-      red[0] = rows_res(S, gquad, nquads, j, S.x, S.h, 1.0);
+      red[0] = row_phase<K, 0>(S, gthread, nthreads, S.x, S.h, 1.0, nullptr);
       double hh_l = 0.0;
-      for (int t = gthread; t < M * 12; t += nthreads) { const double hv = S.h[t]; hh_l = fma(hv, hv, hh_l); }
+      for (int t = gthread; t < NU; t += nthreads) { const double hv = S.h[t]; hh_l = fma(hv, hv, hh_l); }
       red[1] = hh_l; red[2] = 0.0;
       grid_reduce(grid, S, phase, red);
       const double E1 = red[0];
       if (E1 > E0) {
-        for (int t = gthread; t < M * 12; t += nthreads) S.h[t] *= 0.5;
+        for (int t = gthread; t < NU; t += nthreads) S.h[t] *= 0.5;
         halvings++;
         normh = 0.5 * sqrt(red[1]);
         grid.sync();
       } else {
-        for (int t = gthread; t < M * 12; t += nthreads) S.x[t] += S.h[t];
+        for (int t = gthread; t < NU; t += nthreads) S.x[t] += S.h[t];
         normh = sqrt(red[1]);
         E0 = E1; have_f = true; accepted = true;
         grid.sync();
@@ -610,8 +472,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 3) k_solve(SolveDev S) {
     if (normh < (normv + 1e-6) * 1e-6) break;
   }
 
-  // putFreeInputs (Deform.hpp:140-151): rot column-major, excluded nodes keep identity (h, x of excluded nodes never change)
-  for (int t = gthread; t < M * 12; t += nthreads) {
+  // putFreeInputs (Deform.hpp:140-151): rot column-major; excluded nodes keep identity (their x never changes)
+  for (int t = gthread; t < NU; t += nthreads) {
     const int i = t / 12, qi = t - 12 * i, jj = qi >> 2, c = qi & 3;
     const double v = S.x[t];
     if (c < 3) S.rot_out[(size_t)i * 9 + jj + 3 * c] = v; else S.trans_out[(size_t)i * 3 + jj] = v;
@@ -619,6 +481,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 3) k_solve(SolveDev S) {
   if (gthread == 0) {
     S.stats[0] = gn_iters; S.stats[1] = energy; S.stats[2] = halvings; S.stats[3] = normh;
     S.stats[4] = total_cg; S.stats[5] = last_rel; S.stats[6] = flag;
+    S.stats[8] = tphase[0]; S.stats[9] = tphase[1]; S.stats[10] = tphase[2]; S.stats[11] = tphase[3]; S.stats[12] = gridDim.x;
   }
 }
 
@@ -627,8 +490,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 3) k_solve(SolveDev S) {
 using namespace arapgs;
 
 extern "C" size_t arapk_solve_workspace_bytes(int M, int k, int n_groups) {
-  // 6 vectors + dinv + edge constants + row buffers + constraint coefficients (<= groups*20*k entries) + partials
-  size_t d = (size_t)M * 12 * 6 + (size_t)M * 144 + (size_t)M * k * 4 + (size_t)M * k * 3 + (size_t)(n_groups + 1) * 3 +
+  // 7 vectors + edge constants + row buffers (source + destination copies) + constraint coefficients
+  // (<= groups * 20 * k entries) + partials
+  size_t d = (size_t)M * 12 * 7 + (size_t)M * k * 4 + (size_t)M * k * 3 * 2 + (size_t)(n_groups + 1) * 3 +
              (size_t)(n_groups + 1) * 20 * k * 4 + 2 * 2048 * NRED + 64;
   return d * sizeof(double);
 }
@@ -639,8 +503,8 @@ extern "C" int arapk_solve(const ArapSolveGraph* G, const ArapSolveParams* P, vo
   if (workspace_bytes < arapk_solve_workspace_bytes(G->M, G->k, G->n_groups)) { set_error("solve: workspace too small"); return ARAP_ERR_INVALID; }
   if (G->n_cin_entries > (long long)(G->n_groups + 1) * 20 * G->k) { set_error("solve: constraint entry count exceeds the workspace bound"); return ARAP_ERR_INVALID; }
   SolveDev S;
-  S.M = G->M; S.k = G->k; S.n_groups = G->n_groups; S.n_entries = (int)G->n_cin_entries;
-  S.node_pos = G->node_pos; S.nbr = G->nbr; S.in_off = G->in_off; S.in_src = G->in_src; S.in_slot = G->in_slot;
+  S.M = G->M; S.k = G->k; S.n_groups = G->n_groups;
+  S.node_pos = G->node_pos; S.nbr = G->nbr; S.in_off = G->in_off; S.out_to_in = G->out_to_in;
   S.anc_idx = G->anc_idx; S.anc_w = G->anc_w; S.node_free = G->node_free; S.static_in_cnt = G->static_in_cnt;
   S.grp_off = G->grp_off; S.grp_member = G->grp_member; S.grp_aim = G->grp_aim;
   S.cin_off = G->cin_off; S.cin_grp = G->cin_grp; S.cin_member = G->cin_member; S.cin_slot = G->cin_slot;
@@ -650,11 +514,11 @@ extern "C" int arapk_solve(const ArapSolveGraph* G, const ArapSolveParams* P, vo
   S.cg_tol = P->cg_tol > 0 ? P->cg_tol : 1e-10;
   double* w = (double*)workspace;
   const size_t v12 = (size_t)G->M * 12;
-  S.x = w; w += v12; S.h = w; w += v12; S.r = w; w += v12; S.z = w; w += v12; S.p0 = w; w += v12; S.p1 = w; w += v12;
-  S.dinv = w; w += (size_t)G->M * 144;
+  S.x = w; w += v12; S.h = w; w += v12; S.r = w; w += v12; S.z = w; w += v12; S.p0 = w; w += v12; S.p1 = w; w += v12; S.dinv = w; w += v12;
   S.bedge = w; w += (size_t)G->M * G->k * 4;
   S.ccoef = w; w += (size_t)(G->n_groups + 1) * 20 * G->k * 4;  // 16-byte aligned arrays (double2 loads) first
   S.u_reg = w; w += (size_t)G->M * G->k * 3;
+  S.u_in = w; w += (size_t)G->M * G->k * 3;
   S.u_con = w; w += (size_t)(G->n_groups + 1) * 3;
   S.partial = w;
   S.rot_out = rot_out; S.trans_out = trans_out; S.stats = stats_dev;
@@ -664,8 +528,9 @@ extern "C" int arapk_solve(const ArapSolveGraph* G, const ArapSolveParams* P, vo
   void* kern = G->k == 8 ? (void*)k_solve<8> : G->k == 10 ? (void*)k_solve<10> : G->k == 12 ? (void*)k_solve<12> : (void*)k_solve<0>;
   ARAP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kern, SOLVE_THREADS, 0));
   if (per_sm < 1) { set_error("solve: kernel cannot be co-resident"); return ARAP_ERR_CUDA; }
-  const int items = G->M + G->n_groups;
-  int grid = std::min(sms * std::min(per_sm, 4), (items + QUADS_PER_BLOCK - 1) / QUADS_PER_BLOCK);
+  // one thread per E_reg row is the widest phase; small graphs get a small grid (cheaper barriers)
+  const long long rows = (long long)G->M * G->k * 3;
+  int grid = (int)std::min<long long>((long long)sms * std::min(per_sm, 1), (rows + SOLVE_THREADS - 1) / SOLVE_THREADS);
   grid = std::max(1, std::min(grid, 2048));
   void* args[] = {(void*)&S};
   ARAP_CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(SOLVE_THREADS), args, 0, st));

@@ -65,6 +65,8 @@ typedef struct arap_solve_stats {
   double energy;       /* f.f at the last linearisation point (Deform::optimize return) */
   double normh;        /* |h| of the last accepted step */
   double last_rel_residual;
+  double phase_ns[4];  /* block 0's time in: row phase, barrier 1, gather/update phase, barrier 2 (summed over PCG iterations) */
+  int grid_blocks;     /* cooperative grid size used */
 } arap_solve_stats;
 
 typedef struct arap_grid_info {
