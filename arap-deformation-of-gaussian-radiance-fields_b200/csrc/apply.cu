@@ -136,7 +136,7 @@ constexpr int FIT_TILE = 128;
 constexpr int SH_PITCH = 49;    // odd pitch: conflict-free per-thread rows
 constexpr int END_PITCH = 19;
 
-__global__ void __launch_bounds__(FIT_TILE)
+__global__ void __launch_bounds__(FIT_TILE, 6)
 k_fit_gaussians(long long N, const float* __restrict__ ends, const float* __restrict__ scale_backup,
                 const uint8_t* __restrict__ is_static, float* __restrict__ pos, float* __restrict__ rot,
                 float* __restrict__ scale, float* __restrict__ shs) {
@@ -271,7 +271,7 @@ __global__ void k_node_quats(int M, const double* __restrict__ rot, float4* __re
 // 192 B feature rows move as coalesced float4.  Skinning weights (float) and
 // node ids use the same 32-row blocked layout as the LBS tables.
 constexpr int RS_TILE = 128;
-__global__ void __launch_bounds__(RS_TILE)
+__global__ void __launch_bounds__(RS_TILE, 8)
 k_rotate_sample_shs(long long S, int k, const float* __restrict__ w, const uint16_t* __restrict__ idx,
                     const float4* __restrict__ q_xyzw, const uint8_t* __restrict__ is_static,
                     float* __restrict__ feature) {

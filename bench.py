@@ -82,13 +82,6 @@ class ClockSampler:
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
 
 
-class DevArray:
-    """Expose a raw device pointer owned by the ctx to torch (for NCCL) via __cuda_array_interface__."""
-
-    def __init__(self, ptr, shape, typestr="<f4"):
-        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=2)
-
-
 def setup_session(pkg, scenes, workload, n, rank, world, stream):
     cfg = scenes.CONFIGS[workload]
     sc = scenes.make_scene(workload, n=n, seed_offset=rank)
@@ -141,13 +134,10 @@ def run_own(args):
 
     gather = None
     if world > 1:   # all-gather of the deformed SoA (232 B / Gaussian): pos 12 + rot 16 + scale 12 + SH 192
+        par = importlib.import_module(ge.PKG + ".parallel")
         v = s.device_view()
-        parts = [torch.as_tensor(DevArray(p, (N * w,)), device="cuda") for p, w in ((v.pos, 3), (v.rot, 4), (v.scale, 3), (v.shs, 48))]
-        outs = [torch.empty(world * t.numel(), dtype=torch.float32, device="cuda") for t in parts]
-
-        def gather():
-            for t, o in zip(parts, outs):
-                dist.all_gather_into_tensor(o, t)
+        parts = {name: torch.as_tensor(par.DevArray(getattr(v, name), (N, w)), device="cuda") for name, w in par.SOA_WIDTHS}
+        gather = par.SoAGather(parts, world)
 
     def one_step():
         s.aim_translate(DRAG)

@@ -1,0 +1,74 @@
+"""world_size-2 gloo tests (CPU) of the host-side sharding / gather logic used by bench.py --gpus N."""
+import importlib
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+PKG = "arap-deformation-of-gaussian-radiance-fields_b200"
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    par = importlib.import_module(PKG + ".parallel")
+    rng = np.random.default_rng(5)
+    n = 1001
+    full = {k: rng.normal(size=(n, w)).astype(np.float32) for k, w in par.SOA_WIDTHS}
+    lo, hi = par.shard_range(n, rank, world)
+    # unequal shards (1001 is odd): variable all-gather must restore the index order
+    got = {k: par.allgather_variable(v[lo:hi], world) for k, v in full.items()}
+    ok = all(np.array_equal(got[k], full[k]) for k in full)
+    # equal shards: the fixed-size SoA gather used on the GPU path
+    m = 500
+    parts = {k: torch.from_numpy(np.ascontiguousarray(v[rank * m:(rank + 1) * m])) for k, v in full.items()}
+    outs = par.SoAGather(parts, world)()
+    ok &= all(np.array_equal(outs[k].numpy(), full[k][:world * m]) for k in full)
+    # max-over-ranks timing reduction as bench.py does it
+    t = torch.tensor([1.0 + rank], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ok &= float(t.item()) == float(world)
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_ranges_partition_the_index_space():
+    sys.path.insert(0, str(ROOT))
+    par = importlib.import_module(PKG + ".parallel")
+    for n in (0, 1, 7, 1000, 6_000_001):
+        for world in (1, 2, 4, 8):
+            r = [par.shard_range(n, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+            sizes = par.shard_sizes(n, world)
+            assert max(sizes) - min(sizes) <= 1 and sum(sizes) == n
+    assert par.SOA_BYTES_PER_GAUSSIAN == 232
+
+
+def test_gather_world2_gloo():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == {0: True, 1: True}
