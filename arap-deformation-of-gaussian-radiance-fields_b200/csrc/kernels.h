@@ -62,6 +62,7 @@ typedef struct ArapSolveParams {
   int max_gn_iters;            // MAX_ITERS 30
   int max_cg_iters;
   double cg_tol;               // relative residual of the first linear system; later ones reuse its absolute value
+  int force_global_kernel;     // 1: skip the shared-memory-resident fast path (tests)
 } ArapSolveParams;
 
 size_t arapk_solve_workspace_bytes(int M, int k, int n_groups);

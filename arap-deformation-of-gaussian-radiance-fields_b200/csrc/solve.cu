@@ -26,6 +26,7 @@
 #include <cooperative_groups.h>
 #include "common.cuh"
 #include "kernels.h"
+#include "solve_dev.h"
 
 namespace cg = cooperative_groups;
 
@@ -33,33 +34,6 @@ namespace arapgs {
 
 constexpr int SOLVE_THREADS = 1024;
 constexpr int NRED = 3;
-
-struct SolveDev {
-  int M, k, n_groups;
-  const float* node_pos;      // M x 3
-  const int* nbr;             // M x k
-  const int* in_off;          // M + 1: in-edges from FREE sources
-  const int* out_to_in;       // M x k: slot of edge (i,s) in u_in, or -1
-  const int* anc_idx;         // M x k
-  const double* anc_w;        // M x k
-  const uint8_t* node_free;   // M
-  const int* static_in_cnt;   // M
-  const int* grp_off;         // n_groups + 1 -> members
-  const int* grp_member;
-  const float* grp_aim;       // n_groups x 3
-  const int* cin_off;         // M + 1 -> constraint entries touching the node, sorted by group
-  const int* cin_grp;
-  const int* cin_member;
-  const int* cin_slot;
-  double w_rot, w_reg, w_con;  // square-rooted (Deform.hpp:452-454)
-  int max_gn, max_cg;
-  double cg_tol;
-  // work (double).  Vectors: [M][3][4]
-  double *x, *h, *r, *z, *p0, *p1, *dinv, *bedge /* M x k x 4 */, *ccoef /* cin entries x 4 */;
-  double *u_reg /* M x k x 3 */, *u_in /* in-edges x 3 */, *u_con /* groups x 3 */;
-  double* partial;             // 2 x gridDim x NRED
-  double *rot_out, *trans_out, *stats;
-};
 
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
@@ -493,7 +467,7 @@ extern "C" size_t arapk_solve_workspace_bytes(int M, int k, int n_groups) {
   // 7 vectors + edge constants + row buffers (source + destination copies) + constraint coefficients
   // (<= groups * 20 * k entries) + partials
   size_t d = (size_t)M * 12 * 7 + (size_t)M * k * 4 + (size_t)M * k * 3 * 2 + (size_t)(n_groups + 1) * 3 +
-             (size_t)(n_groups + 1) * 20 * k * 4 + 2 * 2048 * NRED + 64;
+             (size_t)(n_groups + 1) * 20 * k * 4 * 2 + (size_t)(n_groups + 1) * 20 * k / 2 + 2 * 2048 * NRED + 64 + 32;
   return d * sizeof(double);
 }
 
@@ -517,11 +491,19 @@ extern "C" int arapk_solve(const ArapSolveGraph* G, const ArapSolveParams* P, vo
   S.x = w; w += v12; S.h = w; w += v12; S.r = w; w += v12; S.z = w; w += v12; S.p0 = w; w += v12; S.p1 = w; w += v12; S.dinv = w; w += v12;
   S.bedge = w; w += (size_t)G->M * G->k * 4;
   S.ccoef = w; w += (size_t)(G->n_groups + 1) * 20 * G->k * 4;  // 16-byte aligned arrays (double2 loads) first
+  S.gent_c = w; w += (size_t)(G->n_groups + 1) * 20 * G->k * 4;
+  S.gent_q = reinterpret_cast<int*>(w); w += ((size_t)(G->n_groups + 1) * 20 * G->k + 1) / 2 + 1;
+  if ((w - (double*)workspace) & 1) w += 1;
   S.u_reg = w; w += (size_t)G->M * G->k * 3;
   S.u_in = w; w += (size_t)G->M * G->k * 3;
   S.u_con = w; w += (size_t)(G->n_groups + 1) * 3;
-  S.partial = w;
+  S.partial = w; w += 2 * 2048 * NRED;
+  unsigned* counter = reinterpret_cast<unsigned*>(w);
   S.rot_out = rot_out; S.trans_out = trans_out; S.stats = stats_dev;
+  if (!P->force_global_kernel) {   // fast path: per-node state resident in shared memory (solve_smem.cu)
+    const int rc = launch_solve_smem(S, counter, st);
+    if (rc >= 0) return rc;
+  }
   int dev = 0, sms = 0, per_sm = 0;
   ARAP_CUDA_TRY(cudaGetDevice(&dev));
   ARAP_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

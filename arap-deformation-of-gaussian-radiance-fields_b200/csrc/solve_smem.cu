@@ -1,0 +1,591 @@
+// Stage (c), fast path: the Gauss-Newton / Jacobi-PCG solve of solve.cu with the per-node state resident in
+// shared memory for the whole solve.
+//
+// Same mathematics, same phases and the same two grid barriers per PCG iteration as solve.cu (see its header for
+// the reference citations).  What changes is where the data lives: nodes are dealt round-robin to the CTAs
+// (owner(i) = i % gridDim, one CTA per SM); a CTA keeps x, r, z, p, h, 1/diag, its own row values u, the per-edge
+// constants and the graph slices of ITS nodes in shared memory.  Only what other CTAs need crosses L2:
+//   z, p (the search-direction pieces neighbours recombine as p = z + beta p_old), x + h for residual evaluations,
+//   u_in (row values delivered to the destination node's in-edge slots) and u_con (constraint rows).
+// That cuts the per-iteration L2 traffic from ~45 MB to ~12 MB at 16k nodes and removes most dependent global loads
+// from both phases, which were latency-bound.  FPS node order is spatially random, so round-robin ownership also
+// spreads the control-region nodes (extra constraint work) evenly.
+//
+// Used when the per-CTA slice fits in shared memory (<= ~27k nodes at k = 10 on 148 SMs); otherwise solve.cu runs.
+#include <cooperative_groups.h>
+#include "common.cuh"
+#include "kernels.h"
+#include "solve_dev.h"
+
+namespace cg = cooperative_groups;
+
+namespace arapgs {
+
+constexpr int SM_THREADS = 1024;
+constexpr int SM_NRED = 3;
+
+struct D4 { double a, b, c, d; };
+__device__ __forceinline__ D4 ld4(const double* p) {
+  const double2 lo = *reinterpret_cast<const double2*>(p), hi = *reinterpret_cast<const double2*>(p + 2);
+  return D4{lo.x, lo.y, hi.x, hi.y};
+}
+__device__ __forceinline__ D4 ld4cg(const double* p) {  // data published by other CTAs: read through L2
+  const double2 lo = __ldcg(reinterpret_cast<const double2*>(p)), hi = __ldcg(reinterpret_cast<const double2*>(p + 2));
+  return D4{lo.x, lo.y, hi.x, hi.y};
+}
+__device__ __forceinline__ void st4(double* p, const D4& v) {
+  *reinterpret_cast<double2*>(p) = make_double2(v.a, v.b);
+  *reinterpret_cast<double2*>(p + 2) = make_double2(v.c, v.d);
+}
+__device__ __forceinline__ unsigned long long gtime2() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
+__device__ __forceinline__ void rot_lin(const D4& A0, const D4& A1, const D4& A2, const D4& P0, const D4& P1, const D4& P2, double w, double (&u)[6]) {
+  const double a0p1 = fma(A0.a, P0.b, fma(A1.a, P1.b, A2.a * P2.b)), a1p0 = fma(A0.b, P0.a, fma(A1.b, P1.a, A2.b * P2.a));
+  const double a0p2 = fma(A0.a, P0.c, fma(A1.a, P1.c, A2.a * P2.c)), a2p0 = fma(A0.c, P0.a, fma(A1.c, P1.a, A2.c * P2.a));
+  const double a1p2 = fma(A0.b, P0.c, fma(A1.b, P1.c, A2.b * P2.c)), a2p1 = fma(A0.c, P0.b, fma(A1.c, P1.b, A2.c * P2.b));
+  u[0] = w * (a0p1 + a1p0); u[1] = w * (a0p2 + a2p0); u[2] = w * (a1p2 + a2p1);
+  u[3] = 2.0 * w * fma(A0.a, P0.a, fma(A1.a, P1.a, A2.a * P2.a));
+  u[4] = 2.0 * w * fma(A0.b, P0.b, fma(A1.b, P1.b, A2.b * P2.b));
+  u[5] = 2.0 * w * fma(A0.c, P0.c, fma(A1.c, P1.c, A2.c * P2.c));
+}
+__device__ __forceinline__ void rot_res(const D4& A0, const D4& A1, const D4& A2, double w, double (&f)[6]) {
+  f[0] = w * fma(A0.a, A0.b, fma(A1.a, A1.b, A2.a * A2.b));
+  f[1] = w * fma(A0.a, A0.c, fma(A1.a, A1.c, A2.a * A2.c));
+  f[2] = w * fma(A0.b, A0.c, fma(A1.b, A1.c, A2.b * A2.c));
+  f[3] = w * (fma(A0.a, A0.a, fma(A1.a, A1.a, A2.a * A2.a)) - 1.0);
+  f[4] = w * (fma(A0.b, A0.b, fma(A1.b, A1.b, A2.b * A2.b)) - 1.0);
+  f[5] = w * (fma(A0.c, A0.c, fma(A1.c, A1.c, A2.c * A2.c)) - 1.0);
+}
+__device__ __forceinline__ double rot_t(const D4& Aj, double w, const double (&u)[6], int c) {
+  if (c == 0) return w * fma(u[0], Aj.b, fma(u[1], Aj.c, 2.0 * u[3] * Aj.a));
+  if (c == 1) return w * fma(u[0], Aj.a, fma(u[2], Aj.c, 2.0 * u[4] * Aj.b));
+  return w * fma(u[1], Aj.a, fma(u[2], Aj.b, 2.0 * u[5] * Aj.c));
+}
+
+// shared-memory slice of one CTA
+struct Loc {
+  double *xs, *rs, *zs, *ps, *hs, *ds, *us;  // [NL*12] x6, [NL*K*3]
+  float4* be;                                // [NL*K]  (g_q - g_i as float, 1)
+  int *nbr, *o2i;                            // [NL*K]
+  int *inb, *ine, *cb, *ce, *sic, *fr;       // [NL]
+  int b, B, nloc;
+};
+
+// grid barrier + deterministic reduction of SM_NRED scalars.  `counter` is monotonically increasing.
+__device__ __forceinline__ void barrier_reduce(const SolveDev& S, unsigned* counter, int& phase, double (&v)[SM_NRED]) {
+  __shared__ double s_part[SM_THREADS / 32][SM_NRED];
+  __shared__ double s_tot[SM_NRED];
+#pragma unroll
+  for (int q = 0; q < SM_NRED; q++)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0)
+#pragma unroll
+    for (int q = 0; q < SM_NRED; q++) s_part[warp][q] = v[q];
+  __syncthreads();
+  if (warp == 0) {
+    double* buf = S.partial + (size_t)(phase & 1) * gridDim.x * SM_NRED;
+    double a[SM_NRED];
+#pragma unroll
+    for (int q = 0; q < SM_NRED; q++) {
+      a[q] = s_part[lane][q];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a[q] += __shfl_xor_sync(0xffffffffu, a[q], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < SM_NRED; q++) buf[(size_t)blockIdx.x * SM_NRED + q] = a[q];
+      __threadfence();
+      atomicAdd(counter, 1u);
+      const unsigned target = (unsigned)(phase + 1) * gridDim.x;
+      while (true) {
+        unsigned cur;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(counter) : "memory");
+        if (cur >= target) break;
+      }
+      __threadfence();
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < SM_NRED; q++) a[q] = 0.0;
+    for (int bb = lane; bb < (int)gridDim.x; bb += 32)
+#pragma unroll
+      for (int q = 0; q < SM_NRED; q++) a[q] += __ldcg(buf + (size_t)bb * SM_NRED + q);
+#pragma unroll
+    for (int q = 0; q < SM_NRED; q++) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a[q] += __shfl_xor_sync(0xffffffffu, a[q], o);
+      if (lane == 0) s_tot[q] = a[q];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < SM_NRED; q++) v[q] = s_tot[q];
+  __syncthreads();
+  phase++;
+}
+
+// remote vector value va[o] + sc*vb[o] (published arrays, through L2)
+__device__ __forceinline__ double rcomb1(const double* va, const double* vb, double sc, size_t o) {
+  return vb ? fma(sc, __ldcg(vb + o), __ldcg(va + o)) : __ldcg(va + o);
+}
+__device__ __forceinline__ D4 rcomb4(const double* va, const double* vb, double sc, size_t o) {
+  D4 v = ld4cg(va + o);
+  if (vb) { const D4 w = ld4cg(vb + o); v.a = fma(sc, w.a, v.a); v.b = fma(sc, w.b, v.b); v.c = fma(sc, w.c, v.c); v.d = fma(sc, w.d, v.d); }
+  return v;
+}
+
+// Row phase over this CTA's nodes (+ its share of the constraint groups).
+//   MODE 1: u = J v; the CTA's own v is in L.ps (already formed); remote v = ga + sc*gb (published z, p_old).
+//   MODE 0: f(v) nonlinear residual; own v in `own` (shared, already formed); remote v = ga (published x + h).
+template <int K, int MODE>
+__device__ __forceinline__ double rows_smem(const SolveDev& S, const Loc& L, const double* own, const double* ga, const double* gb, double sc,
+                                            unsigned long long* tmark = nullptr) {
+  const int k = K;
+  const int k3 = 3 * k;
+  double sq = 0.0;
+  // E_reg rows, four per thread at a time: all remote loads of a batch are issued before any is consumed (the phase is
+  // bound by L2 round trips, not bandwidth).  The neighbour's free flag rides in the sign bit of L.nbr.
+  for (int t0 = threadIdx.x; t0 < L.nloc * k3; t0 += 4 * SM_THREADS) {
+    double ta[4], tb[4]; int qf[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int t = t0 + r * SM_THREADS;
+      qf[r] = -1; ta[r] = 0.0; tb[r] = 0.0;
+      if (t < L.nloc * k3) {
+        const int li = t / k3, rem = t - li * k3, s = rem / 3, j = rem - 3 * s;
+        if (L.fr[li]) {
+          qf[r] = L.nbr[li * k + s];
+          if (qf[r] >= 0) {
+            const size_t o = (size_t)qf[r] * 12 + 4 * j + 3;
+            ta[r] = __ldcg(ga + o);
+            if (gb) tb[r] = __ldcg(gb + o);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int t = t0 + r * SM_THREADS;
+      if (t >= L.nloc * k3) continue;
+      const int li = t / k3, rem = t - li * k3, s = rem / 3, j = rem - 3 * s;
+      if (!L.fr[li]) continue;
+      const int e = li * k + s;
+      const D4 v = ld4(own + (size_t)li * 12 + 4 * j);
+      const double tq = qf[r] >= 0 ? fma(sc, tb[r], ta[r]) : 0.0;
+      double val;
+      if (MODE == 1) {
+        const float4 b = L.be[e];
+        val = S.w_reg * ((fma(v.c, (double)b.z, fma(v.b, (double)b.y, v.a * (double)b.x)) + v.d) - tq);
+      } else {
+        const int i = li * L.B + L.b, q = qf[r] & 0x7fffffff;
+        const double gi0 = S.node_pos[3 * i], gi1 = S.node_pos[3 * i + 1], gi2 = S.node_pos[3 * i + 2];
+        const double gq0 = S.node_pos[3 * q], gq1 = S.node_pos[3 * q + 1], gq2 = S.node_pos[3 * q + 2];
+        const double gij = j == 0 ? gi0 : j == 1 ? gi1 : gi2, gqj = j == 0 ? gq0 : j == 1 ? gq1 : gq2;
+        val = S.w_reg * ((((fma(v.c, gq2 - gi2, fma(v.b, gq1 - gi1, v.a * (gq0 - gi0))) + gij) + v.d) - gqj) - tq);
+      }
+      L.us[(size_t)e * 3 + j] = val;
+      const int slot = L.o2i[e];
+      if (slot >= 0) S.u_in[(size_t)slot * 3 + j] = val;
+      sq = fma(val, val, sq);
+      if (s == 0) {
+        const double sv = S.w_reg * v.d;
+        sq = fma((double)L.sic[li] * sv, sv, sq);
+      }
+    }
+  }
+  if (tmark) tmark[0] = gtime2();
+  // E_rot rows: one thread per local node, dealt from the end of the CTA
+  for (int li = SM_THREADS - 1 - (int)threadIdx.x; li < L.nloc; li += SM_THREADS) {
+    if (!L.fr[li]) continue;
+    const size_t ob = (size_t)li * 12;
+    double u[6];
+    const D4 V0 = ld4(own + ob), V1 = ld4(own + ob + 4), V2 = ld4(own + ob + 8);
+    if (MODE == 1) {
+      const D4 A0 = ld4(L.xs + ob), A1 = ld4(L.xs + ob + 4), A2 = ld4(L.xs + ob + 8);
+      rot_lin(A0, A1, A2, V0, V1, V2, S.w_rot, u);
+    } else rot_res(V0, V1, V2, S.w_rot, u);
+#pragma unroll
+    for (int t = 0; t < 6; t++) sq = fma(u[t], u[t], sq);
+  }
+  if (tmark) tmark[1] = gtime2();
+  // constraint rows: 16-lane team per (group, component); groups dealt round-robin to CTAs
+  {
+    const int l16 = threadIdx.x & 15;
+    const unsigned tmask = 0xFFFFu << (threadIdx.x & 16);
+    const int nteams = SM_THREADS >> 4;
+    const int ng = S.n_groups > L.b ? (S.n_groups - L.b + L.B - 1) / L.B : 0;   // groups g = lg*B + b
+    for (int t = (threadIdx.x >> 4); t < 3 * ng; t += nteams) {
+      const int lg = t / 3, j = t - 3 * lg;
+      const int g = lg * L.B + L.b;
+      const int mb = S.grp_off[g], me = S.grp_off[g + 1];
+      double acc = 0.0;
+      if (MODE == 1) {
+        // precomputed entries (node or -1, w_con wei (v_c - g_q, 1)): one independent load level before the gather
+        for (int m0 = mb; m0 < me; m0 += 4) {
+          int qq[4]; D4 cc[4];
+#pragma unroll
+          for (int r = 0; r < 4; r++) {
+            qq[r] = -1;
+            if (m0 + r < me && l16 < k) {
+              const size_t id = (size_t)(m0 + r) * k + l16;
+              qq[r] = S.gent_q[id];
+              cc[r] = ld4(S.gent_c + id * 4);
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < 4; r++) {
+            if (qq[r] < 0) continue;
+            const D4 v = rcomb4(ga, gb, sc, (size_t)qq[r] * 12 + 4 * j);
+            acc = fma(cc[r].c, v.c, fma(cc[r].b, v.b, fma(cc[r].a, v.a, fma(cc[r].d, v.d, acc))));
+          }
+        }
+      } else {
+      for (int m = mb; m < me; m++) {
+        const int c = S.grp_member[m];
+        if (l16 < k) {
+          const int q = S.anc_idx[c * k + l16];
+          const double wei = S.anc_w[c * k + l16];
+          const float vc0 = S.node_pos[3 * c], vc1 = S.node_pos[3 * c + 1], vc2 = S.node_pos[3 * c + 2];
+          if (!S.node_free[q]) {
+            acc = fma(wei, j == 0 ? (double)vc0 : j == 1 ? (double)vc1 : (double)vc2, acc);
+          } else {
+            const float gq0 = S.node_pos[3 * q], gq1 = S.node_pos[3 * q + 1], gq2 = S.node_pos[3 * q + 2];
+            const D4 v = rcomb4(ga, gb, sc, (size_t)q * 12 + 4 * j);
+            const double gqj = j == 0 ? (double)gq0 : j == 1 ? (double)gq1 : (double)gq2;
+            acc = fma(wei, (fma(v.c, (double)vc2 - (double)gq2, fma(v.b, (double)vc1 - (double)gq1, v.a * ((double)vc0 - (double)gq0))) + gqj) + v.d, acc);
+          }
+        }
+      }
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(tmask, acc, o, 16);
+      if (l16 == 0) {
+        const double val = MODE == 1 ? acc : S.w_con * (acc - (double)(me - mb) * (double)S.grp_aim[3 * g + j]);
+        S.u_con[(size_t)g * 3 + j] = val;
+        sq = fma(val, val, sq);
+      }
+    }
+  }
+  return sq;
+}
+
+// (J^T u) for local unknown (li, j, c)
+template <int K>
+__device__ __forceinline__ double gather_smem(const SolveDev& S, const Loc& L, int li, int j, int c, const D4& Aj, const double (&urot)[6], double vt) {
+  const int k = K;
+  const double* ur = L.us + (size_t)li * k * 3 + j;
+  double y;
+  if (c < 3) {
+    y = rot_t(Aj, S.w_rot, urot, c);
+    const float* be = reinterpret_cast<const float*>(L.be + (size_t)li * k) + c;
+    double acc = 0.0;
+#pragma unroll
+    for (int s = 0; s < K; s++) acc = fma((double)be[4 * s], ur[3 * s], acc);
+    y = fma(S.w_reg, acc, y);
+  } else {
+    double acc = 0.0;
+#pragma unroll
+    for (int s = 0; s < K; s++) acc += ur[3 * s];
+    const double* ui = S.u_in + j;
+    double acc2 = 0.0;
+    const int ib = L.inb[li], ie = L.ine[li];
+    for (int t0 = ib; t0 < ie; t0 += 8) {
+      double uu[8];
+#pragma unroll
+      for (int t = 0; t < 8; t++) uu[t] = (t0 + t < ie) ? __ldcg(ui + (size_t)(t0 + t) * 3) : 0.0;
+#pragma unroll
+      for (int t = 0; t < 8; t++) acc2 += uu[t];
+    }
+    y = S.w_reg * (acc - acc2);
+    y = fma((double)L.sic[li] * S.w_reg * S.w_reg, vt, y);
+  }
+  const int cb = L.cb[li], ce = L.ce[li];
+  for (int t0 = cb; t0 < ce; t0 += 4) {
+    double cc[4], uu[4]; int gg[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) { const bool ok = t0 + t < ce; gg[t] = ok ? S.cin_grp[t0 + t] : -1; cc[t] = ok ? S.ccoef[(size_t)(t0 + t) * 4 + c] : 0.0; }
+#pragma unroll
+    for (int t = 0; t < 4; t++) uu[t] = gg[t] >= 0 ? __ldcg(S.u_con + (size_t)gg[t] * 3 + j) : 0.0;
+#pragma unroll
+    for (int t = 0; t < 4; t++) y = fma(cc[t], uu[t], y);
+  }
+  return y;
+}
+
+template <int K>
+__device__ __forceinline__ double diag_smem(const SolveDev& S, const Loc& L, int li, int j, int c, const D4& Aj) {
+  double d;
+  if (c < 3) {
+    const double w2 = S.w_rot * S.w_rot;
+    const double o1 = c == 0 ? Aj.b : Aj.a, o2 = c == 2 ? Aj.b : Aj.c, own = c == 0 ? Aj.a : c == 1 ? Aj.b : Aj.c;
+    d = w2 * (o1 * o1 + o2 * o2 + 4.0 * own * own);
+    const float* be = reinterpret_cast<const float*>(L.be + (size_t)li * K) + c;
+    double acc = 0.0;
+#pragma unroll
+    for (int s = 0; s < K; s++) acc = fma((double)be[4 * s], (double)be[4 * s], acc);
+    d = fma(S.w_reg * S.w_reg, acc, d);
+  } else {
+    d = S.w_reg * S.w_reg * (double)(K + (L.ine[li] - L.inb[li]) + L.sic[li]);
+  }
+  int cur = -1; double sa = 0.0;
+  for (int t = L.cb[li]; t < L.ce[li]; t++) {
+    const int g = S.cin_grp[t];
+    if (g != cur) { d = fma(sa, sa, d); sa = 0.0; cur = g; }
+    sa += S.ccoef[(size_t)t * 4 + c];
+  }
+  return fma(sa, sa, d);
+}
+
+template <int K>
+__global__ void __launch_bounds__(SM_THREADS, 1) k_solve_smem(SolveDev S, int NL, unsigned* counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Loc L;
+  {
+    double* d = reinterpret_cast<double*>(smem_raw);
+    L.xs = d; d += (size_t)NL * 12; L.rs = d; d += (size_t)NL * 12; L.zs = d; d += (size_t)NL * 12;
+    L.ps = d; d += (size_t)NL * 12; L.hs = d; d += (size_t)NL * 12; L.ds = d; d += (size_t)NL * 12;
+    L.us = d; d += (size_t)NL * K * 3;
+    if ((NL * K * 3) & 1) d += 1;  // keep 16-byte alignment for the float4 array
+    L.be = reinterpret_cast<float4*>(d);
+    int* ip = reinterpret_cast<int*>(L.be + (size_t)NL * K);
+    L.nbr = ip; ip += (size_t)NL * K; L.o2i = ip; ip += (size_t)NL * K;
+    L.inb = ip; ip += NL; L.ine = ip; ip += NL; L.cb = ip; ip += NL; L.ce = ip; ip += NL; L.sic = ip; ip += NL; L.fr = ip;
+  }
+  const int M = S.M, B = gridDim.x, b = blockIdx.x, tid = threadIdx.x;
+  L.b = b; L.B = B; L.nloc = M > b ? (M - b + B - 1) / B : 0;
+  const int nloc = L.nloc, NU = nloc * 12;
+  int phase = 0;
+  double red[SM_NRED];
+
+  // ---- slice set-up: graph meta, per-edge constants, x = identity
+  for (int li = tid; li < nloc; li += SM_THREADS) {
+    const int i = li * B + b;
+    L.fr[li] = S.node_free[i]; L.inb[li] = S.in_off[i]; L.ine[li] = S.in_off[i + 1];
+    L.cb[li] = S.cin_off[i]; L.ce[li] = S.cin_off[i + 1]; L.sic[li] = S.static_in_cnt[i];
+    for (int t = S.cin_off[i]; t < S.cin_off[i + 1]; t++) {   // w_con wei (v_c - g_q, 1) (Deform.cpp:325-328)
+      const int m = S.cin_member[t];
+      const double wv = S.w_con * S.anc_w[m * K + S.cin_slot[t]];
+      double* c = S.ccoef + (size_t)t * 4;
+      c[0] = wv * (double)(S.node_pos[3 * m] - S.node_pos[3 * i]);
+      c[1] = wv * (double)(S.node_pos[3 * m + 1] - S.node_pos[3 * i + 1]);
+      c[2] = wv * (double)(S.node_pos[3 * m + 2] - S.node_pos[3 * i + 2]);
+      c[3] = wv;
+    }
+  }
+  for (int e = tid; e < nloc * K; e += SM_THREADS) {
+    const int li = e / K, s = e - li * K, i = li * B + b;
+    const int q = S.nbr[i * K + s];
+    L.nbr[e] = S.node_free[q] ? q : (q | (int)0x80000000); L.o2i[e] = S.out_to_in[i * K + s];
+    L.be[e] = make_float4(S.node_pos[3 * q] - S.node_pos[3 * i], S.node_pos[3 * q + 1] - S.node_pos[3 * i + 1],
+                          S.node_pos[3 * q + 2] - S.node_pos[3 * i + 2], 1.0f);   // float differences (Deform.cpp:254-256)
+  }
+  {  // constraint-row entries, shared by all CTAs: (member m, slot s) -> node (or -1 if excluded), w_con wei (v_c - g_q, 1)
+    const int n_mem = S.n_groups > 0 ? S.grp_off[S.n_groups] : 0;
+    for (int id = b * SM_THREADS + tid; id < n_mem * K; id += B * SM_THREADS) {
+      const int m = id / K, sl = id - m * K, c = S.grp_member[m];
+      const int q = S.anc_idx[c * K + sl];
+      const double wv = S.w_con * S.anc_w[c * K + sl];
+      S.gent_q[id] = S.node_free[q] ? q : -1;
+      double* gc = S.gent_c + (size_t)id * 4;
+      gc[0] = wv * (double)(S.node_pos[3 * c] - S.node_pos[3 * q]);
+      gc[1] = wv * (double)(S.node_pos[3 * c + 1] - S.node_pos[3 * q + 1]);
+      gc[2] = wv * (double)(S.node_pos[3 * c + 2] - S.node_pos[3 * q + 2]);
+      gc[3] = wv;
+    }
+  }
+  for (int t = tid; t < NU; t += SM_THREADS) {
+    const int li = t / 12, qi = t - 12 * li, c = qi & 3, jj = qi >> 2;
+    const size_t go = (size_t)(li * B + b) * 12 + qi;
+    const double xv = (c == jj) ? 1.0 : 0.0;
+    L.xs[t] = xv; L.hs[t] = 0.0; L.ps[t] = 0.0; L.rs[t] = 0.0; L.zs[t] = 0.0; L.ds[t] = 0.0;
+    S.x[go] = xv; S.z[go] = 0.0; S.p0[go] = 0.0; S.p1[go] = 0.0;   // S.x doubles as the published x + h
+  }
+  red[0] = red[1] = red[2] = 0.0;
+  barrier_reduce(S, counter, phase, red);
+
+  int gn_iters = 0, halvings = 0, total_cg = 0, flag = 0;
+  double energy = 0.0, normh = 0.0, last_rel = 0.0, abs_target = -1.0, E0 = 0.0;
+  bool have_f = false;
+  double tphase[4] = {0.0, 0.0, 0.0, 0.0}, tsub[4] = {0.0, 0.0, 0.0, 0.0};
+
+  for (int gn = 0; gn < S.max_gn; gn++) {
+    gn_iters = gn + 1;
+    if (!have_f) {   // S.x holds the current x of every node (published at init / after every accepted step)
+      red[0] = rows_smem<K, 0>(S, L, L.xs, S.x, nullptr, 0.0);
+      red[1] = red[2] = 0.0;
+      barrier_reduce(S, counter, phase, red);
+      E0 = red[0];
+    }
+    energy = E0;
+    // ---- gradient, Jacobi preconditioner
+    double rz_l = 0.0, gg_l = 0.0, xx_l = 0.0;
+    for (int t = tid; t < NU; t += SM_THREADS) {
+      const int li = t / 12, qi = t - 12 * li, j = qi >> 2, c = qi & 3;
+      if (!L.fr[li]) continue;
+      const size_t ob = (size_t)li * 12;
+      const D4 A0 = ld4(L.xs + ob), A1 = ld4(L.xs + ob + 4), A2 = ld4(L.xs + ob + 8);
+      double f[6]; rot_res(A0, A1, A2, S.w_rot, f);
+      const D4 Aj = j == 0 ? A0 : j == 1 ? A1 : A2;
+      const double xv = c == 0 ? Aj.a : c == 1 ? Aj.b : c == 2 ? Aj.c : Aj.d;
+      const double g = -gather_smem<K>(S, L, li, j, c, Aj, f, xv);
+      const double di = 1.0 / diag_smem<K>(S, L, li, j, c, Aj);
+      const double zv = g * di;
+      L.ds[t] = di; L.rs[t] = g; L.zs[t] = zv; L.hs[t] = 0.0;
+      S.z[(size_t)(li * B + b) * 12 + qi] = zv;
+      rz_l = fma(g, zv, rz_l); gg_l = fma(g, g, gg_l); xx_l = fma(xv, xv, xx_l);
+    }
+    red[0] = rz_l; red[1] = gg_l; red[2] = xx_l;
+    barrier_reduce(S, counter, phase, red);
+    double rz = red[0]; const double gg = red[1]; const double normv = sqrt(red[2]);
+    if (abs_target < 0.0) abs_target = S.cg_tol * S.cg_tol * gg;
+
+    // ---- PCG
+    double beta = 0.0; int cur = 0;
+    if (gg > 0.0) {
+      for (int it = 0; it < S.max_cg; it++) {
+        double* pnew = cur ? S.p1 : S.p0;
+        const double* pold = cur ? S.p0 : S.p1;
+        const unsigned long long t0 = gtime2();
+        // own p = z + beta p (shared) and publish it; remote p is recombined from the published z and p_old
+        for (int t = tid; t < NU; t += SM_THREADS) {
+          const double pv = fma(beta, L.ps[t], L.zs[t]);
+          L.ps[t] = pv;
+          pnew[(size_t)((t / 12) * B + b) * 12 + (t % 12)] = pv;
+        }
+        __syncthreads();
+        unsigned long long tm[2];
+        const unsigned long long t0b = gtime2();
+        red[0] = rows_smem<K, 1>(S, L, L.ps, S.z, pold, beta, tm);
+        red[1] = red[2] = 0.0;
+        const unsigned long long t1 = gtime2();
+        barrier_reduce(S, counter, phase, red);
+        const unsigned long long t2 = gtime2();
+        const double pHp = red[0];
+        const double alpha = rz / pHp;
+        double rzn_l = 0.0, rr_l = 0.0;
+        for (int t = tid; t < NU; t += SM_THREADS) {
+          const int li = t / 12, qi = t - 12 * li, j = qi >> 2, c = qi & 3;
+          if (!L.fr[li]) continue;
+          const size_t ob = (size_t)li * 12;
+          const D4 Aj = ld4(L.xs + ob + 4 * j);
+          double u[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+          if (c < 3) {
+            const D4 A0 = ld4(L.xs + ob), A1 = ld4(L.xs + ob + 4), A2 = ld4(L.xs + ob + 8);
+            const D4 P0 = ld4(L.ps + ob), P1 = ld4(L.ps + ob + 4), P2 = ld4(L.ps + ob + 8);
+            rot_lin(A0, A1, A2, P0, P1, P2, S.w_rot, u);
+          }
+          const double pv = L.ps[t];
+          const double y = gather_smem<K>(S, L, li, j, c, Aj, u, pv);
+          L.hs[t] = fma(alpha, pv, L.hs[t]);
+          const double rv = fma(-alpha, y, L.rs[t]);
+          L.rs[t] = rv;
+          const double zv = rv * L.ds[t];
+          L.zs[t] = zv;
+          S.z[(size_t)(li * B + b) * 12 + qi] = zv;
+          rzn_l = fma(rv, zv, rzn_l); rr_l = fma(rv, rv, rr_l);
+        }
+        red[0] = rzn_l; red[1] = rr_l; red[2] = 0.0;
+        const unsigned long long t3 = gtime2();
+        barrier_reduce(S, counter, phase, red);
+        const unsigned long long t4 = gtime2();
+        tsub[0] += (double)(t0b - t0); tsub[1] += (double)(tm[0] - t0b); tsub[2] += (double)(tm[1] - tm[0]); tsub[3] += (double)(t1 - tm[1]);
+        tphase[0] += (double)(t1 - t0); tphase[1] += (double)(t2 - t1); tphase[2] += (double)(t3 - t2); tphase[3] += (double)(t4 - t3);
+        total_cg++;
+        const double rzn = red[0], rr = red[1];
+        last_rel = sqrt(rr / gg);
+        cur ^= 1;
+        if (!(pHp > 0.0) || !(rr == rr)) { flag |= 1; break; }
+        if (rr <= abs_target || rr <= 1e-30 * gg) break;
+        beta = rzn / rz; rz = rzn;
+        if (it == S.max_cg - 1) flag |= 2;
+      }
+    }
+
+    // ---- step halving (Deform.cpp:144-156): publish x + h, evaluate, accept or halve
+    bool accepted = false;
+    for (double alpha_ls = 1.0; alpha_ls > 1e-15; alpha_ls *= 0.5) {
+      double hh_l = 0.0;
+      for (int t = tid; t < NU; t += SM_THREADS) {
+        const double hv = L.hs[t];
+        hh_l = fma(hv, hv, hh_l);
+        const double xv = L.xs[t] + hv;
+        L.zs[t] = xv;                                                       // zs is free between linear solves: holds x + h
+        S.x[(size_t)((t / 12) * B + b) * 12 + (t % 12)] = xv;
+      }
+      red[0] = 0.0; red[1] = hh_l; red[2] = 0.0;
+      barrier_reduce(S, counter, phase, red);
+      const double hh = red[1];
+      red[0] = rows_smem<K, 0>(S, L, L.zs, S.x, nullptr, 0.0);
+      red[1] = red[2] = 0.0;
+      barrier_reduce(S, counter, phase, red);
+      const double E1 = red[0];
+      if (E1 > E0) {
+        for (int t = tid; t < NU; t += SM_THREADS) L.hs[t] *= 0.5;
+        halvings++;
+        normh = 0.5 * sqrt(hh);
+        __syncthreads();
+      } else {
+        for (int t = tid; t < NU; t += SM_THREADS) L.xs[t] = L.zs[t];
+        normh = sqrt(hh);
+        E0 = E1; have_f = true; accepted = true;   // S.x already holds the accepted x; row buffers hold f(x)
+        __syncthreads();
+        break;
+      }
+    }
+    if (!accepted) {
+      // restore the published x; f(x) must be recomputed
+      for (int t = tid; t < NU; t += SM_THREADS) S.x[(size_t)((t / 12) * B + b) * 12 + (t % 12)] = L.xs[t];
+      red[0] = red[1] = red[2] = 0.0;
+      barrier_reduce(S, counter, phase, red);
+      have_f = false;
+    }
+    if (normh < (normv + 1e-6) * 1e-6) break;
+  }
+
+  // putFreeInputs (Deform.hpp:140-151)
+  for (int t = tid; t < NU; t += SM_THREADS) {
+    const int li = t / 12, qi = t - 12 * li, jj = qi >> 2, c = qi & 3, i = li * B + b;
+    const double v = L.xs[t];
+    if (c < 3) S.rot_out[(size_t)i * 9 + jj + 3 * c] = v; else S.trans_out[(size_t)i * 3 + jj] = v;
+  }
+  if (b == 0 && tid == 0) {
+    S.stats[0] = gn_iters; S.stats[1] = energy; S.stats[2] = halvings; S.stats[3] = normh;
+    S.stats[4] = total_cg; S.stats[5] = last_rel; S.stats[6] = flag;
+    S.stats[8] = tphase[0]; S.stats[9] = tphase[1]; S.stats[10] = tphase[2]; S.stats[11] = tphase[3]; S.stats[12] = gridDim.x;
+    S.stats[13] = tsub[0]; S.stats[14] = tsub[1]; S.stats[15] = tsub[2]; S.stats[7] = tsub[3];
+  }
+}
+
+size_t solve_smem_bytes(int NL, int K) {
+  size_t d = (size_t)NL * 12 * 6 + (size_t)NL * K * 3;
+  if ((NL * K * 3) & 1) d += 1;
+  return d * 8 + (size_t)NL * K * 16 + (size_t)NL * K * 8 + (size_t)NL * 6 * 4 + 64;
+}
+
+// returns ARAP_OK if launched, -1 if the slice does not fit (caller falls back to the global-memory kernel)
+int launch_solve_smem(const SolveDev& S, unsigned* counter, cudaStream_t st) {
+  if (S.k != 8 && S.k != 10 && S.k != 12) return -1;
+  int dev = 0, sms = 0, max_smem = 0;
+  ARAP_CUDA_TRY(cudaGetDevice(&dev));
+  ARAP_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  ARAP_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  // small graphs: fewer CTAs (>= ~24 nodes each) make the barriers cheaper
+  int grid = std::max(1, std::min(sms, (S.M + 23) / 24));
+  const int NL = (S.M + grid - 1) / grid;
+  const size_t smem = solve_smem_bytes(NL, S.k);
+  if (smem > (size_t)max_smem - 2048) return -1;
+  void* kern = S.k == 8 ? (void*)k_solve_smem<8> : S.k == 10 ? (void*)k_solve_smem<10> : (void*)k_solve_smem<12>;
+  ARAP_CUDA_TRY(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  ARAP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kern, SM_THREADS, smem));
+  if (per_sm < 1) return -1;
+  ARAP_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
+  SolveDev Sc = S; int nl = NL; unsigned* cnt = counter;
+  void* args[] = {(void*)&Sc, (void*)&nl, (void*)&cnt};
+  ARAP_CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(SM_THREADS), args, smem, st));
+  return ARAP_OK;
+}
+
+}  // namespace arapgs

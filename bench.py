@@ -219,7 +219,8 @@ def run_own(args):
         "stages_ms": {"solve": round(float(mean[0]), 4), "sample_advect": round(float(mean[1]), 4), "endpoint_lbs": round(float(mean[2]), 4),
                       "six_point_fit": round(float(mean[3]), 4), "sample_sh_rotate": round(float(mean[4]), 4)},
         "solve": {"gn_iters": st["gn_iters"], "cg_iters": st["cg_iters"], "flags": st["flags"], "grid_blocks": st["grid_blocks"],
-                  "phase_us_per_cg_iter": [round(x / 1e3 / max(st["cg_iters"], 1), 2) for x in st["phase_ns"]]},
+                  "phase_us_per_cg_iter": [round(x / 1e3 / max(st["cg_iters"], 1), 2) for x in st["phase_ns"]],
+                  "row_phase_split_us": [round(x / 1e3 / max(st["cg_iters"], 1), 2) for x in st["row_sub_ns"]]},
         "apply_gaussians_per_s": round(N / (apply_ms * 1e-3), 1) if apply_ms > 0 else None,
         "setup_s": {"grid_build_eval": round(setup["t_grid_s"], 3), "graph_knn": round(setup["t_graph_s"], 3)},
         "roofline": {"bound": "hbm", "kernel": "apply pass (d): k_lbs_points<endpoints> + k_fit_gaussians", "achieved": round(apply_gbs, 1),

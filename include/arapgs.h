@@ -55,6 +55,7 @@ typedef struct arap_params {
   int max_cg_iters;    /* PCG iteration cap per linear system */
   double cg_tol;       /* relative residual of the first linear system of a step */
   int skip_static_endpoints; /* 0 = reference behaviour (all endpoints skinned) */
+  int solver_global_memory;  /* 1 = force the global-memory solver kernel (default 0: shared-memory-resident kernel when it fits) */
 } arap_params;
 
 typedef struct arap_solve_stats {
@@ -67,6 +68,7 @@ typedef struct arap_solve_stats {
   double last_rel_residual;
   double phase_ns[4];  /* block 0's time in: row phase, barrier 1, gather/update phase, barrier 2 (summed over PCG iterations) */
   int grid_blocks;     /* cooperative grid size used */
+  double row_sub_ns[4]; /* row phase split: form p, E_reg rows, E_rot rows, constraint rows (shared-memory kernel only) */
 } arap_solve_stats;
 
 typedef struct arap_grid_info {
