@@ -35,13 +35,14 @@ class Params(C.Structure):
                 ("high_quality", C.c_int), ("lpf_parameter", C.c_float),
                 ("w_rot", C.c_double), ("w_reg", C.c_double), ("w_con", C.c_double),
                 ("max_gn_iters", C.c_int), ("max_cg_iters", C.c_int), ("cg_tol", C.c_double),
-                ("skip_static_endpoints", C.c_int), ("solver_global_memory", C.c_int)]
+                ("skip_static_endpoints", C.c_int), ("solver_global_memory", C.c_int), ("reserved0", C.c_int),
+                ("newton_eta0", C.c_double)]
 
 
 class SolveStats(C.Structure):
     _fields_ = [("gn_iters", C.c_int), ("cg_iters", C.c_int), ("halvings", C.c_int), ("flags", C.c_int),
                 ("energy", C.c_double), ("normh", C.c_double), ("last_rel_residual", C.c_double),
-                ("phase_ns", C.c_double * 4), ("grid_blocks", C.c_int), ("row_sub_ns", C.c_double * 4)]
+                ("phase_ns", C.c_double * 4), ("grid_blocks", C.c_int), ("row_sub_ns", C.c_double * 4), ("cg_iters_gn", C.c_int * 8)]
 
 
 class GridInfo(C.Structure):
@@ -360,7 +361,8 @@ class Session:
         s = SolveStats()
         check(lib().arap_solve_stats_get(self._ctx, C.byref(s)))
         return dict(gn_iters=s.gn_iters, cg_iters=s.cg_iters, halvings=s.halvings, flags=s.flags, energy=s.energy,
-                    normh=s.normh, last_rel_residual=s.last_rel_residual, phase_ns=list(s.phase_ns), grid_blocks=s.grid_blocks, row_sub_ns=list(s.row_sub_ns))
+                    normh=s.normh, last_rel_residual=s.last_rel_residual, phase_ns=list(s.phase_ns), grid_blocks=s.grid_blocks, row_sub_ns=list(s.row_sub_ns),
+                    cg_iters_gn=list(s.cg_iters_gn))
 
     def apply(self):
         check(lib().arap_apply(self._ctx))

@@ -63,6 +63,7 @@ typedef struct ArapSolveParams {
   int max_cg_iters;
   double cg_tol;               // relative residual of the first linear system; later ones reuse its absolute value
   int force_global_kernel;     // 1: skip the shared-memory-resident fast path (tests)
+  double newton_eta0;          // > 0: inexact Newton forcing (shared-memory kernel only), see arapgs.h
 } ArapSolveParams;
 
 size_t arapk_solve_workspace_bytes(int M, int k, int n_groups);

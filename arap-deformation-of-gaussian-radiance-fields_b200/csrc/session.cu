@@ -193,7 +193,7 @@ extern "C" int arap_default_params(arap_params* p) {
   if (!p) return ARAP_ERR_INVALID;
   p->grid_num = 64; p->padding = 1; p->knn_k = 10; p->node_num = 150; p->high_quality = 0; p->lpf_parameter = 0.2f;
   p->w_rot = 1.0; p->w_reg = 10.0; p->w_con = 100.0; p->max_gn_iters = 30; p->max_cg_iters = 4000; p->cg_tol = 1e-10;
-  p->skip_static_endpoints = 0; p->solver_global_memory = 0;
+  p->skip_static_endpoints = 0; p->solver_global_memory = 0; p->reserved0 = 0; p->newton_eta0 = 1e-6;
   return ARAP_OK;
 }
 
@@ -215,7 +215,7 @@ extern "C" int arap_create(arap_ctx** out, int device, void* stream, const arap_
   if (stream) c->stream = (cudaStream_t)stream;
   else { ARAP_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
   if (params) c->prm = *params; else arap_default_params(&c->prm);
-  ARAP_CUDA_TRY(cudaMallocHost((void**)&c->stats_h, 16 * sizeof(double)));
+  ARAP_CUDA_TRY(cudaMallocHost((void**)&c->stats_h, 32 * sizeof(double)));
   for (auto& row : c->evr) for (auto& ev : row) ARAP_CUDA_TRY(cudaEventCreate(&ev));
   *out = c.release();
   return ARAP_OK;
@@ -493,7 +493,7 @@ static int finish_graph(arap_ctx* c, int k) {
   TRY(knn_family(c, c->sample_pos.p, c->S, k, c->sample_rows, true));
   TRY(knn_family(c, c->mesh_pts.p, c->Mp, k, c->mesh_rows, false));
   // solve outputs
-  TRY(c->rot_d.alloc((size_t)M * 9)); TRY(c->trans_d.alloc((size_t)M * 3)); TRY(c->stats_d.alloc(16));
+  TRY(c->rot_d.alloc((size_t)M * 9)); TRY(c->trans_d.alloc((size_t)M * 3)); TRY(c->stats_d.alloc(32));
   TRY(c->node_xf.alloc((size_t)M * 112)); TRY(c->node_q.alloc((size_t)M * 4));
   TRY(c->node_free.alloc((size_t)M)); TRY(c->node_static.alloc((size_t)M)); TRY(c->static_in_cnt.alloc((size_t)M)); TRY(c->active_mult.alloc((size_t)M));
   TRY(c->center_tmp.alloc(4));
@@ -732,7 +732,7 @@ extern "C" int arap_solve(arap_ctx* ctx, int on_center) {
   G.anc_idx = ctx->anc_idx.p; G.anc_w = ctx->anc_w.p; G.node_free = ctx->node_free.p; G.static_in_cnt = ctx->static_in_cnt.p;
   G.grp_off = cs.grp_off.p; G.grp_member = cs.grp_member.p; G.grp_aim = cs.grp_aim.p;
   G.cin_off = cs.cin_off.p; G.cin_grp = cs.cin_grp.p; G.cin_member = cs.cin_member.p; G.cin_slot = cs.cin_slot.p; G.n_cin_entries = cs.n_entries;
-  ArapSolveParams P{ctx->prm.w_rot, ctx->prm.w_reg, ctx->prm.w_con, ctx->prm.max_gn_iters, ctx->prm.max_cg_iters, ctx->prm.cg_tol, ctx->prm.solver_global_memory};
+  ArapSolveParams P{ctx->prm.w_rot, ctx->prm.w_reg, ctx->prm.w_con, ctx->prm.max_gn_iters, ctx->prm.max_cg_iters, ctx->prm.cg_tol, ctx->prm.solver_global_memory, ctx->prm.newton_eta0};
   TRY(ctx->solve_ws.alloc(arapk_solve_workspace_bytes(G.M, G.k, G.n_groups)));
   TRY(arapk_solve(&G, &P, ctx->solve_ws.p, ctx->solve_ws.n, ctx->rot_d.p, ctx->trans_d.p, ctx->stats_d.p, st));
   ctx->solved = true;
@@ -741,7 +741,7 @@ extern "C" int arap_solve(arap_ctx* ctx, int on_center) {
 
 extern "C" int arap_solve_stats_get(arap_ctx* ctx, arap_solve_stats* o) {
   GRAPH_CHECK(ctx); if (!o) return ARAP_ERR_INVALID;
-  ARAP_CUDA_TRY(cudaMemcpyAsync(ctx->stats_h, ctx->stats_d.p, 16 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  ARAP_CUDA_TRY(cudaMemcpyAsync(ctx->stats_h, ctx->stats_d.p, 32 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   ARAP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   const double* s = ctx->stats_h;
   o->gn_iters = (int)s[0]; o->energy = s[1]; o->halvings = (int)s[2]; o->normh = s[3]; o->cg_iters = (int)s[4];
@@ -749,6 +749,7 @@ extern "C" int arap_solve_stats_get(arap_ctx* ctx, arap_solve_stats* o) {
   for (int t = 0; t < 4; t++) o->phase_ns[t] = s[8 + t];
   o->grid_blocks = (int)s[12];
   o->row_sub_ns[0] = s[13]; o->row_sub_ns[1] = s[14]; o->row_sub_ns[2] = s[15]; o->row_sub_ns[3] = s[7];
+  for (int t = 0; t < 8; t++) o->cg_iters_gn[t] = (int)s[16 + t];
   return ARAP_OK;
 }
 

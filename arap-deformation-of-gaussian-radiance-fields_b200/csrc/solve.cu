@@ -455,6 +455,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveDev S) {
   if (gthread == 0) {
     S.stats[0] = gn_iters; S.stats[1] = energy; S.stats[2] = halvings; S.stats[3] = normh;
     S.stats[4] = total_cg; S.stats[5] = last_rel; S.stats[6] = flag;
+    for (int t = 13; t < 24; t++) S.stats[t] = 0.0;
     S.stats[8] = tphase[0]; S.stats[9] = tphase[1]; S.stats[10] = tphase[2]; S.stats[11] = tphase[3]; S.stats[12] = gridDim.x;
   }
 }
@@ -486,6 +487,7 @@ extern "C" int arapk_solve(const ArapSolveGraph* G, const ArapSolveParams* P, vo
   S.max_gn = P->max_gn_iters > 0 ? P->max_gn_iters : 30;
   S.max_cg = P->max_cg_iters > 0 ? P->max_cg_iters : 4000;
   S.cg_tol = P->cg_tol > 0 ? P->cg_tol : 1e-10;
+  S.eta0 = P->newton_eta0 > 0 ? P->newton_eta0 : 0.0;
   double* w = (double*)workspace;
   const size_t v12 = (size_t)G->M * 12;
   S.x = w; w += v12; S.h = w; w += v12; S.r = w; w += v12; S.z = w; w += v12; S.p0 = w; w += v12; S.p1 = w; w += v12; S.dinv = w; w += v12;

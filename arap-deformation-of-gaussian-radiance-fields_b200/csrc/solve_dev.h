@@ -25,7 +25,7 @@ struct SolveDev {
   const int* cin_slot;
   double w_rot, w_reg, w_con;  // square-rooted (Deform.hpp:452-454)
   int max_gn, max_cg;
-  double cg_tol;
+  double cg_tol, eta0;
   // work (double).  Vectors: [M][3][4]
   double *x, *h, *r, *z, *p0, *p1, *dinv, *bedge /* M x k x 4 */, *ccoef /* cin entries x 4 */;
   double *u_reg /* M x k x 3 */, *u_in /* in-edges x 3 */, *u_con /* groups x 3 */;

@@ -58,10 +58,13 @@ def test_grid_eval_matches_oracle(pkg, scenes):
     assert op.max() > 0.1
 
 
+@pytest.mark.parametrize("eta0", [0.0, 1e-6])
 @pytest.mark.parametrize("on_center", [False, True])
-def test_drag_steps_match_oracle(pkg, scenes, on_center):
-    """T_step path: solve + sample advect + apply + sample SH, several steps, free-running on both sides."""
+def test_drag_steps_match_oracle(pkg, scenes, on_center, eta0):
+    """T_step path: solve + sample advect + apply + sample SH, several steps, free-running on both sides.
+    eta0 = 0: every Gauss-Newton system solved to the cg_tol target; 1e-6 (default): first system stops 4 decades earlier."""
     sc, s, o, gi, og = _pair(pkg, scenes, n=30000, grid_num=32, knn_k=8, node_num=150)
+    s.set_params(newton_eta0=eta0)
     s.grid_eval(0); o.grid_eval(0)
     g = s.graph_build_fps(); o.graph_build_fps()
     assert np.array_equal(g["anchor"], o.anchor)
@@ -81,7 +84,7 @@ def test_drag_steps_match_oracle(pkg, scenes, on_center):
         st = s.solve_stats()
         _, rot, trans = s.download_nodes()
         assert st["flags"] == 0 and st["gn_iters"] == st_o["iters"] and st["halvings"] == st_o["halvings"]
-        assert np.abs(rot - o.rot).max() <= 2e-8 and np.abs(trans - o.trans).max() <= 2e-8
+        assert np.abs(rot - o.rot).max() <= 2e-9 and np.abs(trans - o.trans).max() <= 2e-9
         assert np.isclose(st["energy"], st_o["energy"], rtol=1e-6)
         s.apply(); o.apply()
     _compare_gaussians(s.download_gaussians(), o.g)
