@@ -14,6 +14,7 @@
 //   idx[(blk*K + j)*32 + lane]  (uint16)     w[(blk*K + j)*32 + lane]  (double)
 // so a warp reading neighbour j of 32 consecutive rows issues one 64 B and one
 // 256 B fully-coalesced request.
+#include <algorithm>
 #include "device_math.cuh"
 #include "sh_fast.cuh"
 #include "kernels.h"
@@ -267,72 +268,123 @@ __global__ void k_node_quats(int M, const double* __restrict__ rot, float4* __re
 }
 
 // ------------------------------------------------------------------ sample SH rotation
-// One thread per sample, 64-sample tiles staged through shared memory so the
-// 192 B feature rows move as coalesced float4.  Skinning weights (float) and
-// node ids use the same 32-row blocked layout as the LBS tables.
+// Persistent CTAs, 128-sample tiles, two shared-memory stages filled with 16-byte cp.async: the next tile's 24.5 KB
+// of SH rows is in flight while the current tile's quaternions are blended and its rows rotated, so DRAM stays busy
+// at 4 CTAs / SM without needing occupancy to hide the load -> compute -> store phases of a tile.
+// Rows sit at a 13-chunk (208 B) pitch: a thread's 12 LDS.128 / STS.128 on its own row are conflict-free
+// (13 r + c mod 8 is a permutation over 8 consecutive rows).  Static samples are copied through unchanged.
+// Skinning weights (float) and node ids use the same 32-row blocked layout as the LBS tables.
 constexpr int RS_TILE = 128;
-__global__ void __launch_bounds__(RS_TILE, 8)
-k_rotate_sample_shs(long long S, int k, const float* __restrict__ w, const uint16_t* __restrict__ idx,
+constexpr int RS_PITCH4 = 13;                       // float4 chunks per staged row
+constexpr int RS_STAGE4 = RS_TILE * RS_PITCH4;      // float4 per stage
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// the rare sin branch of Q_SlerpCUDA, kept out of line so the blend loop stays small
+__device__ __noinline__ void slerp_ratios_slow(float cf, float t, float& rA, float& rB) {
+  const double cosa = (double)cf, td = (double)t;
+  const double sina = sqrt(1.0 - cosa * cosa);
+  const double ang = atan2(sina, cosa);
+  rA = (float)(sin((1.0 - td) * ang) / sina);
+  rB = (float)(sin(td * ang) / sina);
+}
+
+template <int K>
+__global__ void __launch_bounds__(RS_TILE, 3)
+k_rotate_sample_shs(long long S, long long ntiles, int k, const float* __restrict__ w, const uint16_t* __restrict__ idx,
                     const float4* __restrict__ q_xyzw, const uint8_t* __restrict__ is_static,
                     float* __restrict__ feature) {
-  extern __shared__ float smem[];
-  float* s_sh = smem;
-  __shared__ uint8_t s_static[RS_TILE];
-  const long long s0 = (long long)blockIdx.x * RS_TILE;
+  // stage = [SH rows: RS_STAGE4 float4][weights: 128 K float][node ids: 128 K u16], all blocked like the global tables
+  // K = compile-time bound of the neighbour count k (register arrays); k sets the table layout
+  const int STAGE16 = RS_STAGE4 + k * 32 + k * 16;   // 16-byte units
+  extern __shared__ float4 s_tile[];
   const int tid = threadIdx.x;
-  const int rows = (int)min((long long)RS_TILE, S - s0);
-  s_static[tid] = (tid < rows) ? (is_static ? is_static[s0 + tid] : 0) : 1;
-  __syncthreads();
-  const float* gsh = feature + s0 * SH_FLOATS;
-  for (int v = tid; v < rows * 12; v += RS_TILE) {
-    const int r = v / 12, c4 = v - r * 12;
-    if (s_static[r]) continue;
-    const float4 x = ld_stream4(gsh + (size_t)v * 4);
-    float* d = s_sh + r * SH_PITCH + c4 * 4;
-    d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w;
-  }
-  __syncthreads();
-  const long long s = s0 + tid;
-  if (tid < rows && !s_static[tid]) {
-    Quat wq{1.0f, 0.0f, 0.0f, 0.0f};
-    float last = 0.0f;
-    const long long base = (s >> 5) * (long long)(k * 32) + (s & 31);
-    for (int j = 0; j < k; j++) {
-      // Q_SlerpCUDA (cudakdtree.cu:113-148).  The reference mixes double ratios with float quaternions; here the
-      // common lerp branch (incremental steps: cos > 0.99995) runs in float, the sin branch keeps double ratios.
-      // Quaternions agree with the reference's to ~1e-7, far inside the sample-SH tolerance.
-      const float cw = w[base + j * 32];
-      const float t = __fdividef(cw, cw + last);
-      const float4 e = __ldg(q_xyzw + idx[base + j * 32]);
-      Quat eq{e.w, e.x, e.y, e.z};
-      float cf = wq.x * eq.x + wq.y * eq.y + wq.z * eq.z + wq.w * eq.w;
-      if (cf < 0.0f) { eq.x = -eq.x; eq.y = -eq.y; eq.z = -eq.z; eq.w = -eq.w; cf = -cf; }
-      float rA, rB;
-      if (cf > 0.99995f) { rA = 1.0f - t; rB = t; }
-      else {
-        const double cosa = (double)cf, td = (double)t;
-        const double sina = sqrt(1.0 - cosa * cosa);
-        const double ang = atan2(sina, cosa);
-        rA = (float)(sin((1.0 - td) * ang) / sina);
-        rB = (float)(sin(td * ang) / sina);
-      }
-      Quat l;
-      l.x = fmaf(rA, wq.x, rB * eq.x); l.y = fmaf(rA, wq.y, rB * eq.y);
-      l.z = fmaf(rA, wq.z, rB * eq.z); l.w = fmaf(rA, wq.w, rB * eq.w);
-      const float inv = rsqrtf(quat_n2(l));
-      wq = Quat{l.w * inv, l.x * inv, l.y * inv, l.z * inv};
-      last += cw;
+  auto issue = [&](long long tile, int stage) {
+    const long long s0 = tile * RS_TILE;
+    const int rows = (int)min((long long)RS_TILE, S - s0);
+    const float4* g = reinterpret_cast<const float4*>(feature + s0 * SH_FLOATS);
+    float4* d = s_tile + stage * STAGE16;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      const int v = tid + i * RS_TILE;
+      const int r = v / 12, c4 = v - r * 12;
+      if (r < rows) cp_async16(d + r * RS_PITCH4 + c4, g + v);
     }
-    float R[3][3]; quat_to_matrix(quat_normalized(wq), R);
-    sh_rotate_flipped_fast(R, s_sh + tid * SH_PITCH);
-  }
-  __syncthreads();
-  float* osh = feature + s0 * SH_FLOATS;
-  for (int v = tid; v < rows * 12; v += RS_TILE) {
-    const int r = v / 12, c4 = v - r * 12;
-    if (s_static[r]) continue;
-    const float* d = s_sh + r * SH_PITCH + c4 * 4;
-    st_stream4(osh + (size_t)v * 4, make_float4(d[0], d[1], d[2], d[3]));
+    const int nblk = (rows + 31) >> 5;
+    const float4* gw = reinterpret_cast<const float4*>(w + (s0 >> 5) * (long long)(k * 32));
+    const float4* gi = reinterpret_cast<const float4*>(idx + (s0 >> 5) * (long long)(k * 32));
+    for (int c = tid; c < nblk * k * 8; c += RS_TILE) cp_async16(d + RS_STAGE4 + c, gw + c);
+    for (int c = tid; c < nblk * k * 4; c += RS_TILE) cp_async16(d + RS_STAGE4 + k * 32 + c, gi + c);
+  };
+  long long tile = blockIdx.x;
+  if (tile < ntiles) issue(tile, 0);
+  cp_async_commit();
+  for (int it = 0; tile < ntiles; tile += gridDim.x, it++) {
+    const int stage = it & 1;
+    const long long s0 = tile * RS_TILE;
+    const int rows = (int)min((long long)RS_TILE, S - s0);
+    const bool stat = (is_static && tid < rows) ? is_static[s0 + tid] != 0 : false;
+    const long long next = tile + gridDim.x;
+    if (next < ntiles) issue(next, stage ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    float4* st4 = s_tile + stage * STAGE16;
+    const bool live = tid < rows && !stat;
+    if (live) {
+      const float* sw = reinterpret_cast<const float*>(st4 + RS_STAGE4) + (tid >> 5) * (k * 32) + (tid & 31);
+      const uint16_t* si = reinterpret_cast<const uint16_t*>(st4 + RS_STAGE4 + k * 32) + (tid >> 5) * (k * 32) + (tid & 31);
+      float4 e[K]; float cw[K];
+#pragma unroll
+      for (int j = 0; j < K; j++) if (j < k) { e[j] = __ldg(q_xyzw + si[j * 32]); cw[j] = sw[j * 32]; }
+      Quat wq{1.0f, 0.0f, 0.0f, 0.0f};
+      float last = 0.0f;
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        if (j >= k) break;
+        // Q_SlerpCUDA (cudakdtree.cu:113-148).  The reference mixes double ratios with float quaternions; here the
+        // common lerp branch (incremental steps: cos > 0.99995) runs in float, the sin branch keeps double ratios.
+        // Quaternions agree with the reference's to ~1e-7, far inside the sample-SH tolerance.
+        const float t = __fdividef(cw[j], cw[j] + last);
+        Quat eq{e[j].w, e[j].x, e[j].y, e[j].z};
+        float cf = wq.x * eq.x + wq.y * eq.y + wq.z * eq.z + wq.w * eq.w;
+        if (cf < 0.0f) { eq.x = -eq.x; eq.y = -eq.y; eq.z = -eq.z; eq.w = -eq.w; cf = -cf; }
+        float rA, rB;
+        if (cf > 0.99995f) { rA = 1.0f - t; rB = t; }
+        else slerp_ratios_slow(cf, t, rA, rB);
+        Quat l;
+        l.x = fmaf(rA, wq.x, rB * eq.x); l.y = fmaf(rA, wq.y, rB * eq.y);
+        l.z = fmaf(rA, wq.z, rB * eq.z); l.w = fmaf(rA, wq.w, rB * eq.w);
+        const float inv = rsqrtf(quat_n2(l));
+        wq = Quat{l.w * inv, l.x * inv, l.y * inv, l.z * inv};
+        last += cw[j];
+      }
+      float R[3][3];
+      quat_to_matrix(quat_normalized(wq), R);
+      float4* row = st4 + tid * RS_PITCH4;
+      float v[SH_FLOATS];
+#pragma unroll
+      for (int c = 0; c < 12; c++) { const float4 x = row[c]; v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w; }
+      sh_rotate_flipped_fast(R, v);
+#pragma unroll
+      for (int c = 1; c < 12; c++) row[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      row[0].w = v[3];   // DC term (floats 0-2) is rotation invariant
+    }
+    __syncthreads();
+    float4* o = reinterpret_cast<float4*>(feature + s0 * SH_FLOATS);
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      const int vv = tid + i * RS_TILE;
+      const int r = vv / 12, c4 = vv - r * 12;
+      if (r < rows) st_stream4(reinterpret_cast<float*>(o + vv), st4[r * RS_PITCH4 + c4]);
+    }
+    __syncthreads();
   }
 }
 
@@ -438,9 +490,22 @@ extern "C" int arapk_rotate_sample_shs(long long S, int k, const float* w, const
                                        const uint8_t* is_static, float* feature, cudaStream_t st) {
   if (S <= 0) return ARAP_OK;
   int rc = ensure_sh_tables(); if (rc) return rc;
-  const size_t smem = sizeof(float) * RS_TILE * SH_PITCH;
-  k_rotate_sample_shs<<<(unsigned)((S + RS_TILE - 1) / RS_TILE), RS_TILE, smem, st>>>(S, k, w, idx, (const float4*)q_xyzw,
-                                                                                      is_static, feature);
+  if (k < 1 || k > 12) { set_error("rotate_sample_shs: k out of range"); return ARAP_ERR_INVALID; }
+  const size_t smem = 2 * (sizeof(float4) * RS_STAGE4 + (size_t)RS_TILE * k * 6);
+  const long long ntiles = (S + RS_TILE - 1) / RS_TILE;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0; ARAP_CUDA_TRY(cudaGetDevice(&dev)); ARAP_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int mx = (int)(2 * (sizeof(float4) * RS_STAGE4 + (size_t)RS_TILE * 12 * 6));
+    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_rotate_sample_shs<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_rotate_sample_shs<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_rotate_sample_shs<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+  }
+  const unsigned nb = (unsigned)std::min<long long>(ntiles, (long long)sms * 3);
+  const float4* q4 = (const float4*)q_xyzw;
+  if (k <= 8) k_rotate_sample_shs<8><<<nb, RS_TILE, smem, st>>>(S, ntiles, k, w, idx, q4, is_static, feature);
+  else if (k <= 10) k_rotate_sample_shs<10><<<nb, RS_TILE, smem, st>>>(S, ntiles, k, w, idx, q4, is_static, feature);
+  else k_rotate_sample_shs<12><<<nb, RS_TILE, smem, st>>>(S, ntiles, k, w, idx, q4, is_static, feature);
   ARAP_KERNEL_CHECK();
   return ARAP_OK;
 }
