@@ -42,7 +42,7 @@ class Params(C.Structure):
 class SolveStats(C.Structure):
     _fields_ = [("gn_iters", C.c_int), ("cg_iters", C.c_int), ("halvings", C.c_int), ("flags", C.c_int),
                 ("energy", C.c_double), ("normh", C.c_double), ("last_rel_residual", C.c_double),
-                ("phase_ns", C.c_double * 4), ("grid_blocks", C.c_int), ("row_sub_ns", C.c_double * 4), ("cg_iters_gn", C.c_int * 8)]
+                ("phase_ns", C.c_double * 4), ("grid_blocks", C.c_int), ("row_sub_ns", C.c_double * 4), ("cg_iters_gn", C.c_int * 8), ("barrier_skew_ns", C.c_double * 6)]
 
 
 class GridInfo(C.Structure):
@@ -362,7 +362,7 @@ class Session:
         check(lib().arap_solve_stats_get(self._ctx, C.byref(s)))
         return dict(gn_iters=s.gn_iters, cg_iters=s.cg_iters, halvings=s.halvings, flags=s.flags, energy=s.energy,
                     normh=s.normh, last_rel_residual=s.last_rel_residual, phase_ns=list(s.phase_ns), grid_blocks=s.grid_blocks, row_sub_ns=list(s.row_sub_ns),
-                    cg_iters_gn=list(s.cg_iters_gn))
+                    cg_iters_gn=list(s.cg_iters_gn), barrier_skew_ns=list(s.barrier_skew_ns))
 
     def apply(self):
         check(lib().arap_apply(self._ctx))

@@ -750,6 +750,7 @@ extern "C" int arap_solve_stats_get(arap_ctx* ctx, arap_solve_stats* o) {
   o->grid_blocks = (int)s[12];
   o->row_sub_ns[0] = s[13]; o->row_sub_ns[1] = s[14]; o->row_sub_ns[2] = s[15]; o->row_sub_ns[3] = s[7];
   for (int t = 0; t < 8; t++) o->cg_iters_gn[t] = (int)s[16 + t];
+  for (int t = 0; t < 6; t++) o->barrier_skew_ns[t] = s[24 + t];
   return ARAP_OK;
 }
 

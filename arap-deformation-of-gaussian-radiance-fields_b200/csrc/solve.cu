@@ -503,7 +503,7 @@ extern "C" int arapk_solve(const ArapSolveGraph* G, const ArapSolveParams* P, vo
   unsigned* counter = reinterpret_cast<unsigned*>(w);
   S.rot_out = rot_out; S.trans_out = trans_out; S.stats = stats_dev;
   if (!P->force_global_kernel) {   // fast path: per-node state resident in shared memory (solve_smem.cu)
-    const int rc = launch_solve_smem(S, counter, st);
+    const int rc = launch_solve_smem(S, reinterpret_cast<unsigned*>(S.partial), st);   // barrier slots live in the partials area (2 x 148 x 64 B)
     if (rc >= 0) return rc;
   }
   int dev = 0, sms = 0, per_sm = 0;

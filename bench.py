@@ -133,6 +133,8 @@ def run_own(args):
     M, k, N, S = s.M, cfg["k"], s.N, gi["samples"]
     if args.newton_eta0 is not None:
         s.set_params(newton_eta0=args.newton_eta0)
+    if args.max_cg is not None:
+        s.set_params(max_cg_iters=args.max_cg)
 
     gather = None
     if world > 1:   # all-gather of the deformed SoA (232 B / Gaussian): pos 12 + rot 16 + scale 12 + SH 192
@@ -223,7 +225,8 @@ def run_own(args):
         "solve": {"gn_iters": st["gn_iters"], "cg_iters": st["cg_iters"], "flags": st["flags"], "grid_blocks": st["grid_blocks"],
                   "phase_us_per_cg_iter": [round(x / 1e3 / max(st["cg_iters"], 1), 2) for x in st["phase_ns"]],
                   "row_phase_split_us": [round(x / 1e3 / max(st["cg_iters"], 1), 2) for x in st["row_sub_ns"]],
-                  "cg_iters_gn": st["cg_iters_gn"][:st["gn_iters"]]},
+                  "cg_iters_gn": st["cg_iters_gn"][:st["gn_iters"]],
+                  "row_phase_last_warp_us_and_barrier_us": [round(x / 1e3 / max(st["gn_iters"], 1), 2) for x in st["barrier_skew_ns"]]},
         "apply_gaussians_per_s": round(N / (apply_ms * 1e-3), 1) if apply_ms > 0 else None,
         "setup_s": {"grid_build_eval": round(setup["t_grid_s"], 3), "graph_knn": round(setup["t_graph_s"], 3)},
         "roofline": {"bound": "hbm", "kernel": "apply pass (d): k_lbs_points<endpoints> + k_fit_gaussians", "achieved": round(apply_gbs, 1),
@@ -319,6 +322,7 @@ def main():
     ap.add_argument("--gaussians", type=int, default=0, help="override the Gaussian count per GPU (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--newton-eta0", type=float, default=None, help="override arap_params.newton_eta0 (debug)")
+    ap.add_argument("--max-cg", type=int, default=None, help="override arap_params.max_cg_iters (debug)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

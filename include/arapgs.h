@@ -76,6 +76,9 @@ typedef struct arap_solve_stats {
   int grid_blocks;     /* cooperative grid size used */
   double row_sub_ns[4]; /* row phase split: form p, E_reg rows, E_rot rows, constraint rows (shared-memory kernel only) */
   int cg_iters_gn[8];  /* PCG iterations of the first 8 Gauss-Newton iterations */
+  double barrier_skew_ns[6]; /* diagnostics sampled at PCG iteration 50 of each Gauss-Newton iteration (summed), block 0: time from the
+                                start of the row phase until its LAST warp has finished E_reg rows, E_rot rows, constraint gathers,
+                                the CTA sync, the whole phase; [5] = last CTA's arrival at the barrier -> block 0's exit */
 } arap_solve_stats;
 
 typedef struct arap_grid_info {
