@@ -18,7 +18,8 @@ CONFIGS = {
     "stripes": dict(index=0, n=200_000, s_med=0.008, grid=64, nodes=200, k=10),
     "pinocchio": dict(index=1, n=30_000, s_med=0.008, grid=64, nodes=501, k=8),
     "sphere1m": dict(index=2, n=1_000_000, s_med=0.004, grid=64, nodes=4000, k=10),
-    "shells6m": dict(index=3, n=6_000_000, s_med=0.002, grid=128, nodes=16000, k=10),
+    "shells6m": dict(index=3, n=6_000_000, s_med=0.002, grid=128, nodes=16000, k=10,
+                     samples_at_n=58_776_512),   # 64 x valid cells of the full scene (grid_build on the GPU arm)
     "shells50m": dict(index=4, n=50_000_000, s_med=0.001, grid=128, nodes=16000, k=10),
 }
 
