@@ -370,6 +370,10 @@ class Session:
     def step(self, on_center=False):
         check(lib().arap_step(self._ctx, int(bool(on_center))))
 
+    def soa_ready_wait(self, stream):
+        """Make CUDA stream `stream` (integer handle) wait for the last step's deformed SoA (see arap_soa_ready_wait)."""
+        check(lib().arap_soa_ready_wait(self._ctx, C.c_void_p(int(stream))))
+
     def download_nodes(self):
         pos, rot, trans = np.zeros((self.M, 3), f32), np.zeros((self.M, 9), f64), np.zeros((self.M, 3), f64)
         check(lib().arap_download_nodes(self._ctx, _ptr(pos), _ptr(rot), _ptr(trans)))

@@ -176,6 +176,7 @@ struct arap_ctx {
   // solve
   DBuf<double> rot_d, trans_d, stats_d; DBuf<char> solve_ws; DBuf<char> node_xf; DBuf<float> node_q;
   double* stats_h = nullptr;  // pinned
+  cudaEvent_t ev_soa = nullptr;   // recorded after the six-point fit of every apply: the rasteriser-facing SoA is final
   bool solved = false;
   // timing
   // timing: a ring of per-step event sets so a whole timed region can be read back afterwards
@@ -217,6 +218,7 @@ extern "C" int arap_create(arap_ctx** out, int device, void* stream, const arap_
   if (params) c->prm = *params; else arap_default_params(&c->prm);
   ARAP_CUDA_TRY(cudaMallocHost((void**)&c->stats_h, 32 * sizeof(double)));
   for (auto& row : c->evr) for (auto& ev : row) ARAP_CUDA_TRY(cudaEventCreate(&ev));
+  ARAP_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_soa, cudaEventDisableTiming));
   *out = c.release();
   return ARAP_OK;
 }
@@ -227,6 +229,7 @@ extern "C" int arap_destroy(arap_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->stats_h) cudaFreeHost(ctx->stats_h);
   for (auto& row : ctx->evr) for (auto& ev : row) if (ev) cudaEventDestroy(ev);
+  if (ctx->ev_soa) cudaEventDestroy(ctx->ev_soa);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return ARAP_OK;
@@ -754,8 +757,13 @@ extern "C" int arap_solve_stats_get(arap_ctx* ctx, arap_solve_stats* o) {
   return ARAP_OK;
 }
 
-// The per-step update, in the reference's order (GV:1499-1522): samples first (they use the pre-update node
-// positions), then mesh points, endpoints, node positions (double-buffered), the six-point fit, sample SH.
+// The per-step update.  The reference's order (GV:1499-1522) is samples, mesh points, end points, nodes, six-point fit,
+// sample SH; every one of these reads only the solve result, the pre-update node positions (captured in node_xf / the
+// double-buffered node_pos) and its own data, so the order is free.  The Gaussian side runs FIRST here: the
+// rasteriser-facing SoA is final after the fit (ev_soa), and a consumer on another stream (the multi-GPU all-gather,
+// the rasteriser) overlaps the two sample passes, which are the longer half of the update.
+// Timing events: e1 after the solve, e2 after the point LBS passes, e3 after the fit, e4 after the sample advection,
+// e5 after the sample SH pass.
 extern "C" int arap_apply(arap_ctx* ctx) {
   GRAPH_CHECK(ctx);
   if (!ctx->solved) { set_error("apply: no solve result"); return ARAP_ERR_STATE; }
@@ -763,14 +771,15 @@ extern "C" int arap_apply(arap_ctx* ctx) {
   const bool tm = ctx->timing;
   if (tm) cudaEventRecord(ctx->ev[1], st);
   TRY(arapk_node_xf(M, ctx->rot_d.p, ctx->trans_d.p, ctx->node_pos.p, ctx->node_xf.p, st));
-  if (ctx->S > 0) TRY(arapk_lbs_points(ctx->sample_pos.p, ctx->sample_pos.p, ctx->S, k, ctx->sample_rows.idx.p, ctx->sample_rows.w.p, ctx->node_xf.p, ctx->sample_static.p, 1, st));
-  if (tm) cudaEventRecord(ctx->ev[2], st);
   if (ctx->Mp > 0) TRY(arapk_lbs_points(ctx->mesh_pts.p, ctx->mesh_pts.p, ctx->Mp, k, ctx->mesh_rows.idx.p, ctx->mesh_rows.w.p, ctx->node_xf.p, nullptr, 1, st));
   TRY(arapk_lbs_points(ctx->ends.p, ctx->ends.p, ctx->N * 6, k, ctx->end_rows.idx.p, ctx->end_rows.w.p, ctx->node_xf.p,
                        ctx->prm.skip_static_endpoints ? ctx->gs_static.p : nullptr, 6, st));
   TRY(arapk_lbs_points(ctx->node_pos.p, ctx->node_next.p, M, k, ctx->node_rows.idx.p, ctx->node_rows.w.p, ctx->node_xf.p, nullptr, 1, st));
-  if (tm) cudaEventRecord(ctx->ev[3], st);
+  if (tm) cudaEventRecord(ctx->ev[2], st);
   TRY(arapk_fit_gaussians(ctx->N, ctx->ends.p, ctx->scale_backup.p, ctx->gs_static.p, ctx->pos.p, ctx->rot.p, ctx->scale.p, ctx->shs.p, st));
+  ARAP_CUDA_TRY(cudaEventRecord(ctx->ev_soa, st));
+  if (tm) cudaEventRecord(ctx->ev[3], st);
+  if (ctx->S > 0) TRY(arapk_lbs_points(ctx->sample_pos.p, ctx->sample_pos.p, ctx->S, k, ctx->sample_rows.idx.p, ctx->sample_rows.w.p, ctx->node_xf.p, ctx->sample_static.p, 1, st));
   if (tm) cudaEventRecord(ctx->ev[4], st);
   if (ctx->S > 0 && ctx->aim_feature.p) {
     TRY(arapk_node_quats(M, ctx->rot_d.p, ctx->node_q.p, st));
@@ -783,6 +792,12 @@ extern "C" int arap_apply(arap_ctx* ctx) {
   return ARAP_OK;
 }
 
+extern "C" int arap_soa_ready_wait(arap_ctx* ctx, void* stream) {
+  CTX_CHECK(ctx);
+  ARAP_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, ctx->ev_soa, 0));
+  return ARAP_OK;
+}
+
 extern "C" int arap_step(arap_ctx* ctx, int on_center) {
   GRAPH_CHECK(ctx);
   if (ctx->timing) { ctx->ev = ctx->evr[ctx->tsteps % arap_ctx::TRING]; cudaEventRecord(ctx->ev[0], ctx->stream); }
@@ -792,12 +807,19 @@ extern "C" int arap_step(arap_ctx* ctx, int on_center) {
   return ARAP_OK;
 }
 
+// columns: solve, samples_lbs, points_lbs, fit, sample_sh, total  (event order: see arap_apply)
+static int stage_times(cudaEvent_t* e, float* ms6) {
+  static const int from[5] = {0, 3, 1, 2, 4};
+  for (int i = 0; i < 5; i++) ARAP_CUDA_TRY(cudaEventElapsedTime(&ms6[i], e[from[i]], e[from[i] + 1]));
+  ARAP_CUDA_TRY(cudaEventElapsedTime(&ms6[5], e[0], e[6]));
+  return ARAP_OK;
+}
+
 extern "C" int arap_last_step_timing(arap_ctx* ctx, float* ms6) {
   CTX_CHECK(ctx);
   if (!ctx->timing) { set_error("timing not enabled"); return ARAP_ERR_STATE; }
   ARAP_CUDA_TRY(cudaEventSynchronize(ctx->ev[6]));
-  for (int i = 0; i < 5; i++) ARAP_CUDA_TRY(cudaEventElapsedTime(&ms6[i], ctx->ev[i], ctx->ev[i + 1]));
-  ARAP_CUDA_TRY(cudaEventElapsedTime(&ms6[5], ctx->ev[0], ctx->ev[6]));
+  TRY(stage_times(ctx->ev, ms6));
   return ARAP_OK;
 }
 
@@ -810,8 +832,7 @@ extern "C" int arap_step_timings(arap_ctx* ctx, float* ms, int max_steps, int* n
   for (int t = 0; t < n; t++) {
     cudaEvent_t* e = ctx->evr[(ctx->tsteps - n + t) % arap_ctx::TRING];
     ARAP_CUDA_TRY(cudaEventSynchronize(e[6]));
-    for (int i = 0; i < 5; i++) ARAP_CUDA_TRY(cudaEventElapsedTime(&ms[6 * t + i], e[i], e[i + 1]));
-    ARAP_CUDA_TRY(cudaEventElapsedTime(&ms[6 * t + 5], e[0], e[6]));
+    TRY(stage_times(e, ms + 6 * t));
   }
   if (n_out) *n_out = n;
   return ARAP_OK;

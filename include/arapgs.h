@@ -179,6 +179,13 @@ int arap_solve_stats_get(arap_ctx* ctx, arap_solve_stats* out); /* synchronises 
 int arap_apply(arap_ctx* ctx);
 /* solve + apply */
 int arap_step(arap_ctx* ctx, int constraints_on_center);
+/* Makes `stream` (a cudaStream_t) wait until the deformed SoA (arap_device_view: pos/rot/scale/shs) of the last
+ * arap_apply / arap_step is final, i.e. until its six-point fit has run — the per-step sample SH pass that follows
+ * (GV:1519) does not touch the SoA.  Lets a consumer (the rasteriser, or the multi-GPU all-gather of the deformed
+ * Gaussians) start on its own stream while that pass is still running.  The caller must make the ctx stream wait
+ * for the consumer before the next arap_apply overwrites the SoA.  No reference counterpart (GV:1640-1647 copies
+ * after the whole step). */
+int arap_soa_ready_wait(arap_ctx* ctx, void* stream);
 int arap_download_nodes(arap_ctx* ctx, float* node_pos, double* rot, double* trans);
 /* per-stage device time of the last arap_step in ms: [0] solve [1] samples lbs [2] endpoints+mesh+nodes lbs [3] fit [4] sample SH [5] total */
 int arap_last_step_timing(arap_ctx* ctx, float* ms6);
