@@ -370,6 +370,10 @@ class Session:
     def step(self, on_center=False):
         check(lib().arap_step(self._ctx, int(bool(on_center))))
 
+    def soa_release_event(self, event):
+        """Hand over a CUDA event (integer handle) the next apply waits for before it overwrites the SoA."""
+        check(lib().arap_soa_release_event(self._ctx, C.c_void_p(int(event))))
+
     def soa_ready_wait(self, stream):
         """Make CUDA stream `stream` (integer handle) wait for the last step's deformed SoA (see arap_soa_ready_wait)."""
         check(lib().arap_soa_ready_wait(self._ctx, C.c_void_p(int(stream))))

@@ -177,6 +177,7 @@ struct arap_ctx {
   DBuf<double> rot_d, trans_d, stats_d; DBuf<char> solve_ws; DBuf<char> node_xf; DBuf<float> node_q;
   double* stats_h = nullptr;  // pinned
   cudaEvent_t ev_soa = nullptr;   // recorded after the six-point fit of every apply: the rasteriser-facing SoA is final
+  cudaEvent_t ev_release = nullptr;  // caller's event (not owned): its reads of the SoA are done; the next fit waits for it
   bool solved = false;
   // timing
   // timing: a ring of per-step event sets so a whole timed region can be read back afterwards
@@ -776,6 +777,7 @@ extern "C" int arap_apply(arap_ctx* ctx) {
                        ctx->prm.skip_static_endpoints ? ctx->gs_static.p : nullptr, 6, st));
   TRY(arapk_lbs_points(ctx->node_pos.p, ctx->node_next.p, M, k, ctx->node_rows.idx.p, ctx->node_rows.w.p, ctx->node_xf.p, nullptr, 1, st));
   if (tm) cudaEventRecord(ctx->ev[2], st);
+  if (ctx->ev_release) { ARAP_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_release, 0)); ctx->ev_release = nullptr; }
   TRY(arapk_fit_gaussians(ctx->N, ctx->ends.p, ctx->scale_backup.p, ctx->gs_static.p, ctx->pos.p, ctx->rot.p, ctx->scale.p, ctx->shs.p, st));
   ARAP_CUDA_TRY(cudaEventRecord(ctx->ev_soa, st));
   if (tm) cudaEventRecord(ctx->ev[3], st);
@@ -795,6 +797,12 @@ extern "C" int arap_apply(arap_ctx* ctx) {
 extern "C" int arap_soa_ready_wait(arap_ctx* ctx, void* stream) {
   CTX_CHECK(ctx);
   ARAP_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, ctx->ev_soa, 0));
+  return ARAP_OK;
+}
+
+extern "C" int arap_soa_release_event(arap_ctx* ctx, void* event) {
+  CTX_CHECK(ctx);
+  ctx->ev_release = (cudaEvent_t)event;
   return ARAP_OK;
 }
 

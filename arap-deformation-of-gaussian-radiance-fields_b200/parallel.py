@@ -45,6 +45,44 @@ class SoAGather:
         return self.outs
 
 
+class SoAGatherPush:
+    """All-gather of equally sized per-rank SoA shards by peer stores: every rank copies its shard straight into the
+    gathered arrays of all ranks (symmetric memory, peer-mapped over NVLink) with device-to-device copies, which run on
+    the copy engines — no SM is needed, so the gather also overlaps kernels that fill the GPU (the cooperative solve).
+    A device-side barrier at the end orders the pushes of all ranks before any consumer.
+    Measured (8 B200s, 1.39 GB shard): ~270 GB/s per rank, against ~900 GB/s for NCCL's SM kernels — kept as an option
+    (`ARAP_GATHER=push`), NCCL is the default."""
+
+    def __init__(self, parts: dict, world: int, rank: int):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.parts, self.outs, self.dst, self.streams = parts, {}, {}, None
+        group = dist.group.WORLD
+        for k, t in parts.items():
+            n = t.shape[0]
+            out = symm.empty((world * n,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            hdl = symm.rendezvous(out, group.group_name)
+            self.dst[k] = [hdl.get_buffer(r, out.shape, out.dtype)[rank * n:(rank + 1) * n] for r in range(world)]
+            self.outs[k] = out
+            self.hdl = hdl
+
+    def __call__(self):
+        import torch
+        cur = torch.cuda.current_stream()
+        if self.streams is None:   # one stream per destination: the copies to different peers use different copy engines
+            self.streams = [torch.cuda.Stream(priority=-1) for _ in range(len(next(iter(self.dst.values()))))]
+        for r, st in enumerate(self.streams):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                for k, t in self.parts.items():
+                    self.dst[k][r].copy_(t, non_blocking=True)
+        for st in self.streams:
+            cur.wait_stream(st)
+        self.hdl.barrier()
+        return self.outs
+
+
 def allgather_variable(local: "np.ndarray", world: int):
     """All-gather of unequal shards (host arrays, any backend): pads to the largest shard."""
     import torch

@@ -153,21 +153,34 @@ def run_own(args):
         par = importlib.import_module(ge.PKG + ".parallel")
         v = s.device_view()
         parts = {name: torch.as_tensor(par.DevArray(getattr(v, name), (N, w)), device="cuda") for name, w in par.SOA_WIDTHS}
-        gather = par.SoAGather(parts, world)
+        # NCCL all-gather (default) or peer stores through the copy engines (ARAP_GATHER=push).  Measured on 8 B200s:
+        # the copy engines sustain ~270 GB/s per rank for the 9.7 GB a rank sends per step (43.7 ms/step), NCCL's SM
+        # kernels ~900 GB/s (28.7 ms/step); at 2 GPUs both hide behind the sample passes (22.5 / 22.1 ms/step).
+        if os.environ.get("ARAP_GATHER", "nccl") != "push":
+            gather = par.SoAGather(parts, world)
+        else:
+            gather = par.SoAGatherPush(parts, world, rank)
+            ref = par.SoAGather(parts, world)()     # one NCCL all-gather of the initial SoA checks the peer-store path
+            torch.cuda.synchronize(); dist.barrier()
+            got = gather()
+            torch.cuda.synchronize(); dist.barrier()
+            assert all(torch.equal(ref[kk], got[kk]) for kk in ref), "peer-store all-gather differs from NCCL"
+            del ref
 
     side = torch.cuda.Stream(priority=-1) if gather else None
+    ev_rel = torch.cuda.Event() if gather else None
 
     def one_step():
         # N > 1: the all-gather of step n runs on a high-priority side stream as soon as the six-point fit has
         # written the SoA, concurrently with the sample SH pass of the same step; the next step's apply waits for it
-        if gather:
-            tstream.wait_stream(side)
         s.aim_translate(DRAG)
         s.step(False)
         if gather:
             s.soa_ready_wait(side.cuda_stream)
             with torch.cuda.stream(side):
                 gather()
+                ev_rel.record(side)
+            s.soa_release_event(ev_rel.cuda_event)   # the next step's fit waits for this gather; its solve does not
 
     def barrier():
         if world > 1:
@@ -208,14 +221,14 @@ def run_own(args):
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         aim[active] += DRAG
-        if gather:
-            tstream.wait_stream(side)
         s.aim_set(aim)              # H2D M x 3 floats (+ sync)
         s.step(False)
         if gather:
             s.soa_ready_wait(side.cuda_stream)
             with torch.cuda.stream(side):
                 gather()
+                ev_rel.record(side)
+            s.soa_release_event(ev_rel.cuda_event)
         aim, _, _ = s.download_nodes()  # D2H node positions (+ rot/trans), synchronises
         s.solve_stats()
     barrier()
@@ -245,7 +258,7 @@ def run_own(args):
                    "grid": cfg["grid"], "samples_per_gpu": S, "valid_cells": gi["valid_cells"], "list_pairs": gi["pairs"],
                    "constraints": "per-node, two caps (|z|>0.4)", "active_nodes": setup["n_active"], "pinned_nodes": setup["n_pinned"],
                    "l2": "inputs (>1.4 GB SoA + tables per step) exceed the 126 MB L2",
-                   "parallelism": "replicated solve, Gaussians/samples sharded by index, NCCL all-gather of the deformed SoA on a side stream (overlaps the sample SH pass)" if world > 1 else "single GPU"},
+                   "parallelism": "replicated solve, Gaussians/samples sharded by index, NCCL all-gather of the deformed SoA on a high-priority side stream (starts when the six-point fit is done: overlaps the sample passes)" if world > 1 else "single GPU"},
         "stages_ms": {"solve": round(float(mean[0]), 4), "sample_advect": round(float(mean[1]), 4), "endpoint_lbs": round(float(mean[2]), 4),
                       "six_point_fit": round(float(mean[3]), 4), "sample_sh_rotate": round(float(mean[4]), 4)},
         "solve": {"gn_iters": st["gn_iters"], "cg_iters": st["cg_iters"], "flags": st["flags"], "grid_blocks": st["grid_blocks"],

@@ -186,6 +186,11 @@ int arap_step(arap_ctx* ctx, int constraints_on_center);
  * for the consumer before the next arap_apply overwrites the SoA.  No reference counterpart (GV:1640-1647 copies
  * after the whole step). */
 int arap_soa_ready_wait(arap_ctx* ctx, void* stream);
+/* The other half: `event` (a cudaEvent_t the caller recorded on its own stream after its last read of the SoA; not
+ * owned, must stay alive until the next arap_apply) — the next arap_apply makes the ctx stream wait for it right
+ * before the kernel that overwrites the SoA (the six-point fit), so the consumer also overlaps the next solve and
+ * end-point pass.  One-shot: consumed by that arap_apply. */
+int arap_soa_release_event(arap_ctx* ctx, void* event);
 int arap_download_nodes(arap_ctx* ctx, float* node_pos, double* rot, double* trans);
 /* per-stage device time of the last arap_step in ms: [0] solve [1] samples lbs [2] endpoints+mesh+nodes lbs [3] fit [4] sample SH [5] total */
 int arap_last_step_timing(arap_ctx* ctx, float* ms6);
