@@ -181,6 +181,32 @@ def graph_obj_load(path) -> np.ndarray:
     return pts
 
 
+def ply_load(path) -> dict:
+    """3DGS PLY -> activated, Morton-ordered SoA (arap_ply_load).  Keys: pos, rot (w,x,y,z), scale, opacity, shs, index, aabb_min/max."""
+    n = C.c_longlong()
+    check(lib().arap_ply_load(str(path).encode(), C.byref(n), None, None, None, None, None, None, None, None))
+    N = n.value
+    out = dict(pos=np.zeros((N, 3), f32), rot=np.zeros((N, 4), f32), scale=np.zeros((N, 3), f32), opacity=np.zeros(N, f32),
+               shs=np.zeros((N, 48), f32), index=np.zeros(N, np.int32), aabb_min=np.zeros(3, f32), aabb_max=np.zeros(3, f32))
+    check(lib().arap_ply_load(str(path).encode(), C.byref(n), _ptr(out["pos"]), _ptr(out["rot"]), _ptr(out["scale"]), _ptr(out["opacity"]),
+                              _ptr(out["shs"]), _ptr(out["index"]), _ptr(out["aabb_min"]), _ptr(out["aabb_max"])))
+    return out
+
+
+def ply_save(path, g: dict, box_min=None, box_max=None, skip=None) -> int:
+    """Write a 3DGS PLY in the reference's format (arap_ply_save); returns the number of vertices written."""
+    pos, rot, scale = _np(g["pos"], f32), _np(g["rot"], f32), _np(g["scale"], f32)
+    op, shs = _np(g["opacity"], f32), _np(g["shs"], f32)
+    bmin = _np(box_min, f32) if box_min is not None else None
+    bmax = _np(box_max, f32) if box_max is not None else None
+    sk = _np(skip, np.uint8) if skip is not None else None
+    w = C.c_longlong()
+    check(lib().arap_ply_save(str(path).encode(), C.c_longlong(len(pos)), _ptr(pos), _ptr(rot), _ptr(scale), _ptr(op), _ptr(shs),
+                              _ptr(bmin) if bmin is not None else None, _ptr(bmax) if bmax is not None else None,
+                              _ptr(sk) if sk is not None else None, C.byref(w)))
+    return w.value
+
+
 def graph_obj_save(path, pts) -> None:
     p = _np(pts, f32)
     check(lib().arap_graph_obj_save(str(path).encode(), _ptr(p), len(p)))

@@ -17,6 +17,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OBJ = HERE / "_build"
 SO = HERE / "libarapgs.so"
+CLI = HERE / "arap_replay"
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -62,6 +63,11 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         list(ex.map(_compile, jobs))
     if jobs or not SO.exists():
         _compile([NVCC, *ARCH, "-shared", "-o", str(SO), *map(str, objs), "-lcudart"])
+    # headless replay CLI (tools/arap_replay.cpp): plain C++ over the C ABI, linked against the library next to it
+    cli_src = HERE.parent / "tools" / "arap_replay.cpp"
+    if cli_src.exists() and (jobs or not CLI.exists() or cli_src.stat().st_mtime > CLI.stat().st_mtime):
+        _compile(["g++", *CXX_FLAGS, str(cli_src), "-o", str(CLI), f"-L{HERE}", "-larapgs", "-Wl,-rpath,$ORIGIN",
+                  "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64", "-lcudart"])
     return SO
 
 

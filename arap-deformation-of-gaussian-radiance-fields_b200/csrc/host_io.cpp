@@ -7,7 +7,10 @@
 //   LoadDeformScript0/1, RunDeformScript  GaussianView.cpp:2512-2600, 2790-2816, 1918-1993
 //   LoadMeshPoints / writeVectorToObj     helper.cpp:264-282, 1111-1126
 //   config                                GaussianView.cpp:459-487, helper.cpp:198-230
+#include <algorithm>
+#include <cfloat>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -194,6 +197,131 @@ extern "C" int arap_config_load(const char* path, int* grid_num, int* is_synthet
   if (v[2] == 1) { soup = 1; hq = 1; } else if (v[2] == 2) { soup = 0; hq = 1; }
   if (has_soup) *has_soup = soup;
   if (high_quality) *high_quality = hq;
+  return ARAP_OK;
+}
+
+// ------------------------------------------------------------------ 3DGS PLY (GV:43-339)
+// Binary little-endian vertex records of 62 floats (x y z nx ny nz f_dc[3] f_rest[45] opacity scale[3] rot[4]) or 63 with a
+// trailing `index` property (the reference's "soup" files, helper.hpp:98-108).  The loader applies the reference's
+// activations (normalised quaternion, exp scale, sigmoid opacity), interleaves the channel-major f_rest block into
+// 16 x RGB, and orders the Gaussians by the 63-bit Morton code of their position inside the cloud's bounding box.
+namespace {
+struct PlyHeader { long long count = 0; int props = 0; std::streampos data = 0; };
+int ply_header(std::ifstream& f, const char* path, PlyHeader& h) {
+  std::string line;
+  bool fmt_ok = false, ended = false;
+  if (!std::getline(f, line) || line.substr(0, 3) != "ply") { set_error(std::string("ply_load: not a PLY file: ") + path); return ARAP_ERR_IO; }
+  while (std::getline(f, line)) {
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    std::istringstream ss(line); std::string a, b;
+    ss >> a;
+    if (a == "format") { ss >> b; fmt_ok = b == "binary_little_endian"; }
+    else if (a == "element") { ss >> b; if (b == "vertex") ss >> h.count; }
+    else if (a == "property") { ss >> b; if (b != "float") { set_error("ply_load: only float properties are supported"); return ARAP_ERR_IO; } h.props++; }
+    else if (a == "end_header") { ended = true; break; }
+  }
+  if (!ended || !fmt_ok || h.count < 0 || (h.props != 62 && h.props != 63)) {
+    set_error("ply_load: expected binary_little_endian with 62 (or 63, with index) float properties per vertex");
+    return ARAP_ERR_IO;
+  }
+  h.data = f.tellg();
+  return ARAP_OK;
+}
+inline float sigmoidf(float x) { return 1.0f / (1.0f + std::exp(-x)); }              // helper.hpp sigmoid
+inline float inverse_sigmoidf(float x) { return std::log(x / (1.0f - x)); }          // helper.hpp inverse_sigmoid
+}  // namespace
+
+extern "C" int arap_ply_load(const char* path, long long* n, float* pos, float* rot, float* scale, float* opacity, float* shs,
+                             int* index, float aabb_min[3], float aabb_max[3]) {
+  if (!path || !n) { set_error("ply_load: bad arguments"); return ARAP_ERR_INVALID; }
+  std::ifstream f(path, std::ios_base::binary);
+  if (!f.good()) { set_error(std::string("ply_load: cannot open ") + path); return ARAP_ERR_IO; }
+  PlyHeader h;
+  int rc = ply_header(f, path, h); if (rc) return rc;
+  if (!pos) { *n = h.count; return ARAP_OK; }   // first call: the count
+  if (*n < h.count) { set_error("ply_load: output arrays are smaller than the vertex count"); return ARAP_ERR_INVALID; }
+  const size_t P = (size_t)h.props, cnt = (size_t)h.count;
+  std::vector<float> rec(cnt * P);
+  f.read(reinterpret_cast<char*>(rec.data()), (std::streamsize)(rec.size() * sizeof(float)));
+  if ((size_t)f.gcount() != rec.size() * sizeof(float)) { set_error("ply_load: truncated vertex data"); return ARAP_ERR_IO; }
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (size_t i = 0; i < cnt; i++)
+    for (int c = 0; c < 3; c++) { mn[c] = std::min(mn[c], rec[i * P + c]); mx[c] = std::max(mx[c], rec[i * P + c]); }
+  // Morton order (GV:91-116): 21 bits per axis of floor((2^21 - 1) * (p - min) / (max - min)), x in bit 3i, y in 3i+1, z in 3i+2.
+  // The reference's std::sort leaves the order of equal codes unspecified; ties keep file order here.
+  std::vector<std::pair<uint64_t, uint32_t>> order(cnt);
+  for (size_t i = 0; i < cnt; i++) {
+    uint64_t code = 0;
+    int q[3];
+    for (int c = 0; c < 3; c++) {
+      const float rel = (rec[i * P + c] - mn[c]) / (mx[c] - mn[c]);
+      q[c] = (int)((float)((1 << 21) - 1) * rel);
+    }
+    for (int b = 0; b < 21; b++)
+      for (int c = 0; c < 3; c++) code |= (uint64_t)((unsigned)q[c] & (1u << b)) << (2 * b + c);
+    order[i] = {code, (uint32_t)i};
+  }
+  std::stable_sort(order.begin(), order.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+  for (size_t k = 0; k < cnt; k++) {
+    const float* r = rec.data() + (size_t)order[k].second * P;
+    for (int c = 0; c < 3; c++) pos[3 * k + c] = r[c];
+    if (rot) {
+      const float* q = r + 58;
+      float l2 = 0.f;
+      for (int j = 0; j < 4; j++) l2 += q[j] * q[j];
+      const float len = std::sqrt(l2);
+      for (int j = 0; j < 4; j++) rot[4 * k + j] = q[j] / len;
+    }
+    if (scale) for (int j = 0; j < 3; j++) scale[3 * k + j] = std::exp(r[55 + j]);
+    if (opacity) opacity[k] = sigmoidf(r[54]);
+    if (shs) {
+      float* o = shs + 48 * k; const float* sh = r + 6;
+      o[0] = sh[0]; o[1] = sh[1]; o[2] = sh[2];
+      for (int j = 1; j < 16; j++) { o[3 * j] = sh[(j - 1) + 3]; o[3 * j + 1] = sh[(j - 1) + 18]; o[3 * j + 2] = sh[(j - 1) + 33]; }
+    }
+    if (index) index[k] = P == 63 ? (int)std::lround(r[62]) : (int)order[k].second;
+  }
+  if (aabb_min) for (int c = 0; c < 3; c++) aabb_min[c] = mn[c];
+  if (aabb_max) for (int c = 0; c < 3; c++) aabb_max[c] = mx[c];
+  *n = h.count;
+  return ARAP_OK;
+}
+
+// savePly (GV:273-339): Gaussians outside [box_min, box_max] or flagged `skip` are dropped; scale -> log, opacity ->
+// inverse sigmoid, SH back to channel-major f_rest; header text identical to the reference's.
+extern "C" int arap_ply_save(const char* path, long long n, const float* pos, const float* rot, const float* scale, const float* opacity,
+                             const float* shs, const float box_min[3], const float box_max[3], const uint8_t* skip, long long* written) {
+  if (!path || n < 0 || !pos || !rot || !scale || !opacity || !shs) { set_error("ply_save: bad arguments"); return ARAP_ERR_INVALID; }
+  auto keep = [&](long long i) {
+    if (box_min && box_max)
+      for (int c = 0; c < 3; c++) if (pos[3 * i + c] < box_min[c] || pos[3 * i + c] > box_max[c]) return false;
+    return !(skip && skip[i]);
+  };
+  long long count = 0;
+  for (long long i = 0; i < n; i++) count += keep(i);
+  std::ofstream f(path, std::ios_base::binary);
+  if (!f.is_open()) { set_error(std::string("ply_save: cannot open ") + path); return ARAP_ERR_IO; }
+  f << "ply\nformat binary_little_endian 1.0\nelement vertex " << count << "\n";
+  for (const char* p : {"x", "y", "z", "nx", "ny", "nz", "f_dc_0", "f_dc_1", "f_dc_2"}) f << "property float " << p << "\n";
+  for (int i = 0; i < 45; i++) f << "property float f_rest_" << i << "\n";
+  for (const char* p : {"opacity", "scale_0", "scale_1", "scale_2", "rot_0", "rot_1", "rot_2", "rot_3"}) f << "property float " << p << "\n";
+  f << "end_header\n";
+  std::vector<float> rec((size_t)count * 62, 0.0f);
+  size_t k = 0;
+  for (long long i = 0; i < n; i++) {
+    if (!keep(i)) continue;
+    float* r = rec.data() + k * 62; k++;
+    for (int c = 0; c < 3; c++) r[c] = pos[3 * i + c];
+    const float* sh = shs + 48 * i;
+    r[6] = sh[0]; r[7] = sh[1]; r[8] = sh[2];
+    for (int j = 1; j < 16; j++) { r[6 + (j - 1) + 3] = sh[3 * j]; r[6 + (j - 1) + 18] = sh[3 * j + 1]; r[6 + (j - 1) + 33] = sh[3 * j + 2]; }
+    r[54] = inverse_sigmoidf(opacity[i]);
+    for (int j = 0; j < 3; j++) r[55 + j] = std::log(scale[3 * i + j]);
+    for (int j = 0; j < 4; j++) r[58 + j] = rot[4 * i + j];
+  }
+  f.write(reinterpret_cast<const char*>(rec.data()), (std::streamsize)(rec.size() * sizeof(float)));
+  if (!f.good()) { set_error("ply_save: write failed"); return ARAP_ERR_IO; }
+  if (written) *written = count;
   return ARAP_OK;
 }
 

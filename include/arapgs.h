@@ -217,6 +217,18 @@ int arap_history_move(const arap_history* h, int i, float* movements_out, int* n
 /* LoadMeshPoints: `v x y z` lines only (HC:264-282). Two-call pattern: pts==NULL returns the count. */
 int arap_graph_obj_load(const char* path, float* pts, int* n);
 int arap_graph_obj_save(const char* path, const float* pts, int n);          /* writeVectorToObj (HC:1111-1126) */
+/* loadPly_Origin / loadPly (GV:43-271): 3DGS point_cloud.ply, binary little-endian, 62 float properties per vertex (63 with the
+ * trailing `index` of the reference's "soup" files).  Applies the reference's activations (normalised quaternion w,x,y,z; exp
+ * scale; sigmoid opacity), interleaves f_rest into 16 x RGB and orders the Gaussians by the Morton code of their position in
+ * the cloud's bounding box (ties keep file order; the reference's std::sort leaves them unspecified).  Two-call pattern:
+ * pos == NULL returns the vertex count in *n; otherwise *n is the capacity of the arrays on entry.  rot/scale/opacity/shs/index/
+ * aabb may be NULL.  index = the file's `index` property when present, else the vertex's position in the file. */
+int arap_ply_load(const char* path, long long* n, float* pos, float* rot, float* scale, float* opacity, float* shs, int* index,
+                  float aabb_min[3], float aabb_max[3]);
+/* savePly (GV:273-339): header text identical to the reference's; Gaussians outside [box_min, box_max] (NULL = keep all) or with
+ * skip[i] != 0 (the reference's too_small) are dropped; *written (may be NULL) = vertices written. */
+int arap_ply_save(const char* path, long long n, const float* pos, const float* rot, const float* scale, const float* opacity,
+                  const float* shs, const float box_min[3], const float box_max[3], const uint8_t* skip, long long* written);
 /* <ply>_config.txt: grid_num is_synthetic conf2 (GV:459-487) */
 int arap_config_load(const char* path, int* grid_num, int* is_synthetic, int* has_soup, int* high_quality);
 /* Run a loaded history through the state machine of GV:1757-1916 (blocks added/deleted, per-move block types,

@@ -210,3 +210,30 @@ def test_full_size_properties_1m(pkg, scenes):
     assert np.abs(after["pos"] - before["pos"] - np.float32([0.003, -0.002, 0.004])).max() <= 3e-7
     assert (np.abs(after["scale"] - before["scale"]) / before["scale"]).max() <= 5e-4
     assert np.abs(np.abs((after["rot"] * before["rot"]).sum(1)) - 1).max() <= 1e-5
+
+
+def test_headless_replay_cli(pkg, scenes, golden, tmp_path):
+    """tools/arap_replay (plain C++ over the C ABI): ply + deform.txt -> ply equals the in-process replay bit for bit."""
+    import subprocess
+    from pathlib import Path
+    cli = Path(pkg.__file__).parent / "arap_replay"
+    assert cli.exists(), "build() did not produce the arap_replay CLI"
+    sc = scenes.make_scene("pinocchio", n=30000)
+    src, dst = tmp_path / "point_cloud.ply", tmp_path / "deformed.ply"
+    pkg.ply_save(src, sc)
+    g = pkg.ply_load(src)
+    s = pkg.Session(device=0, grid_num=32, knn_k=8, node_num=150)
+    s.set_gaussians(g["pos"], g["rot"], g["scale"], g["opacity"], g["shs"])
+    s.grid_build(); s.grid_eval(0); s.graph_build_fps()
+    n_steps = s.replay(pkg.History.load(golden / "pinocchio_deform.txt"), rebuild_graph=True)
+    ref = s.download_gaussians()
+    r = subprocess.run([str(cli), str(src), str(golden / "pinocchio_deform.txt"), str(dst), "--grid", "32", "--k", "8", "--nodes", "150"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert f"replayed {n_steps} drag steps" in r.stdout
+    raw = dst.read_bytes().split(b"end_header\n", 1)[1]
+    rec = np.frombuffer(raw, np.float32).reshape(-1, 62)
+    assert len(rec) == 30000
+    assert np.array_equal(rec[:, :3], ref["pos"]) and np.array_equal(rec[:, 58:62], ref["rot"])
+    assert np.array_equal(rec[:, 6:9], ref["shs"][:, :3]) and np.array_equal(rec[:, 9:24], ref["shs"][:, 3::3])
+    assert np.allclose(rec[:, 55:58], np.log(ref["scale"]), rtol=1e-6, atol=1e-6)
