@@ -237,3 +237,27 @@ def test_headless_replay_cli(pkg, scenes, golden, tmp_path):
     assert np.array_equal(rec[:, :3], ref["pos"]) and np.array_equal(rec[:, 58:62], ref["rot"])
     assert np.array_equal(rec[:, 6:9], ref["shs"][:, :3]) and np.array_equal(rec[:, 9:24], ref["shs"][:, 3::3])
     assert np.allclose(rec[:, 55:58], np.log(ref["scale"]), rtol=1e-6, atol=1e-6)
+
+
+def test_rendered_psnr_after_drag(pkg, scenes):
+    """Image-space parity (north_star: >= 50 dB PSNR on rendered views): the product's and the oracle's deformed Gaussians
+    through the same deterministic splat renderer (tests/splat_render.py), four orbit views."""
+    import splat_render as sr
+    sc, s, o, gi, og = _pair(pkg, scenes, n=30000, grid_num=32, knn_k=8, node_num=150)
+    g = s.graph_build_fps(); o.graph_build_fps()
+    blocks, types = scenes.cap_blocks(g["node_pos"], lo=-0.3, hi=0.3)
+    s.set_blocks(blocks, types); o.set_blocks(blocks, types)
+    before = s.download_gaussians()
+    for step in range(6):
+        s.aim_translate([0.004, 0.0, 0.02]); o.aim_translate([0.004, 0.0, 0.02])
+        s.step(False); o.step(False)
+    out = s.download_gaussians()
+    worst, moved = float("inf"), float("inf")
+    for cam in sr.orbit_cameras(4, size=192):
+        a, b, c = sr.render(out, cam), sr.render(o.g, cam), sr.render(before, cam)
+        assert a.max() > 0.2                                   # something is on screen
+        worst = min(worst, sr.psnr(a, b))
+        moved = min(moved, sr.psnr(a, c))
+    print(f"rendered PSNR product vs oracle (worst of 4 views): {worst:.1f} dB; deformed vs undeformed: {moved:.1f} dB")
+    assert worst >= 50.0, worst                                # product vs oracle: >= 50 dB on every view
+    assert moved < 45.0, moved                                 # ...and the metric sees the deformation itself
