@@ -35,8 +35,8 @@ class Params(C.Structure):
                 ("high_quality", C.c_int), ("lpf_parameter", C.c_float),
                 ("w_rot", C.c_double), ("w_reg", C.c_double), ("w_con", C.c_double),
                 ("max_gn_iters", C.c_int), ("max_cg_iters", C.c_int), ("cg_tol", C.c_double),
-                ("skip_static_endpoints", C.c_int), ("solver_global_memory", C.c_int), ("reserved0", C.c_int),
-                ("newton_eta0", C.c_double)]
+                ("skip_static_endpoints", C.c_int), ("solver_global_memory", C.c_int), ("lbs_mode", C.c_int),
+                ("newton_eta0", C.c_double), ("warm_start", C.c_int)]
 
 
 class SolveStats(C.Structure):
@@ -74,6 +74,8 @@ def lib() -> C.CDLL:
         _lib.arapk_knn_index_struct_bytes.restype = C.c_size_t
         _lib.arapk_solve_workspace_bytes.restype = C.c_size_t
         _lib.arapk_grid_scratch_bytes.restype = C.c_size_t
+        _lib.arapk_lbs_tile_count.restype = C.c_longlong
+        _lib.arapk_lbs_tile_count.argtypes = [C.c_longlong]
         _lib.arapk_grid_scratch_bytes.argtypes = [C.c_longlong, C.c_int]
     return _lib
 

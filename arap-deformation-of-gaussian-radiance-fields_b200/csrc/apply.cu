@@ -42,17 +42,48 @@ __global__ void k_node_xf(int M, const double* __restrict__ rot, const double* _
 // ------------------------------------------------------------------ LBS
 // One thread per point.  Double products, float accumulator rounded after each
 // neighbour — exactly the reference's `Pos output += double_expr` sequence.
+//
+// round_to_float: RN-even rounding of a double to float precision WITHOUT leaving the FP64 pipe.
+// M = 1.5 * 2^(e+29) (e = exponent of s) puts the unit in the last place of s + M at 2^(e-23), the float
+// ulp of s; the hardware add rounds to nearest-even there and the subtraction is exact.  Identical to
+// (double)(float)s for every s in the normal float range and for 0 (float denormals, |s| < 2^-126, excluded);
+// it replaces two XU-pipe conversions (16 lanes/clk/SM) by two DADD (64 lanes/clk/SM) and two integer ops.
+__device__ __forceinline__ double round_to_float(double s) {
+  const int hi = __double2hiint(s);
+  const double M = __hiloint2double((hi & 0x7ff00000) + 0x01d80000, 0);
+  return (s + M) - M;
+}
+
+struct LbsAcc {  // the float accumulator, kept either as float or as a float-valued double
+  double d0, d1, d2;
+};
+
+template <bool MAGIC>
+__device__ __forceinline__ void lbs_neighbour(float c0, float c1, float c2, double w, const double2 a01, const double2 a23,
+                                              const double2 a45, const double2 a67, const double2 a8c0, const double2 c12,
+                                              const float4 g, LbsAcc& o) {
+  const double t0 = (double)(c0 - g.x), t1 = (double)(c1 - g.y), t2 = (double)(c2 - g.z);
+  // A column-major: row r = (A[r], A[r+3], A[r+6])
+  const double e0 = fma(a67.x, t2, fma(a23.y, t1, fma(a01.x, t0, a8c0.y)));
+  const double e1 = fma(a67.y, t2, fma(a45.x, t1, fma(a01.y, t0, c12.x)));
+  const double e2 = fma(a8c0.x, t2, fma(a45.y, t1, fma(a23.x, t0, c12.y)));
+  if (MAGIC) {
+    o.d0 = round_to_float(fma(w, e0, o.d0));
+    o.d1 = round_to_float(fma(w, e1, o.d1));
+    o.d2 = round_to_float(fma(w, e2, o.d2));
+  } else {
+    o.d0 = (double)(float)fma(w, e0, o.d0);
+    o.d1 = (double)(float)fma(w, e1, o.d1);
+    o.d2 = (double)(float)fma(w, e2, o.d2);
+  }
+}
+
 template <int K>
-__global__ void __launch_bounds__(256)
-k_lbs_points(const float* __restrict__ in, float* __restrict__ out, long long P, int k_rt,
-             const uint16_t* __restrict__ ridx, const double* __restrict__ rw,
-             const NodeXf* __restrict__ nodes, const uint8_t* __restrict__ skip, int group) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P) return;
-  if (skip && skip[i / group]) return;
-  const int k = K > 0 ? K : k_rt;
+__device__ __forceinline__ void lbs_row_global(const float* __restrict__ in, float* __restrict__ out, long long i, int k,
+                                               const uint16_t* __restrict__ ridx, const double* __restrict__ rw,
+                                               const NodeXf* __restrict__ nodes) {
   const float c0 = in[3 * i], c1 = in[3 * i + 1], c2 = in[3 * i + 2];
-  float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+  LbsAcc o{0.0, 0.0, 0.0};
   const long long base = (i >> 5) * (long long)(k * 32) + (i & 31);
 #pragma unroll
   for (int j = 0; j < (K > 0 ? K : KNN_MAX); j++) {
@@ -63,16 +94,141 @@ k_lbs_points(const float* __restrict__ in, float* __restrict__ out, long long P,
     const double2 a01 = __ldg(n + 0), a23 = __ldg(n + 1), a45 = __ldg(n + 2), a67 = __ldg(n + 3);
     const double2 a8c0 = __ldg(n + 4), c12 = __ldg(n + 5);
     const float4 g = __ldg(reinterpret_cast<const float4*>(n + 6));
-    const double t0 = (double)(c0 - g.x), t1 = (double)(c1 - g.y), t2 = (double)(c2 - g.z);
-    // A column-major: row r = (A[r], A[r+3], A[r+6])
-    const double e0 = fma(a67.x, t2, fma(a23.y, t1, fma(a01.x, t0, a8c0.y)));
-    const double e1 = fma(a67.y, t2, fma(a45.x, t1, fma(a01.y, t0, c12.x)));
-    const double e2 = fma(a8c0.x, t2, fma(a45.y, t1, fma(a23.x, t0, c12.y)));
-    o0 = (float)fma(w, e0, (double)o0);
-    o1 = (float)fma(w, e1, (double)o1);
-    o2 = (float)fma(w, e2, (double)o2);
+    lbs_neighbour<false>(c0, c1, c2, w, a01, a23, a45, a67, a8c0, c12, g, o);
   }
-  out[3 * i] = o0; out[3 * i + 1] = o1; out[3 * i + 2] = o2;
+  out[3 * i] = (float)o.d0; out[3 * i + 1] = (float)o.d1; out[3 * i + 2] = (float)o.d2;
+}
+
+template <int K>
+__global__ void __launch_bounds__(256)
+k_lbs_points(const float* __restrict__ in, float* __restrict__ out, long long P, int k_rt,
+             const uint16_t* __restrict__ ridx, const double* __restrict__ rw,
+             const NodeXf* __restrict__ nodes, const uint8_t* __restrict__ skip, int group) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  if (skip && skip[i / group]) return;
+  lbs_row_global<K>(in, out, i, K > 0 ? K : k_rt, ridx, rw, nodes);
+}
+
+// ------------------------------------------------------------------ LBS, node records staged per tile
+// The skinning tables never change after set-up, so the set of DISTINCT nodes a tile of LT_ROWS consecutive rows
+// touches is precomputed (k_build_tiles): rows are in cell order, hence a tile sees a few dozen nodes, not
+// LT_ROWS * k.  Per step a CTA copies those records once into shared memory (coalesced 16-byte loads, one L2 read
+// per record per tile) and every (row, neighbour) pair reads its record from there through a one-byte slot number.
+// That replaces ten 112-byte L1 gathers per row (the global-memory kernel sits at 83-95 % l1tex throughput with
+// DRAM at 25-34 %) by shared-memory reads that mostly broadcast, and the id table shrinks from 2 to 1.2 bytes per pair.
+// Staged records sit at a 144-byte pitch: bank group of 16-byte part p of slot s is (s + p) mod 8.
+// A tile with more than `cap` distinct nodes has cnt = 0 and takes the global-memory path (same arithmetic).
+constexpr int LT_ROWS = 128;
+constexpr int LT_CAP = 96;
+constexpr int LT_PITCH = 9;   // 16-byte units per staged record (7 used)
+constexpr int LT_WORDS = 3;   // slot words per row: 12 one-byte slots
+
+template <int K, bool MAGIC>
+__global__ void __launch_bounds__(LT_ROWS)
+k_lbs_tiles(const float* __restrict__ in, float* __restrict__ out, long long P, int k_rt, const uint32_t* __restrict__ slots,
+            const double* __restrict__ rw, const uint16_t* __restrict__ ridx, const uint16_t* __restrict__ tile_cnt,
+            const uint16_t* __restrict__ tile_nodes, const NodeXf* __restrict__ nodes, const uint8_t* __restrict__ skip,
+            int group) {
+  __shared__ double2 s_rec[LT_CAP * LT_PITCH];
+  const int tid = threadIdx.x;
+  const long long tile = blockIdx.x;
+  const long long i = tile * LT_ROWS + tid;
+  const int k = K > 0 ? K : k_rt;
+  const int cnt = tile_cnt[tile];
+  const bool live = i < P && !(skip && skip[i / group]);
+  if (cnt == 0) {  // more distinct nodes than the staging area holds (uniform per CTA)
+    if (live) lbs_row_global<K>(in, out, i, k, ridx, rw, nodes);
+    return;
+  }
+  const uint16_t* tn = tile_nodes + tile * LT_CAP;
+  for (int v = tid; v < cnt * 7; v += LT_ROWS) {
+    const int r = v / 7, part = v - r * 7;
+    s_rec[r * LT_PITCH + part] = __ldg(reinterpret_cast<const double2*>(nodes + tn[r]) + part);
+  }
+  // this row's streamed operands, all in flight before the barrier
+  float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+  uint32_t sw[LT_WORDS] = {0u, 0u, 0u};
+  double w[K > 0 ? K : KNN_MAX];
+  if (live) {
+    c0 = in[3 * i]; c1 = in[3 * i + 1]; c2 = in[3 * i + 2];
+    const long long sb = (i >> 5) * (long long)(LT_WORDS * 32) + (i & 31);
+#pragma unroll
+    for (int m = 0; m < LT_WORDS; m++) sw[m] = slots[sb + m * 32];
+    const long long base = (i >> 5) * (long long)(k * 32) + (i & 31);
+#pragma unroll
+    for (int j = 0; j < (K > 0 ? K : KNN_MAX); j++) w[j] = (K > 0 || j < k) ? rw[base + j * 32] : 0.0;
+  }
+  __syncthreads();
+  if (!live) return;
+  LbsAcc o{0.0, 0.0, 0.0};
+#pragma unroll
+  for (int j = 0; j < (K > 0 ? K : KNN_MAX); j++) {
+    if (K == 0 && j >= k) break;
+    const unsigned slot = (sw[j >> 2] >> ((j & 3) * 8)) & 0xffu;
+    const double2* n = s_rec + slot * LT_PITCH;
+    const double2 a01 = n[0], a23 = n[1], a45 = n[2], a67 = n[3], a8c0 = n[4], c12 = n[5];
+    const float4 g = *reinterpret_cast<const float4*>(n + 6);
+    lbs_neighbour<MAGIC>(c0, c1, c2, w[j], a01, a23, a45, a67, a8c0, c12, g, o);
+  }
+  out[3 * i] = (float)o.d0; out[3 * i + 1] = (float)o.d1; out[3 * i + 2] = (float)o.d2;
+}
+
+// Set-up: distinct node list + one-byte slots of every tile.  One CTA per tile: a 64 Kbit bitmap of the node ids
+// the tile touches, ranked by a popcount prefix (slots are therefore in ascending node id — deterministic).
+__global__ void __launch_bounds__(LT_ROWS)
+k_build_tiles(long long rows, int k, const uint16_t* __restrict__ ridx, uint32_t* __restrict__ slots,
+              uint16_t* __restrict__ tile_cnt, uint16_t* __restrict__ tile_nodes) {
+  __shared__ uint32_t bm[2048];
+  __shared__ uint16_t pre[2048];
+  __shared__ int wsum[LT_ROWS / 32];
+  const int tid = threadIdx.x;
+  const long long tile = blockIdx.x;
+  const long long i = tile * LT_ROWS + tid;
+  for (int v = tid; v < 2048; v += LT_ROWS) bm[v] = 0u;
+  __syncthreads();
+  const long long base = (i >> 5) * (long long)(k * 32) + (i & 31);
+  if (i < rows)
+    for (int j = 0; j < k; j++) { const unsigned n = ridx[base + j * 32]; atomicOr(&bm[n >> 5], 1u << (n & 31)); }
+  __syncthreads();
+  constexpr int WPT = 2048 / LT_ROWS;  // bitmap words per thread
+  int c = 0;
+#pragma unroll
+  for (int v = 0; v < WPT; v++) c += __popc(bm[tid * WPT + v]);
+  int inc = c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if ((tid & 31) >= d) inc += t; }
+  if ((tid & 31) == 31) wsum[tid >> 5] = inc;
+  __syncthreads();
+  int off = inc - c, total = 0;
+#pragma unroll
+  for (int v = 0; v < LT_ROWS / 32; v++) { if (v < (tid >> 5)) off += wsum[v]; total += wsum[v]; }
+  const bool ok = total <= LT_CAP;
+  int run = off;
+#pragma unroll
+  for (int v = 0; v < WPT; v++) {
+    const int wd = tid * WPT + v;
+    pre[wd] = (uint16_t)run;
+    uint32_t b = bm[wd];
+    while (b) {
+      const int bit = __ffs(b) - 1; b &= b - 1;
+      if (ok) tile_nodes[tile * LT_CAP + run] = (uint16_t)(wd * 32 + bit);
+      run++;
+    }
+  }
+  if (tid == 0) tile_cnt[tile] = ok ? (uint16_t)total : (uint16_t)0;
+  __syncthreads();
+  if (i < rows) {
+    uint32_t sw[LT_WORDS] = {0u, 0u, 0u};
+    if (ok)
+      for (int j = 0; j < k; j++) {
+        const unsigned n = ridx[base + j * 32];
+        const unsigned rank = pre[n >> 5] + __popc(bm[n >> 5] & ((1u << (n & 31)) - 1u));
+        sw[j >> 2] |= rank << ((j & 3) * 8);
+      }
+    const long long sb = (i >> 5) * (long long)(LT_WORDS * 32) + (i & 31);
+    for (int m = 0; m < LT_WORDS; m++) slots[sb + m * 32] = sw[m];
+  }
 }
 
 // ------------------------------------------------------------------ end points
@@ -456,6 +612,47 @@ extern "C" int arapk_lbs_points(const float* in, float* out, long long P, int k,
     case 12: k_lbs_points<12><<<grid, bs, 0, st>>>(in, out, P, k, ridx, rw, nx, skip, group); break;
     default: k_lbs_points<0><<<grid, bs, 0, st>>>(in, out, P, k, ridx, rw, nx, skip, group); break;
   }
+  ARAP_KERNEL_CHECK();
+  return ARAP_OK;
+}
+
+extern "C" long long arapk_lbs_tile_count(long long rows) { return (rows + LT_ROWS - 1) / LT_ROWS; }
+extern "C" int arapk_lbs_tile_cap(void) { return LT_CAP; }
+
+// slots: ceil(rows/32)*32*3 words; tile_cnt: tile_count entries; tile_nodes: tile_count * cap entries
+extern "C" int arapk_lbs_build_tiles(long long rows, int k, const uint16_t* ridx, uint32_t* slots, uint16_t* tile_cnt,
+                                     uint16_t* tile_nodes, cudaStream_t st) {
+  if (rows <= 0) return ARAP_OK;
+  if (k < 1 || k > KNN_MAX) { set_error("lbs_build_tiles: k out of range"); return ARAP_ERR_INVALID; }
+  k_build_tiles<<<(unsigned)arapk_lbs_tile_count(rows), LT_ROWS, 0, st>>>(rows, k, ridx, slots, tile_cnt, tile_nodes);
+  ARAP_KERNEL_CHECK();
+  return ARAP_OK;
+}
+
+template <bool MAGIC>
+static void launch_lbs_tiles(const float* in, float* out, long long P, int k, const uint32_t* slots, const double* rw,
+                             const uint16_t* ridx, const uint16_t* tile_cnt, const uint16_t* tile_nodes, const NodeXf* nx,
+                             const uint8_t* skip, int group, cudaStream_t st) {
+  const unsigned grid = (unsigned)arapk_lbs_tile_count(P);
+  switch (k) {
+    case 8: k_lbs_tiles<8, MAGIC><<<grid, LT_ROWS, 0, st>>>(in, out, P, k, slots, rw, ridx, tile_cnt, tile_nodes, nx, skip, group); break;
+    case 10: k_lbs_tiles<10, MAGIC><<<grid, LT_ROWS, 0, st>>>(in, out, P, k, slots, rw, ridx, tile_cnt, tile_nodes, nx, skip, group); break;
+    case 12: k_lbs_tiles<12, MAGIC><<<grid, LT_ROWS, 0, st>>>(in, out, P, k, slots, rw, ridx, tile_cnt, tile_nodes, nx, skip, group); break;
+    default: k_lbs_tiles<0, MAGIC><<<grid, LT_ROWS, 0, st>>>(in, out, P, k, slots, rw, ridx, tile_cnt, tile_nodes, nx, skip, group); break;
+  }
+}
+
+// LBS through per-tile staged node records.  magic = 1: float rounding of the accumulator on the FP64 pipe
+// (round_to_float), 0: by conversion instructions.  Results are bit-identical to arapk_lbs_points.
+extern "C" int arapk_lbs_tiles(const float* in, float* out, long long P, int k, const uint32_t* slots, const double* rw,
+                               const uint16_t* ridx, const uint16_t* tile_cnt, const uint16_t* tile_nodes,
+                               const void* node_xf, const uint8_t* skip, int group, int magic, cudaStream_t st) {
+  if (P <= 0) return ARAP_OK;
+  if (k < 1 || k > KNN_MAX) { set_error("lbs_tiles: k out of range"); return ARAP_ERR_INVALID; }
+  if (group < 1) group = 1;
+  const NodeXf* nx = (const NodeXf*)node_xf;
+  if (magic) launch_lbs_tiles<true>(in, out, P, k, slots, rw, ridx, tile_cnt, tile_nodes, nx, skip, group, st);
+  else launch_lbs_tiles<false>(in, out, P, k, slots, rw, ridx, tile_cnt, tile_nodes, nx, skip, group, st);
   ARAP_KERNEL_CHECK();
   return ARAP_OK;
 }

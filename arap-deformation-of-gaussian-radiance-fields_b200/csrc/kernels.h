@@ -15,6 +15,13 @@ extern "C" {
 int arapk_node_xf(int M, const double* rot, const double* trans, const float* node_pos, void* node_xf, cudaStream_t st);
 int arapk_lbs_points(const float* in, float* out, long long P, int k, const uint16_t* ridx, const double* rw,
                      const void* node_xf, const uint8_t* skip, int group, cudaStream_t st);
+long long arapk_lbs_tile_count(long long rows);
+int arapk_lbs_tile_cap(void);
+int arapk_lbs_build_tiles(long long rows, int k, const uint16_t* ridx, uint32_t* slots, uint16_t* tile_cnt,
+                          uint16_t* tile_nodes, cudaStream_t st);
+int arapk_lbs_tiles(const float* in, float* out, long long P, int k, const uint32_t* slots, const double* rw,
+                    const uint16_t* ridx, const uint16_t* tile_cnt, const uint16_t* tile_nodes, const void* node_xf,
+                    const uint8_t* skip, int group, int magic, cudaStream_t st);
 int arapk_end_points(long long N, const float* pos, const float* rot, const float* scale, float* ends, cudaStream_t st);
 int arapk_fit_gaussians(long long N, const float* ends, const float* scale_backup, const uint8_t* is_static, float* pos,
                         float* rot, float* scale, float* shs, cudaStream_t st);
@@ -64,7 +71,11 @@ typedef struct ArapSolveParams {
   double cg_tol;               // relative residual of the first linear system; later ones reuse its absolute value
   int force_global_kernel;     // 1: skip the shared-memory-resident fast path (tests)
   double newton_eta0;          // > 0: inexact Newton forcing (shared-memory kernel only), see arapgs.h
+  double* warm_buf;            // device, arapk_solve_warm_doubles(M) doubles, zeroed by the caller whenever the unknown set changes;
+                               // null = every PCG solve starts from 0.  See arapgs.h (arap_params.warm_start).
 } ArapSolveParams;
+
+size_t arapk_solve_warm_doubles(int M);
 
 size_t arapk_solve_workspace_bytes(int M, int k, int n_groups);
 int arapk_solve(const ArapSolveGraph* G, const ArapSolveParams* P, void* workspace, size_t workspace_bytes,

@@ -134,6 +134,8 @@ struct DBuf {
 struct RowTable {  // blocked skinning rows of one query family
   long long rows = 0; int k = 0;
   DBuf<uint16_t> idx; DBuf<double> w; DBuf<float> wf;
+  // per-tile distinct node lists + one-byte slots for the staged LBS kernel (apply.cu: k_lbs_tiles)
+  DBuf<uint32_t> slots; DBuf<uint16_t> tile_cnt, tile_nodes;
   size_t entries() const { return (size_t)((rows + 31) / 32) * 32 * k; }
 };
 
@@ -174,7 +176,7 @@ struct arap_ctx {
   struct ConSet { int n_groups = 0; long long n_entries = 0; DBuf<int> grp_off, grp_member, aim_off, aim_nodes, cin_off, cin_grp, cin_member, cin_slot; DBuf<float> grp_aim; };
   ConSet con[2];
   // solve
-  DBuf<double> rot_d, trans_d, stats_d; DBuf<char> solve_ws; DBuf<char> node_xf; DBuf<float> node_q;
+  DBuf<double> rot_d, trans_d, stats_d, warm_d; DBuf<char> solve_ws; DBuf<char> node_xf; DBuf<float> node_q;
   double* stats_h = nullptr;  // pinned
   cudaEvent_t ev_soa = nullptr;   // recorded after the six-point fit of every apply: the rasteriser-facing SoA is final
   cudaEvent_t ev_release = nullptr;  // caller's event (not owned): its reads of the SoA are done; the next fit waits for it
@@ -195,7 +197,7 @@ extern "C" int arap_default_params(arap_params* p) {
   if (!p) return ARAP_ERR_INVALID;
   p->grid_num = 64; p->padding = 1; p->knn_k = 10; p->node_num = 150; p->high_quality = 0; p->lpf_parameter = 0.2f;
   p->w_rot = 1.0; p->w_reg = 10.0; p->w_con = 100.0; p->max_gn_iters = 30; p->max_cg_iters = 4000; p->cg_tol = 1e-10;
-  p->skip_static_endpoints = 0; p->solver_global_memory = 0; p->reserved0 = 0; p->newton_eta0 = 1e-6;
+  p->skip_static_endpoints = 0; p->solver_global_memory = 0; p->lbs_mode = 0; p->newton_eta0 = 1e-6; p->warm_start = 1;
   return ARAP_OK;
 }
 
@@ -447,6 +449,23 @@ static int knn_family(arap_ctx* c, const float* queries, long long Q, int k, Row
   return ARAP_OK;
 }
 
+static int build_tiles(arap_ctx* c, RowTable& t) {
+  if (t.rows <= 0) return ARAP_OK;
+  const size_t nt = (size_t)arapk_lbs_tile_count(t.rows);
+  TRY(t.slots.alloc((size_t)((t.rows + 31) / 32) * 32 * 3)); TRY(t.tile_cnt.alloc(nt)); TRY(t.tile_nodes.alloc(nt * (size_t)arapk_lbs_tile_cap()));
+  return arapk_lbs_build_tiles(t.rows, t.k, t.idx.p, t.slots.p, t.tile_cnt.p, t.tile_nodes.p, c->stream);
+}
+
+// LBS of one row family.  prm.lbs_mode: 0 = staged node records + FP64-pipe float rounding (default),
+// 1 = global-memory gathers (first version), 2 = staged records, rounding by conversion instructions.
+static int lbs_family(arap_ctx* c, const float* in, float* out, const RowTable& t, const uint8_t* skip, int group) {
+  if (t.rows <= 0) return ARAP_OK;
+  if (c->prm.lbs_mode == 1 || !t.slots.p)
+    return arapk_lbs_points(in, out, t.rows, t.k, t.idx.p, t.w.p, c->node_xf.p, skip, group, c->stream);
+  return arapk_lbs_tiles(in, out, t.rows, t.k, t.slots.p, t.w.p, t.idx.p, t.tile_cnt.p, t.tile_nodes.p, c->node_xf.p, skip, group,
+                         c->prm.lbs_mode == 0, c->stream);
+}
+
 static int finish_graph(arap_ctx* c, int k) {
   cudaStream_t st = c->stream;
   const int M = c->M;
@@ -496,8 +515,10 @@ static int finish_graph(arap_ctx* c, int k) {
   TRY(knn_family(c, c->ends.p, c->N * 6, k, c->end_rows, false));
   TRY(knn_family(c, c->sample_pos.p, c->S, k, c->sample_rows, true));
   TRY(knn_family(c, c->mesh_pts.p, c->Mp, k, c->mesh_rows, false));
+  TRY(build_tiles(c, c->end_rows)); TRY(build_tiles(c, c->sample_rows)); TRY(build_tiles(c, c->mesh_rows)); TRY(build_tiles(c, c->node_rows));
   // solve outputs
   TRY(c->rot_d.alloc((size_t)M * 9)); TRY(c->trans_d.alloc((size_t)M * 3)); TRY(c->stats_d.alloc(32));
+  TRY(c->warm_d.alloc(arapk_solve_warm_doubles(M)));
   TRY(c->node_xf.alloc((size_t)M * 112)); TRY(c->node_q.alloc((size_t)M * 4));
   TRY(c->node_free.alloc((size_t)M)); TRY(c->node_static.alloc((size_t)M)); TRY(c->static_in_cnt.alloc((size_t)M)); TRY(c->active_mult.alloc((size_t)M));
   TRY(c->center_tmp.alloc(4));
@@ -628,6 +649,7 @@ extern "C" int arap_set_blocks(arap_ctx* ctx, int n_blocks, const int* block_off
   CTX_CHECK(ctx);
   if (!ctx->graph_ready) { set_error("set_blocks: graph not built"); return ARAP_ERR_STATE; }
   const int M = ctx->M, k = ctx->k; cudaStream_t st = ctx->stream;
+  ARAP_CUDA_TRY(cudaMemsetAsync(ctx->warm_d.p, 0, 8 * sizeof(double), st));   // the unknown set may change: no warm start for the next solve
   ctx->blocks.clear(); ctx->block_types.clear();
   for (int b = 0; b < n_blocks; b++) {
     std::vector<uint32_t> v(block_nodes + block_off[b], block_nodes + block_off[b + 1]);
@@ -736,7 +758,8 @@ extern "C" int arap_solve(arap_ctx* ctx, int on_center) {
   G.anc_idx = ctx->anc_idx.p; G.anc_w = ctx->anc_w.p; G.node_free = ctx->node_free.p; G.static_in_cnt = ctx->static_in_cnt.p;
   G.grp_off = cs.grp_off.p; G.grp_member = cs.grp_member.p; G.grp_aim = cs.grp_aim.p;
   G.cin_off = cs.cin_off.p; G.cin_grp = cs.cin_grp.p; G.cin_member = cs.cin_member.p; G.cin_slot = cs.cin_slot.p; G.n_cin_entries = cs.n_entries;
-  ArapSolveParams P{ctx->prm.w_rot, ctx->prm.w_reg, ctx->prm.w_con, ctx->prm.max_gn_iters, ctx->prm.max_cg_iters, ctx->prm.cg_tol, ctx->prm.solver_global_memory, ctx->prm.newton_eta0};
+  ArapSolveParams P{ctx->prm.w_rot, ctx->prm.w_reg, ctx->prm.w_con, ctx->prm.max_gn_iters, ctx->prm.max_cg_iters, ctx->prm.cg_tol, ctx->prm.solver_global_memory, ctx->prm.newton_eta0,
+                    ctx->prm.warm_start ? ctx->warm_d.p : nullptr};
   TRY(ctx->solve_ws.alloc(arapk_solve_workspace_bytes(G.M, G.k, G.n_groups)));
   TRY(arapk_solve(&G, &P, ctx->solve_ws.p, ctx->solve_ws.n, ctx->rot_d.p, ctx->trans_d.p, ctx->stats_d.p, st));
   ctx->solved = true;
@@ -772,16 +795,15 @@ extern "C" int arap_apply(arap_ctx* ctx) {
   const bool tm = ctx->timing;
   if (tm) cudaEventRecord(ctx->ev[1], st);
   TRY(arapk_node_xf(M, ctx->rot_d.p, ctx->trans_d.p, ctx->node_pos.p, ctx->node_xf.p, st));
-  if (ctx->Mp > 0) TRY(arapk_lbs_points(ctx->mesh_pts.p, ctx->mesh_pts.p, ctx->Mp, k, ctx->mesh_rows.idx.p, ctx->mesh_rows.w.p, ctx->node_xf.p, nullptr, 1, st));
-  TRY(arapk_lbs_points(ctx->ends.p, ctx->ends.p, ctx->N * 6, k, ctx->end_rows.idx.p, ctx->end_rows.w.p, ctx->node_xf.p,
-                       ctx->prm.skip_static_endpoints ? ctx->gs_static.p : nullptr, 6, st));
-  TRY(arapk_lbs_points(ctx->node_pos.p, ctx->node_next.p, M, k, ctx->node_rows.idx.p, ctx->node_rows.w.p, ctx->node_xf.p, nullptr, 1, st));
+  if (ctx->Mp > 0) TRY(lbs_family(ctx, ctx->mesh_pts.p, ctx->mesh_pts.p, ctx->mesh_rows, nullptr, 1));
+  TRY(lbs_family(ctx, ctx->ends.p, ctx->ends.p, ctx->end_rows, ctx->prm.skip_static_endpoints ? ctx->gs_static.p : nullptr, 6));
+  TRY(lbs_family(ctx, ctx->node_pos.p, ctx->node_next.p, ctx->node_rows, nullptr, 1));
   if (tm) cudaEventRecord(ctx->ev[2], st);
   if (ctx->ev_release) { ARAP_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_release, 0)); ctx->ev_release = nullptr; }
   TRY(arapk_fit_gaussians(ctx->N, ctx->ends.p, ctx->scale_backup.p, ctx->gs_static.p, ctx->pos.p, ctx->rot.p, ctx->scale.p, ctx->shs.p, st));
   ARAP_CUDA_TRY(cudaEventRecord(ctx->ev_soa, st));
   if (tm) cudaEventRecord(ctx->ev[3], st);
-  if (ctx->S > 0) TRY(arapk_lbs_points(ctx->sample_pos.p, ctx->sample_pos.p, ctx->S, k, ctx->sample_rows.idx.p, ctx->sample_rows.w.p, ctx->node_xf.p, ctx->sample_static.p, 1, st));
+  if (ctx->S > 0) TRY(lbs_family(ctx, ctx->sample_pos.p, ctx->sample_pos.p, ctx->sample_rows, ctx->sample_static.p, 1));
   if (tm) cudaEventRecord(ctx->ev[4], st);
   if (ctx->S > 0 && ctx->aim_feature.p) {
     TRY(arapk_node_quats(M, ctx->rot_d.p, ctx->node_q.p, st));

@@ -472,6 +472,8 @@ extern "C" size_t arapk_solve_workspace_bytes(int M, int k, int n_groups) {
   return d * sizeof(double);
 }
 
+extern "C" size_t arapk_solve_warm_doubles(int M) { return 8 + (size_t)SOLVE_WARM_MAX * (size_t)M * 12; }
+
 extern "C" int arapk_solve(const ArapSolveGraph* G, const ArapSolveParams* P, void* workspace, size_t workspace_bytes,
                            double* rot_out, double* trans_out, double* stats_dev, cudaStream_t st) {
   if (G->M < 1 || G->k < 1 || G->k > KNN_MAX) { set_error("solve: bad graph"); return ARAP_ERR_INVALID; }
@@ -502,6 +504,7 @@ extern "C" int arapk_solve(const ArapSolveGraph* G, const ArapSolveParams* P, vo
   S.partial = w; w += 2 * 2048 * NRED;
   unsigned* counter = reinterpret_cast<unsigned*>(w);
   S.rot_out = rot_out; S.trans_out = trans_out; S.stats = stats_dev;
+  S.warm = P->warm_buf;
   if (!P->force_global_kernel) {   // fast path: per-node state resident in shared memory (solve_smem.cu)
     const int rc = launch_solve_smem(S, reinterpret_cast<unsigned*>(S.partial), st);   // barrier slots live in the partials area (2 x 148 x 64 B)
     if (rc >= 0) return rc;

@@ -33,7 +33,11 @@ struct SolveDev {
   int* gent_q;                 // node of each entry, -1 if excluded
   double* partial;             // 2 x gridDim x NRED
   double *rot_out, *trans_out, *stats;
+  // warm start of the linear solves (shared-memory kernel): warm[0] = number of Gauss-Newton systems whose solution the
+  // previous solve saved, warm + 8 + g * M * 12 = that solution for system g < SOLVE_WARM_MAX; null = off
+  double* warm;
 };
+constexpr int SOLVE_WARM_MAX = 4;
 
 
 // solve_smem.cu: returns ARAP_OK if launched, a positive error code on CUDA failure, -1 if the per-CTA slice does not

@@ -718,6 +718,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_solve_smem(SolveDev S, unsign
   red[0] = red[1] = red[2] = 0.0;
   barrier_reduce<1>(S, counter, phase, red);
 
+  const int n_warm = S.warm ? min((int)S.warm[0], SOLVE_WARM_MAX) : 0;   // rewritten by block 0 at the very end, i.e. after barriers every CTA passes after this read
   int gn_iters = 0, halvings = 0, total_cg = 0, flag = 0;
   double energy = 0.0, normh = 0.0, last_rel = 0.0, abs_target = -1.0, E0 = 0.0;
   bool have_f = false;
@@ -736,6 +737,13 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_solve_smem(SolveDev S, unsign
     }
     energy = E0;
     // ---- gradient, Jacobi preconditioner
+    // Warm start.  Consecutive drag steps solve nearly the same systems, so system gn starts from the solution h' the
+    // previous step found for ITS system gn instead of from 0.  It is folded into the loop as a first iteration with
+    // p = h' and alpha forced to 1 (h = h', r = g - H h', z = r / diag), after which plain PCG continues with beta = 0.
+    // The stopping rule is unchanged (residual relative to |g|), so the answer is the same to the solver tolerance;
+    // only the number of iterations drops.
+    const bool warm = gn < n_warm;
+    double* warm_h = S.warm ? S.warm + 8 + (size_t)gn * S.M * 12 : nullptr;
     double rz_l = 0.0, gg_l = 0.0, xx_l = 0.0;
     for (int t = tid; t < NU; t += SM_THREADS) {
       const int li = t / 12, qi = t - 12 * li, j = qi >> 2, c = qi & 3;
@@ -748,8 +756,10 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_solve_smem(SolveDev S, unsign
       const double g = -gather_smem<K>(S, L, li, j, c, Aj, f, xv);
       const double di = 1.0 / diag_smem<K>(S, L, li, j, c, Aj);
       const double zv = g * di;
-      L.ds[t] = di; L.rs[t] = g; L.zs[t] = zv; L.hs[t] = 0.0;
-      S.z[(size_t)(li * B + b) * 12 + pub(qi)] = zv;
+      // warm start: the first search direction is the previous drag step's solution of this system (see the PCG loop)
+      const double z0 = warm ? warm_h[(size_t)(li * B + b) * 12 + qi] : zv;
+      L.ds[t] = di; L.rs[t] = g; L.zs[t] = z0; L.hs[t] = 0.0;
+      S.z[(size_t)(li * B + b) * 12 + pub(qi)] = z0;
       rz_l = fma(g, zv, rz_l); gg_l = fma(g, g, gg_l); xx_l = fma(xv, xv, xx_l);
     }
     red[0] = rz_l; red[1] = gg_l; red[2] = xx_l;
@@ -794,7 +804,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_solve_smem(SolveDev S, unsign
           barrier_skew(counter, phase - 1, t2, s_skew + 5);
         }
         const double pHp = red[0];
-        const double alpha = rz / pHp;
+        const double alpha = (warm && it == 0) ? 1.0 : rz / pHp;
         double rzn_l = 0.0, rr_l = 0.0;
         for (int t0 = 0; t0 < NU; t0 += SM_GB * SM_THREADS) {   // NU is a multiple of 4: quads are all in or all out
           GatherLd G[SM_GB];
@@ -836,12 +846,14 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_solve_smem(SolveDev S, unsign
         const double rzn = red[0], rr = red[1];
         last_rel = sqrt(rr / gg);
         cur ^= 1;
-        if (!(pHp > 0.0) || !(rr == rr)) { flag |= 1; break; }
+        if ((!(pHp > 0.0) && !(warm && it == 0)) || !(rr == rr)) { flag |= 1; break; }   // a zero warm guess is fine (p = 0)
         if (rr <= target || rr <= 1e-30 * gg) break;
-        beta = rzn / rz; rz = rzn;
+        beta = (warm && it == 0) ? 0.0 : rzn / rz; rz = rzn;
         if (it == S.max_cg - 1) flag |= 2;
       }
     }
+    if (S.warm && gn < SOLVE_WARM_MAX)   // this system's solution (before step halving) seeds the next drag step
+      for (int t = tid; t < NU; t += SM_THREADS) warm_h[(size_t)((t / 12) * B + b) * 12 + (t % 12)] = L.hs[t];
 
     // ---- step halving (Deform.cpp:144-156): publish x + h, evaluate, accept or halve
     bool accepted = false;
@@ -891,6 +903,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_solve_smem(SolveDev S, unsign
     if (c < 3) S.rot_out[(size_t)i * 9 + jj + 3 * c] = v; else S.trans_out[(size_t)i * 3 + jj] = v;
   }
   if (b == 0 && tid == 0) {
+    if (S.warm) S.warm[0] = (flag & 1) ? 0.0 : (double)min(gn_iters, SOLVE_WARM_MAX);
     S.stats[0] = gn_iters; S.stats[1] = energy; S.stats[2] = halvings; S.stats[3] = normh;
     S.stats[4] = total_cg; S.stats[5] = last_rel; S.stats[6] = flag;
     S.stats[8] = s_time[0]; S.stats[9] = s_time[1]; S.stats[10] = s_time[2]; S.stats[11] = s_time[3]; S.stats[12] = gridDim.x;

@@ -191,6 +191,27 @@ def run_own(args):
         one_step()
     barrier()
     s.enable_timing(True)
+    # debug: stage timers of parameter variants on the same session (stderr; the reported run follows with the defaults
+    # plus --set).  --variants "lbs_mode=1;lbs_mode=2,warm_start=0"
+    def parse(spec):
+        return {kv.split("=")[0]: (float(kv.split("=")[1]) if "." in kv or "e" in kv.split("=")[1] else int(kv.split("=")[1])) for kv in spec.split(",") if kv}
+    base = {kk: getattr(s.params, kk) for kk in ("lbs_mode", "warm_start", "newton_eta0")}
+    for spec in [v for v in args.variants.split(";") if v]:
+        s.set_params(**{**base, **parse(spec)})
+        for _ in range(3):
+            one_step()
+        barrier()
+        s.enable_timing(True)
+        for _ in range(10):
+            one_step()
+        barrier()
+        m10 = s.step_timings(10).mean(0)
+        print(json.dumps({"variant": spec, "stages_ms": [round(float(x), 4) for x in m10], "cg_iters": s.solve_stats()["cg_iters"]}), file=sys.stderr, flush=True)
+    s.set_params(**{**base, **parse(args.set)})
+    for _ in range(3):
+        one_step()
+    barrier()
+    s.enable_timing(True)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -367,6 +388,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--newton-eta0", type=float, default=None, help="override arap_params.newton_eta0 (debug)")
     ap.add_argument("--max-cg", type=int, default=None, help="override arap_params.max_cg_iters (debug)")
+    ap.add_argument("--set", default="", help="arap_params overrides for the reported run, e.g. lbs_mode=1,warm_start=0 (debug)")
+    ap.add_argument("--variants", default="", help="';'-separated override sets timed before the reported run (debug, stderr)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

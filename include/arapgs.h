@@ -56,12 +56,17 @@ typedef struct arap_params {
   double cg_tol;       /* relative residual of the first linear system of a step */
   int skip_static_endpoints; /* 0 = reference behaviour (all endpoints skinned) */
   int solver_global_memory;  /* 1 = force the global-memory solver kernel (default 0: shared-memory-resident kernel when it fits) */
-  int reserved0;
+  int lbs_mode;        /* skinning (LBS) kernel: 0 = node records staged per 128-row tile in shared memory + float rounding on the
+                          FP64 pipe (default), 1 = global-memory gathers, 2 = staged records + conversion instructions.
+                          All three produce identical bits. */
   double newton_eta0;  /* each Gauss-Newton linear system stops at relative residual newton_eta0 of its own right-hand side
                           or at the cg_tol target, whichever is looser (0 = cg_tol target only).  Default 1e-6: the error of
                           system k reaches the result damped by the remaining Gauss-Newton steps, ~ newton_eta0 x (last step
                           length); measured node-transform deviation from the reference's direct solves stays at the 1e-11 level
                           of the cg_tol-only rule with ~25% fewer PCG iterations (1e-4 is where the parity bar is reached). */
+  int warm_start;      /* 1 (default): every PCG solve of a drag step starts from the solution the previous step found for the same
+                          Gauss-Newton system (zero after arap_set_blocks / a graph build).  Same stopping rule, same answer to the
+                          solver tolerance, fewer iterations while the drag is coherent.  0 = start from zero like the first step. */
 } arap_params;
 
 typedef struct arap_solve_stats {

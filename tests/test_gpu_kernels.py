@@ -108,6 +108,57 @@ def test_lbs_points_bit_exact(pkg, orc, k):
     assert np.abs(out - ref).max() <= 1.2e-7
 
 
+@pytest.mark.parametrize("k", [10, 8, 12, 5, 1])
+def test_lbs_tiles_bit_exact(pkg, orc, k):
+    """The staged-record LBS kernel (per-tile distinct node lists, one-byte slots, optional FP64-pipe float rounding) must
+    give the same bits as the global-gather kernel and the oracle, on tiles that fit the staging area and tiles that do not."""
+    lib = pkg.lib()
+    rng = np.random.default_rng(100 + k)
+    M, P = 3000, 150011
+    nodes = (rng.normal(size=(M, 3)) * 0.4).astype(np.float32)
+    pts = (rng.normal(size=(P, 3)) * 0.4).astype(np.float32)
+    half = P // 2                                                     # first half spatially coherent (few nodes per tile), rest random
+    ctr = (rng.normal(size=(half // 125 + 1, 3)) * 0.4).astype(np.float32)
+    pts[:half] = (np.repeat(ctr, 125, axis=0)[:half] + rng.normal(size=(half, 3)) * 0.01).astype(np.float32)
+    pts[7] = 0.0                                                      # exact zeros through the rounding trick
+    idx, w = orc.knn_weights(nodes, pts, k)
+    rot, trans = _random_transforms(rng, M)
+    rot[3] = np.eye(3).reshape(9); trans[3] = 0.0
+    skip = (rng.uniform(size=P) < 0.1).astype(np.uint8)
+    ref = orc.lbs_points(pts.copy(), idx[:, :k], w, nodes, rot, trans, skip=skip.astype(np.int32))
+    bi, bw = _blocked(idx, w, k)
+    xf = torch.empty(M * 112, dtype=torch.uint8, device="cuda")
+    d_rot, d_trans, d_nodes = dev(rot), dev(trans), dev(nodes)
+    pkg.check(lib.arapk_node_xf(M, ptr(d_rot), ptr(d_trans), ptr(d_nodes), ptr(xf), stream()))
+    d_bi, d_bw, d_skip = dev(bi), dev(bw), dev(skip)
+    nt, cap = lib.arapk_lbs_tile_count(P), lib.arapk_lbs_tile_cap()
+    d_slots = torch.zeros(((P + 31) // 32) * 32 * 3, dtype=torch.int32, device="cuda")
+    d_cnt = torch.zeros(nt, dtype=torch.int16, device="cuda")
+    d_tn = torch.zeros(nt * cap, dtype=torch.int16, device="cuda")
+    pkg.check(lib.arapk_lbs_build_tiles(C.c_longlong(P), k, ptr(d_bi), ptr(d_slots), ptr(d_cnt), ptr(d_tn), stream()))
+    torch.cuda.synchronize()
+    cnt = d_cnt.cpu().numpy().astype(np.int64)
+    if k > 1:
+        assert (cnt > 0).sum() > nt // 4 and (cnt == 0).sum() > nt // 4, ((cnt > 0).sum(), nt)   # both paths exercised
+    # distinct lists are what the rows reference
+    t0 = int(np.nonzero(cnt > 0)[0][0])
+    want = np.unique(idx[t0 * 128:(t0 + 1) * 128, :k])
+    assert np.array_equal(d_tn.cpu().numpy().view(np.uint16)[t0 * cap:t0 * cap + cnt[t0]], want)
+    d_a = dev(pts)
+    pkg.check(lib.arapk_lbs_points(ptr(d_a), ptr(d_a), C.c_longlong(P), k, ptr(d_bi), ptr(d_bw), ptr(xf), ptr(d_skip), 1, stream()))
+    outs = [d_a.cpu().numpy()]
+    for magic in (0, 1):
+        d_b = dev(pts)
+        pkg.check(lib.arapk_lbs_tiles(ptr(d_b), ptr(d_b), C.c_longlong(P), k, ptr(d_slots), ptr(d_bw), ptr(d_bi), ptr(d_cnt), ptr(d_tn),
+                                      ptr(xf), ptr(d_skip), 1, magic, stream()))
+        torch.cuda.synchronize()
+        outs.append(d_b.cpu().numpy())
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])     # three kernels, same bits
+    mism = np.nonzero(outs[2] != ref)[0]
+    assert len(mism) <= 2, (len(mism), np.abs(outs[2] - ref).max())
+    assert np.abs(outs[2] - ref).max() <= 1.2e-7
+
+
 def test_end_points_and_fit_match_oracle(pkg, orc, scenes):
     lib = pkg.lib()
     sc = scenes.make_scene("sphere1m", n=50001)

@@ -102,6 +102,42 @@ def test_drag_steps_match_oracle(pkg, scenes, on_center, eta0):
     assert np.abs(sp - o.sample_pos).max() <= 3e-7 and np.abs(sf - o.aim_feature).max() <= 2e-5
 
 
+def test_warm_start_and_lbs_kernels_agree(pkg, scenes):
+    """Defaults (PCG warm start from the previous drag step, staged-record LBS) vs the first version's path (cold PCG,
+    global-gather LBS): same node transforms to the solver tolerance, fewer PCG iterations, same Gaussians."""
+    sc = scenes.make_scene("sphere1m", n=30000)
+    ss = []
+    for kw in (dict(), dict(warm_start=0, lbs_mode=1), dict(lbs_mode=2)):
+        s = pkg.Session(device=0, grid_num=32, knn_k=10, node_num=200)
+        s.set_params(**kw)
+        s.set_gaussians(sc["pos"], sc["rot"], sc["scale"], sc["opacity"], sc["shs"])
+        s.grid_build(); s.grid_eval(0)
+        g = s.graph_build_fps()
+        blocks, types = scenes.cap_blocks(g["node_pos"], lo=-0.3, hi=0.3)
+        s.set_blocks(blocks, types)
+        ss.append(s)
+    iters = np.zeros((3, 6), int)
+    for step in range(6):
+        d = [0.002, 0.0, 0.01] if step != 3 else [0.0, 0.0, 0.0]      # a zero-delta step in the middle (zero warm guess afterwards)
+        res = []
+        for i, s in enumerate(ss):
+            s.aim_translate(d)
+            s.solve(False)
+            st = s.solve_stats()
+            assert st["flags"] == 0
+            iters[i, step] = st["cg_iters"]
+            res.append(s.download_nodes()[1:])
+            s.apply()
+        for r in res[1:]:
+            assert np.abs(res[0][0] - r[0]).max() <= 2e-9 and np.abs(res[0][1] - r[1]).max() <= 2e-9
+    assert iters[0, 0] == iters[1, 0]                                  # first step: nothing to start from
+    assert iters[0, 1:3].sum() < 0.8 * iters[1, 1:3].sum(), iters     # coherent drag: fewer iterations
+    outs = [s.download_gaussians() for s in ss]
+    for o in outs[1:]:
+        _compare_gaussians(outs[0], o)
+    assert all(np.array_equal(outs[0][k], outs[2][k]) for k in outs[0])   # the two staged-record variants: identical bits
+
+
 def test_twist_scale_and_excluded_blocks(pkg, scenes):
     sc, s, o, gi, og = _pair(pkg, scenes, n=20000, grid_num=32, knn_k=10, node_num=120)
     g = s.graph_build_fps(); o.graph_build_fps()
