@@ -207,10 +207,11 @@ def run_own(args):
         barrier()
         m10 = s.step_timings(10).mean(0)
         print(json.dumps({"variant": spec, "stages_ms": [round(float(x), 4) for x in m10], "cg_iters": s.solve_stats()["cg_iters"]}), file=sys.stderr, flush=True)
-    s.set_params(**{**base, **parse(args.set)})
-    for _ in range(3):
-        one_step()
-    barrier()
+    if args.set or args.variants:
+        s.set_params(**{**base, **parse(args.set)})
+        for _ in range(3):
+            one_step()
+        barrier()
     s.enable_timing(True)
     clocks = ClockSampler(local)
     if rank == 0:

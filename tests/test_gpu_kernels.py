@@ -142,8 +142,12 @@ def test_lbs_tiles_bit_exact(pkg, orc, k):
         assert (cnt > 0).sum() > nt // 4 and (cnt == 0).sum() > nt // 4, ((cnt > 0).sum(), nt)   # both paths exercised
     # distinct lists are what the rows reference
     t0 = int(np.nonzero(cnt > 0)[0][0])
-    want = np.unique(idx[t0 * 128:(t0 + 1) * 128, :k])
-    assert np.array_equal(d_tn.cpu().numpy().view(np.uint16)[t0 * cap:t0 * cap + cnt[t0]], want)
+    staged = d_tn.cpu().numpy().view(np.uint16)[t0 * cap:t0 * cap + cnt[t0]]
+    assert np.array_equal(np.unique(staged), np.unique(idx[t0 * 128:(t0 + 1) * 128, :k]))   # unused slots repeat a node of the tile
+    sl = d_slots.cpu().numpy().view(np.uint8).reshape(-1, 3, 32, 4)                       # [block][word][lane][byte]
+    for r in range(t0 * 128, min((t0 + 1) * 128, P), 17):
+        got = [staged[sl[r // 32, j // 4, r % 32, j % 4]] for j in range(k)]
+        assert np.array_equal(got, idx[r, :k])                                            # slot -> node is the row's neighbour list
     d_a = dev(pts)
     pkg.check(lib.arapk_lbs_points(ptr(d_a), ptr(d_a), C.c_longlong(P), k, ptr(d_bi), ptr(d_bw), ptr(xf), ptr(d_skip), 1, stream()))
     outs = [d_a.cpu().numpy()]
