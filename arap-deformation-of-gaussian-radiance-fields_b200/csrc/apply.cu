@@ -15,6 +15,7 @@
 // so a warp reading neighbour j of 32 consecutive rows issues one 64 B and one
 // 256 B fully-coalesced request.
 #include <algorithm>
+#include <cstdlib>
 #include "device_math.cuh"
 #include "sh_fast.cuh"
 #include "kernels.h"
@@ -313,7 +314,7 @@ __device__ __forceinline__ void polar_newton(const double (&M)[3][3], double (&X
   for (int r = 0; r < 3; r++)
 #pragma unroll
     for (int c = 0; c < 3; c++) X[r][c] = M[r][c];
-  for (int it = 0; it < 12; it++) {
+  for (int it = 0; it < 14; it++) {
     double C[3][3];  // cofactors: X^-T = C / det
     C[0][0] = fma(X[1][1], X[2][2], -(X[1][2] * X[2][1]));
     C[0][1] = fma(X[1][2], X[2][0], -(X[1][0] * X[2][2]));
@@ -329,16 +330,15 @@ __device__ __forceinline__ void polar_newton(const double (&M)[3][3], double (&X
     const float adet = fabsf((float)det);
     const double mu = (adet > 1.25f || adet < 0.8f) ? (double)rcbrtf(adet) : 1.0;
     const double a = 0.5 * mu, b = 0.5 / (mu * det);
-    double delta = 0.0;
+    // After any step every singular value is (a + 1/a)/2 >= 1, so | |det| - 1 | bounds max(sigma - 1); the error
+    // squares per step ((sigma - 1)^2 / 2 sigma): below 2e-8 this step is the last one (result error ~2e-16).
+    // Replaces a max |X_new - X| test that cost more FP64 instructions than the update itself and one extra iteration.
+    const bool last = it > 0 && fabs(fabs(det) - 1.0) < 2e-8;
 #pragma unroll
     for (int r = 0; r < 3; r++)
 #pragma unroll
-      for (int c = 0; c < 3; c++) {
-        const double nx = fma(a, X[r][c], b * C[r][c]);
-        delta = fmax(delta, fabs(nx - X[r][c]));
-        X[r][c] = nx;
-      }
-    if (delta < 1e-15) break;
+      for (int c = 0; c < 3; c++) X[r][c] = fma(a, X[r][c], b * C[r][c]);
+    if (last) break;
   }
 }
 
@@ -346,6 +346,22 @@ constexpr int FIT_TILE = 128;
 constexpr int SH_PITCH = 49;    // odd pitch: conflict-free per-thread rows
 constexpr int END_PITCH = 19;
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+// One 128-Gaussian tile per CTA.  The SH tile (24.5 KB) is fetched with 4-byte cp.async straight into its odd-pitch rows
+// and lands while the pose (centre, polar factor, quaternion, scale) is computed from the end points; waiting for it in
+// registers before doing anything else was 36 % of the kernel's stall samples.
 __global__ void __launch_bounds__(FIT_TILE, 6)
 k_fit_gaussians(long long N, const float* __restrict__ ends, const float* __restrict__ scale_backup,
                 const uint8_t* __restrict__ is_static, float* __restrict__ pos, float* __restrict__ rot,
@@ -359,29 +375,27 @@ k_fit_gaussians(long long N, const float* __restrict__ ends, const float* __rest
   const int tid = threadIdx.x;
   const int rows = (int)min((long long)FIT_TILE, N - g0);
   s_static[tid] = (tid < rows) ? (is_static ? is_static[g0 + tid] : 0) : 1;
-  __syncthreads();
-
-  // coalesced float4 staging of the SH tile (48 floats = 12 float4 per row) and
-  // the endpoint tile (18 floats per row; 2 rows = 9 float4)
-  const float* gsh = shs + g0 * SH_FLOATS;
-  for (int v = tid; v < rows * 12; v += FIT_TILE) {
-    const int r = v / 12, c4 = v - r * 12;
-    if (s_static[r]) continue;
-    const float4 x = ld_stream4(gsh + (size_t)v * 4);
-    float* d = s_sh + r * SH_PITCH + c4 * 4;
-    d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w;
-  }
+  // endpoint tile (18 floats per row, 8-byte granules) through registers into odd-pitch rows
   const float* gend = ends + g0 * 18;
   const int nend = rows * 18;
-  for (int v = tid * 2; v < nend; v += FIT_TILE * 2) {  // 8-byte granules (18 floats/row is even)
+  for (int v = tid * 2; v < nend; v += FIT_TILE * 2) {
     const int r = v / 18, c = v - r * 18;
     const float2 x = __ldg(reinterpret_cast<const float2*>(gend + v));
     s_end[r * END_PITCH + c] = x.x; s_end[r * END_PITCH + c + 1] = x.y;
   }
   __syncthreads();
+  const float* gsh = shs + g0 * SH_FLOATS;
+#pragma unroll 12
+  for (int t = 0; t < SH_FLOATS; t++) {
+    const int v = tid + t * FIT_TILE, r = v / SH_FLOATS, c = v - r * SH_FLOATS;
+    if (r < rows && !s_static[r]) cp_async4(s_sh + r * SH_PITCH + c, gsh + v);
+  }
+  cp_async_commit();
 
   const long long g = g0 + tid;
-  if (tid < rows && !s_static[tid]) {
+  const bool act = tid < rows && !s_static[tid];
+  float Rs[3][3];
+  if (act) {
     const float* e = s_end + tid * END_PITCH;
     const float4 o4 = ldg4(rot + 4 * g);
     const Quat oq{o4.x, o4.y, o4.z, o4.w};
@@ -415,9 +429,11 @@ k_fit_gaussians(long long N, const float* __restrict__ ends, const float* __rest
       pos[3 * g + i] = c[i];
     }
     const Quat rq = quat_normalized(quat_mul(q, quat_inverse(oq)));
-    float Rs[3][3]; quat_to_matrix(rq, Rs);
-    sh_rotate_flipped_fast(Rs, s_sh + tid * SH_PITCH);
+    quat_to_matrix(rq, Rs);
   }
+  cp_async_wait<0>();
+  __syncthreads();
+  if (act) sh_rotate_flipped_fast(Rs, s_sh + tid * SH_PITCH);
   __syncthreads();
   float* osh = shs + g0 * SH_FLOATS;
   for (int v = tid; v < rows * 12; v += FIT_TILE) {
@@ -486,14 +502,6 @@ __global__ void k_node_quats(int M, const double* __restrict__ rot, float4* __re
 constexpr int RS_TILE = 128;
 constexpr int RS_PITCH4 = 13;                       // float4 chunks per staged row
 constexpr int RS_STAGE4 = RS_TILE * RS_PITCH4;      // float4 per stage
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // the rare sin branch of Q_SlerpCUDA, kept out of line so the blend loop stays small
 __device__ __noinline__ void slerp_ratios_slow(float cf, float t, float& rA, float& rB) {

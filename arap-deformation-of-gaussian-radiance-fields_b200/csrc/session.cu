@@ -759,7 +759,7 @@ extern "C" int arap_solve(arap_ctx* ctx, int on_center) {
   G.grp_off = cs.grp_off.p; G.grp_member = cs.grp_member.p; G.grp_aim = cs.grp_aim.p;
   G.cin_off = cs.cin_off.p; G.cin_grp = cs.cin_grp.p; G.cin_member = cs.cin_member.p; G.cin_slot = cs.cin_slot.p; G.n_cin_entries = cs.n_entries;
   ArapSolveParams P{ctx->prm.w_rot, ctx->prm.w_reg, ctx->prm.w_con, ctx->prm.max_gn_iters, ctx->prm.max_cg_iters, ctx->prm.cg_tol, ctx->prm.solver_global_memory, ctx->prm.newton_eta0,
-                    ctx->prm.warm_start ? ctx->warm_d.p : nullptr};
+                    ctx->prm.warm_start ? ctx->warm_d.p : nullptr, ctx->prm.warm_start > 1 ? ctx->prm.warm_start - 1 : 0};
   TRY(ctx->solve_ws.alloc(arapk_solve_workspace_bytes(G.M, G.k, G.n_groups)));
   TRY(arapk_solve(&G, &P, ctx->solve_ws.p, ctx->solve_ws.n, ctx->rot_d.p, ctx->trans_d.p, ctx->stats_d.p, st));
   ctx->solved = true;

@@ -36,6 +36,7 @@ struct SolveDev {
   // warm start of the linear solves (shared-memory kernel): warm[0] = number of Gauss-Newton systems whose solution the
   // previous solve saved, warm + 8 + g * M * 12 = that solution for system g < SOLVE_WARM_MAX; null = off
   double* warm;
+  int warm_systems;            // how many Gauss-Newton systems of a step may be warm-started (<= SOLVE_WARM_MAX)
 };
 constexpr int SOLVE_WARM_MAX = 4;
 

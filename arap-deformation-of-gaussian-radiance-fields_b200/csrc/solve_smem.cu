@@ -718,7 +718,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_solve_smem(SolveDev S, unsign
   red[0] = red[1] = red[2] = 0.0;
   barrier_reduce<1>(S, counter, phase, red);
 
-  const int n_warm = S.warm ? min((int)S.warm[0], SOLVE_WARM_MAX) : 0;   // rewritten by block 0 at the very end, i.e. after barriers every CTA passes after this read
+  const int n_warm = S.warm ? min((int)S.warm[0], S.warm_systems) : 0;   // rewritten by block 0 at the very end, i.e. after barriers every CTA passes after this read
   int gn_iters = 0, halvings = 0, total_cg = 0, flag = 0;
   double energy = 0.0, normh = 0.0, last_rel = 0.0, abs_target = -1.0, E0 = 0.0;
   bool have_f = false;

@@ -66,7 +66,8 @@ typedef struct arap_params {
                           of the cg_tol-only rule with ~25% fewer PCG iterations (1e-4 is where the parity bar is reached). */
   int warm_start;      /* 1 (default): every PCG solve of a drag step starts from the solution the previous step found for the same
                           Gauss-Newton system (zero after arap_set_blocks / a graph build).  Same stopping rule, same answer to the
-                          solver tolerance, fewer iterations while the drag is coherent.  0 = start from zero like the first step. */
+                          solver tolerance, fewer iterations while the drag is coherent.  0 = start from zero like the first step;
+                          n > 1 = warm-start only the first n - 1 systems of a step. */
 } arap_params;
 
 typedef struct arap_solve_stats {

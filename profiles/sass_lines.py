@@ -30,6 +30,7 @@ agg = defaultdict(lambda: [0, 0, defaultdict(int)])
 tot_s = tot_i = 0
 for r in rows[2:]:
     if len(r) <= iinst: continue
+    if r[ia] == 'Address': break   # a second launch of the same kernel follows: the first one is enough
     a = int(r[ia], 16) if r[ia].startswith('0x') else int(r[ia])
     if base is None: base = a
     line = addr2line.get(a - base)
