@@ -86,7 +86,7 @@ def ncu_traffic(workload, n, key):
     """dram__bytes_read + dram__bytes_write of the pass from the committed ncu --set full capture (profiles/), per launch;
     None when the run is not the captured configuration."""
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_summary_r01.json")) as f:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_summary_r01b.json")) as f:
             d = json.load(f)
         return d[key] if d["workload"] == workload and d["gaussians"] == n else None
     except (OSError, KeyError, ValueError):
@@ -290,10 +290,10 @@ def run_own(args):
                   "row_phase_last_warp_us_and_barrier_us": [round(x / 1e3 / max(st["gn_iters"], 1), 2) for x in st["barrier_skew_ns"]]},
         "apply_gaussians_per_s": round(N / (apply_ms * 1e-3), 1) if apply_ms > 0 else None,
         "setup_s": {"grid_build_eval": round(setup["t_grid_s"], 3), "graph_knn": round(setup["t_graph_s"], 3)},
-        "roofline": {"bound": "hbm", "kernel": "apply pass (d): k_lbs_points<endpoints> + k_fit_gaussians", "achieved": round(apply_gbs, 1),
+        "roofline": {"bound": "hbm", "kernel": "apply pass (d): k_lbs_tiles<endpoints> + k_fit_gaussians", "achieved": round(apply_gbs, 1),
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(apply_gbs / peak, 4), "traffic": ncu_traffic(args.workload, N, "apply_pass_bytes"),
                      "algorithmic_bytes_per_launch": apply_bytes, "ms_per_launch": round(apply_ms, 4)},
-        "roofline_samples": {"bound": "hbm", "kernel": "sample pass (a9+a10): k_lbs_points<samples> + k_rotate_sample_shs",
+        "roofline_samples": {"bound": "hbm", "kernel": "sample pass (a9+a10): k_lbs_tiles<samples> + k_rotate_sample_shs",
                              "achieved": round(sample_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(sample_gbs / peak, 4),
                              "traffic": ncu_traffic(args.workload, N, "sample_pass_bytes"),
                              "algorithmic_bytes_per_launch": sample_bytes, "ms_per_launch": round(sample_ms, 4)},
