@@ -180,8 +180,8 @@ k_lbs_tiles(const float* __restrict__ in, float* __restrict__ out, long long P, 
 // Slot numbers are then chosen to avoid shared-memory bank conflicts in k_lbs_tiles: an LDS.128 is served one
 // quarter-warp (8 consecutive rows) at a time, and two records conflict there iff their slots are congruent mod 8
 // (144-byte pitch).  Nodes that are read by the same quarter-warp for the same neighbour position j are joined in a
-// graph, the graph is coloured greedily with 8 colours (least-loaded admissible colour), and slot = colour + 8 * (index
-// within the colour).  Measured on the 6M-Gaussian workload: 5.8 -> ~4 wavefronts per LDS.128 for the end-point rows.
+// graph weighted by how often that happens, every node takes the colour (of 8) that costs the fewest conflicts with the
+// nodes placed before it, and slot = colour + 8 * (index within the colour).  Measured on the 6M-Gaussian workload: 5.8 -> ~4 wavefronts per LDS.128 for the end-point rows.
 // tile_cnt = number of slots to stage (highest slot + 1; unused slots repeat a node of the tile), 0 = too many nodes.
 __global__ void __launch_bounds__(LT_ROWS)
 k_build_tiles(long long rows, int k, const uint16_t* __restrict__ ridx, uint32_t* __restrict__ slots,
@@ -189,7 +189,7 @@ k_build_tiles(long long rows, int k, const uint16_t* __restrict__ ridx, uint32_t
   __shared__ uint32_t bm[2048];
   __shared__ uint16_t pre[2048];
   __shared__ int wsum[LT_ROWS / 32];
-  __shared__ uint32_t adj[LT_CAP][3];
+  __shared__ uint16_t cow[LT_CAP][LT_CAP];   // co-occurrence counts: how many (quarter-warp, j) reads see both nodes
   __shared__ uint16_t node_of[LT_CAP];
   __shared__ uint8_t slot_of[LT_CAP];
   __shared__ int s_nslots;
@@ -197,7 +197,7 @@ k_build_tiles(long long rows, int k, const uint16_t* __restrict__ ridx, uint32_t
   const long long tile = blockIdx.x;
   const long long i = tile * LT_ROWS + tid;
   for (int v = tid; v < 2048; v += LT_ROWS) bm[v] = 0u;
-  for (int v = tid; v < LT_CAP * 3; v += LT_ROWS) (&adj[0][0])[v] = 0u;
+  for (int v = tid; v < LT_CAP * LT_CAP / 2; v += LT_ROWS) reinterpret_cast<uint32_t*>(&cow[0][0])[v] = 0u;
   __syncthreads();
   const long long base = (i >> 5) * (long long)(k * 32) + (i & 31);
   if (i < rows)
@@ -246,26 +246,41 @@ k_build_tiles(long long rows, int k, const uint16_t* __restrict__ ridx, uint32_t
   for (int j = 0; j < k; j++)
     for (int d = 1; d < 8; d++) {
       const int other = __shfl_xor_sync(0xffffffffu, rk[j], d);
-      if (rk[j] >= 0 && other >= 0 && other != rk[j]) atomicOr(&adj[rk[j]][other >> 5], 1u << (other & 31));
+      // 16-bit counters updated through their 32-bit word (a tile has 128 * 12 * 7 < 65536 increments per counter)
+      if (rk[j] >= 0 && other >= 0 && other != rk[j])
+        atomicAdd(reinterpret_cast<uint32_t*>(&cow[rk[j]][other & ~1]), (other & 1) ? 0x10000u : 1u);
     }
   __syncthreads();
   if (tid == 0) {
     int load[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int maxload = min(LT_CAP / 8, (total + 7) / 8 + 1);   // keeps the slot range (= records staged per step) tight
     uint8_t colour[LT_CAP];
     int hi = 0;
     for (int v = 0; v < total; v++) {
-      unsigned forb = 0;
-      for (int wd = 0; wd < 3; wd++) {
-        uint32_t m = adj[v][wd];
-        while (m) { const int u = wd * 32 + __ffs(m) - 1; m &= m - 1; if (u < v) forb |= 1u << colour[u]; }
-      }
+      unsigned cost[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // conflicts this node would have with the nodes already placed
+      for (int u = 0; u < v; u++) cost[colour[u]] += cow[v][u];
       int best = -1;
       for (int cc = 0; cc < 8; cc++)
-        if (!((forb >> cc) & 1u) && load[cc] < LT_CAP / 8 && (best < 0 || load[cc] < load[best])) best = cc;
-      if (best < 0)
-        for (int cc = 0; cc < 8; cc++) if (load[cc] < LT_CAP / 8 && (best < 0 || load[cc] < load[best])) best = cc;
+        if (load[cc] < maxload && (best < 0 || cost[cc] < cost[best] || (cost[cc] == cost[best] && load[cc] < load[best]))) best = cc;
       colour[v] = (uint8_t)best;
-      const int sl = best + 8 * load[best]++;
+      load[best]++;
+    }
+    // local search: move a node to a cheaper colour while that lowers its conflict count (three sweeps)
+    for (int sweep = 0; sweep < 3; sweep++) {
+      int moved = 0;
+      for (int v = 0; v < total; v++) {
+        unsigned cost[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int u = 0; u < total; u++) cost[colour[u]] += cow[v][u];   // cow[v][v] = 0
+        int best = colour[v];
+        for (int cc = 0; cc < 8; cc++)
+          if (cc != colour[v] && load[cc] < maxload && cost[cc] < cost[best]) best = cc;
+        if (best != colour[v]) { load[colour[v]]--; load[best]++; colour[v] = (uint8_t)best; moved++; }
+      }
+      if (!moved) break;
+    }
+    int used[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int v = 0; v < total; v++) {
+      const int sl = colour[v] + 8 * used[colour[v]]++;
       slot_of[v] = (uint8_t)sl;
       hi = sl > hi ? sl : hi;
     }

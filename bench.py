@@ -309,7 +309,7 @@ def run_own(args):
         dist.destroy_process_group()
 
 
-def cpu_sample_step(scenes, workload, full_n, cfg, sample_n, sample_nodes, steps=2):
+def cpu_sample_step(scenes, workload, full_n, cfg, sample_n, sample_nodes, steps=2, return_steps=False):
     """One bounded CPU sample of the workload through the oracle (the OpenMP restatement of the reference path)."""
     import oracle
     from oracle.session import OracleSession
@@ -323,11 +323,15 @@ def cpu_sample_step(scenes, workload, full_n, cfg, sample_n, sample_nodes, steps
     blocks, types = scenes.cap_blocks(o.node_pos)
     o.set_blocks(blocks, types)
     acc = dict(solve=0.0, samples_lbs=0.0, points_lbs=0.0, fit=0.0, sample_sh=0.0)
+    per_step = []
     for _ in range(steps):
         o.aim_translate(DRAG)
         o.step(False)
+        per_step.append({kk: o.timing[kk] for kk in acc})
         for kk in acc:
             acc[kk] += o.timing[kk] / steps
+    if return_steps:
+        return per_step, gi, threads
     return acc, gi, threads
 
 
@@ -354,16 +358,17 @@ def run_reference(args):
     N = args.gaussians or cfg["n"]
     world = int(os.environ.get("WORLD_SIZE", 1))
     sample_n, sample_nodes = min(N, 200_000), min(cfg["nodes"], 1000)
-    vals = []
-    parts = None
-    for i in range(max(1, min(args.steps, 3))):
-        acc, gi, threads = cpu_sample_step(scenes, args.workload, N, cfg, sample_n, sample_nodes, steps=1 + (1 if i == 0 and args.warmup else 0))
-        # the sample count follows the occupied volume, not the Gaussian count: the 200k-Gaussian sample of the scene
-        # already has 89% of the full scene's samples; scale by the full scene's count when it is known, else not at all
-        S_full = cfg.get("samples_at_n") if N == cfg["n"] and cfg.get("samples_at_n") else gi["samples"]
-        ms = ((acc["points_lbs"] + acc["fit"]) * 1e3 * (N / sample_n) + (acc["samples_lbs"] + acc["sample_sh"]) * 1e3 * (S_full / max(gi["samples"], 1))
-              + acc["solve"] * 1e3)
-        vals.append(ms)
+    # one set-up (scene, grid, FPS, brute-force kNN of the sample: most of the wall time), then W untimed + K timed steps,
+    # both bounded so that the arm ends within a few minutes on the box's host cores
+    warm, timed = min(max(args.warmup, 0), 1), max(1, min(args.steps, 3))
+    per_step, gi, threads = cpu_sample_step(scenes, args.workload, N, cfg, sample_n, sample_nodes, steps=warm + timed, return_steps=True)
+    # the sample count follows the occupied volume, not the Gaussian count: the 200k-Gaussian sample of the scene
+    # already has 89% of the full scene's samples; scale by the full scene's count when it is known, else not at all
+    S_full = cfg.get("samples_at_n") if N == cfg["n"] and cfg.get("samples_at_n") else gi["samples"]
+    vals, parts = [], None
+    for acc in per_step[warm:]:
+        vals.append((acc["points_lbs"] + acc["fit"]) * 1e3 * (N / sample_n) + (acc["samples_lbs"] + acc["sample_sh"]) * 1e3 * (S_full / max(gi["samples"], 1))
+                    + acc["solve"] * 1e3)
         parts = acc
     v = float(np.median(vals))
     sample = (f"oracle (OpenMP port; the reference cannot be built here: no Eigen/GL, CudaRasterizer fetched from the network) on {sample_n} Gaussians, "
