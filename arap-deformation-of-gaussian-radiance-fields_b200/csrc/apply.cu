@@ -398,6 +398,12 @@ k_fit_gaussians(long long N, const float* __restrict__ ends, const float* __rest
     const float2 x = __ldg(reinterpret_cast<const float2*>(gend + v));
     s_end[r * END_PITCH + c] = x.x; s_end[r * END_PITCH + c + 1] = x.y;
   }
+  // per-Gaussian operands of the pose, requested BEFORE the bulk SH copy: memory responses return roughly in issue order
+  // per SM, so a load queued behind the 24.5 KB tile waits for all of it (these two were 22 % of the stall samples)
+  const long long g = g0 + tid;
+  float4 o4 = make_float4(1.f, 0.f, 0.f, 0.f);
+  float sb0 = 1.f, sb1 = 1.f, sb2 = 1.f;
+  if (tid < rows) { o4 = ldg4(rot + 4 * g); sb0 = scale_backup[3 * g]; sb1 = scale_backup[3 * g + 1]; sb2 = scale_backup[3 * g + 2]; }
   __syncthreads();
   const float* gsh = shs + g0 * SH_FLOATS;
 #pragma unroll 12
@@ -407,12 +413,10 @@ k_fit_gaussians(long long N, const float* __restrict__ ends, const float* __rest
   }
   cp_async_commit();
 
-  const long long g = g0 + tid;
   const bool act = tid < rows && !s_static[tid];
   float Rs[3][3];
   if (act) {
     const float* e = s_end + tid * END_PITCH;
-    const float4 o4 = ldg4(rot + 4 * g);
     const Quat oq{o4.x, o4.y, o4.z, o4.w};
     float c[3];
 #pragma unroll
@@ -439,7 +443,7 @@ k_fit_gaussians(long long N, const float* __restrict__ ends, const float* __rest
     *reinterpret_cast<float4*>(rot + 4 * g) = make_float4(q.w, q.x, q.y, q.z);
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-      const float s0 = scale_backup[3 * g + i];
+      const float s0 = i == 0 ? sb0 : i == 1 ? sb1 : sb2;
       scale[3 * g + i] = K[i] / ((s0 + 1e-3f) * 2.0f) * s0;
       pos[3 * g + i] = c[i];
     }
@@ -531,7 +535,7 @@ template <int K>
 __global__ void __launch_bounds__(RS_TILE, 3)
 k_rotate_sample_shs(long long S, long long ntiles, int k, const float* __restrict__ w, const uint16_t* __restrict__ idx,
                     const float4* __restrict__ q_xyzw, const uint8_t* __restrict__ is_static,
-                    float* __restrict__ feature) {
+                    float* __restrict__ feature, int order) {
   // stage = [SH rows: RS_STAGE4 float4][weights: 128 K float][node ids: 128 K u16], all blocked like the global tables
   // K = compile-time bound of the neighbour count k (register arrays); k sets the table layout
   const int STAGE16 = RS_STAGE4 + k * 32 + k * 16;   // 16-byte units
@@ -563,18 +567,31 @@ k_rotate_sample_shs(long long S, long long ntiles, int k, const float* __restric
     const int rows = (int)min((long long)RS_TILE, S - s0);
     const bool stat = (is_static && tid < rows) ? is_static[s0 + tid] != 0 : false;
     const long long next = tile + gridDim.x;
-    if (next < ntiles) issue(next, stage ^ 1);
-    cp_async_commit();
-    cp_async_wait<1>();
+    if (!order) {
+      if (next < ntiles) issue(next, stage ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
     float4* st4 = s_tile + stage * STAGE16;
-    const bool live = tid < rows && !stat;
-    if (live) {
+    // The quaternion gathers go out BEFORE the next tile's 32 KB of bulk loads (order = 1): memory responses come back
+    // roughly in issue order per SM, so a gather queued behind the bulk loads waits for all of them (16 % of the stall
+    // samples sat on the first use of e[0]).
+    float4 e[K]; float cw[K];
+    if (tid < rows) {
       const float* sw = reinterpret_cast<const float*>(st4 + RS_STAGE4) + (tid >> 5) * (k * 32) + (tid & 31);
       const uint16_t* si = reinterpret_cast<const uint16_t*>(st4 + RS_STAGE4 + k * 32) + (tid >> 5) * (k * 32) + (tid & 31);
-      float4 e[K]; float cw[K];
 #pragma unroll
       for (int j = 0; j < K; j++) if (j < k) { e[j] = __ldg(q_xyzw + si[j * 32]); cw[j] = sw[j * 32]; }
+    }
+    if (order) {
+      if (next < ntiles) issue(next, stage ^ 1);
+      cp_async_commit();
+    }
+    const bool live = tid < rows && !stat;
+    if (live) {
       Quat wq{1.0f, 0.0f, 0.0f, 0.0f};
       float last = 0.0f;
 #pragma unroll
@@ -776,9 +793,11 @@ extern "C" int arapk_rotate_sample_shs(long long S, int k, const float* w, const
   }
   const unsigned nb = (unsigned)std::min<long long>(ntiles, (long long)sms * 3);
   const float4* q4 = (const float4*)q_xyzw;
-  if (k <= 8) k_rotate_sample_shs<8><<<nb, RS_TILE, smem, st>>>(S, ntiles, k, w, idx, q4, is_static, feature);
-  else if (k <= 10) k_rotate_sample_shs<10><<<nb, RS_TILE, smem, st>>>(S, ntiles, k, w, idx, q4, is_static, feature);
-  else k_rotate_sample_shs<12><<<nb, RS_TILE, smem, st>>>(S, ntiles, k, w, idx, q4, is_static, feature);
+  static int order = -1;   // ARAP_ROT_ORDER=0: bulk loads of the next tile issued before the gathers (first version)
+  if (order < 0) { const char* ev = getenv("ARAP_ROT_ORDER"); order = ev ? atoi(ev) : 1; }
+  if (k <= 8) k_rotate_sample_shs<8><<<nb, RS_TILE, smem, st>>>(S, ntiles, k, w, idx, q4, is_static, feature, order);
+  else if (k <= 10) k_rotate_sample_shs<10><<<nb, RS_TILE, smem, st>>>(S, ntiles, k, w, idx, q4, is_static, feature, order);
+  else k_rotate_sample_shs<12><<<nb, RS_TILE, smem, st>>>(S, ntiles, k, w, idx, q4, is_static, feature, order);
   ARAP_KERNEL_CHECK();
   return ARAP_OK;
 }
