@@ -14,6 +14,7 @@
 // Used when the per-CTA slice fits in shared memory (<= ~27k nodes at k = 10 on 148 SMs); otherwise solve.cu runs.
 #include <cooperative_groups.h>
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 #include "common.cuh"
 #include "kernels.h"
@@ -929,6 +930,7 @@ int launch_solve_smem(const SolveDev& S, unsigned* counter, cudaStream_t st) {
   ARAP_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   // small graphs: fewer CTAs (>= ~24 nodes each) make the barriers cheaper
   int grid = std::max(1, std::min(sms, (S.M + 23) / 24));
+  if (const char* ev = getenv("ARAP_SOLVE_GRID")) grid = std::max(1, std::min(sms, atoi(ev)));   // measurement aid
   const int NL = (S.M + grid - 1) / grid;
   void* kern = nullptr; size_t smem = 0;
   auto pick = [&](auto kc) {
