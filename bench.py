@@ -86,7 +86,7 @@ def ncu_traffic(workload, n, key):
     """dram__bytes_read + dram__bytes_write of the pass from the committed ncu --set full capture (profiles/), per launch;
     None when the run is not the captured configuration."""
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_summary_r01b.json")) as f:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_summary_r01c.json")) as f:
             d = json.load(f)
         return d[key] if d["workload"] == workload and d["gaussians"] == n else None
     except (OSError, KeyError, ValueError):
