@@ -299,7 +299,7 @@ def run_own(args):
                              "algorithmic_bytes_per_launch": sample_bytes, "ms_per_launch": round(sample_ms, 4)},
         "e2e": {"value": round(e2e_ms, 4), "unit": UNIT, "h2d_bytes_per_step": M * 12, "d2h_bytes_per_step": M * (12 + 72 + 24) + 64,
                 "what": "arap_aim_set(host aims) + arap_step + arap_download_nodes + arap_solve_stats_get per step"},
-        "gpu_launches": 11 * args.steps,
+        "gpu_launches": 10 * args.steps,   # per step: aim_translate, group_aims, solve, node_xf, 3 x lbs_tiles, fit, node_quats, rotate (profiles/launches_r01c.csv)
         "clocks": clk,
     }
     if world == 1 and not args.no_cpu_baseline:
