@@ -26,7 +26,7 @@ CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off"]
 
 CU = ["apply.cu", "knn.cu", "solve.cu", "solve_smem.cu", "grid.cu", "session.cu"]
 CPP = ["host_io.cpp"]
-HEADERS = ["common.cuh", "device_math.cuh", "sh_fast.cuh", "solve_dev.h", "kernels.h", "session.h", "../../include/arapgs.h"]
+HEADERS = ["common.cuh", "device_math.cuh", "sh_fast.cuh", "solve_dev.h", "kernels.h", "session.h", "../../include/arapgs.h", "../../include/arapgs_kernels.h"]
 
 
 def _stale(src: Path, obj: Path) -> bool:
