@@ -358,8 +358,9 @@ __device__ __forceinline__ void polar_newton(const double (&M)[3][3], double (&X
 }
 
 constexpr int FIT_TILE = 128;
-constexpr int SH_PITCH = 49;    // odd pitch: conflict-free per-thread rows
-constexpr int END_PITCH = 19;
+constexpr int FIT_PITCH4 = 13;  // float4 chunks per staged SH row
+constexpr int END_PITCH = 19;   // odd pitch: conflict-free per-thread rows
+
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -374,16 +375,19 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
 }
 
-// One 128-Gaussian tile per CTA.  The SH tile (24.5 KB) is fetched with 4-byte cp.async straight into its odd-pitch rows
-// and lands while the pose (centre, polar factor, quaternion, scale) is computed from the end points; waiting for it in
-// registers before doing anything else was 36 % of the kernel's stall samples.
-__global__ void __launch_bounds__(FIT_TILE, 6)
+// One 128-Gaussian tile per CTA.  The SH tile (24.5 KB) is fetched with 16-byte cp.async into rows at a 13-chunk pitch
+// (a thread's 12 LDS.128 / STS.128 on its own row are conflict-free, as in k_rotate_sample_shs) and lands while the pose
+// (centre, polar factor, quaternion, scale) is computed from the end points; waiting for it in registers before doing
+// anything else was 36 % of the kernel's stall samples.  The rotation itself runs on a register copy of the row.
+// (A first version copied the tile with 4-byte cp.async into odd-pitch rows for scalar access: that copy loop alone was
+// 25 % of the kernel's instructions.)
+template <int MINB>
+__global__ void __launch_bounds__(FIT_TILE, MINB)
 k_fit_gaussians(long long N, const float* __restrict__ ends, const float* __restrict__ scale_backup,
                 const uint8_t* __restrict__ is_static, float* __restrict__ pos, float* __restrict__ rot,
                 float* __restrict__ scale, float* __restrict__ shs) {
-  extern __shared__ float smem[];
-  float* s_sh = smem;                              // FIT_TILE x SH_PITCH
-  float* s_end = smem + FIT_TILE * SH_PITCH;       // FIT_TILE x END_PITCH
+  extern __shared__ float4 s_sh4[];                                        // FIT_TILE x FIT_PITCH4 float4
+  float* s_end = reinterpret_cast<float*>(s_sh4 + FIT_TILE * FIT_PITCH4);  // FIT_TILE x END_PITCH
   __shared__ uint8_t s_static[FIT_TILE];
 
   const long long g0 = (long long)blockIdx.x * FIT_TILE;
@@ -405,11 +409,11 @@ k_fit_gaussians(long long N, const float* __restrict__ ends, const float* __rest
   float sb0 = 1.f, sb1 = 1.f, sb2 = 1.f;
   if (tid < rows) { o4 = ldg4(rot + 4 * g); sb0 = scale_backup[3 * g]; sb1 = scale_backup[3 * g + 1]; sb2 = scale_backup[3 * g + 2]; }
   __syncthreads();
-  const float* gsh = shs + g0 * SH_FLOATS;
-#pragma unroll 12
-  for (int t = 0; t < SH_FLOATS; t++) {
-    const int v = tid + t * FIT_TILE, r = v / SH_FLOATS, c = v - r * SH_FLOATS;
-    if (r < rows && !s_static[r]) cp_async4(s_sh + r * SH_PITCH + c, gsh + v);
+  const float4* gsh = reinterpret_cast<const float4*>(shs + g0 * SH_FLOATS);
+#pragma unroll
+  for (int t = 0; t < 12; t++) {
+    const int v = tid + t * FIT_TILE, r = v / 12, c4 = v - r * 12;
+    if (r < rows && !s_static[r]) cp_async16(s_sh4 + r * FIT_PITCH4 + c4, gsh + v);
   }
   cp_async_commit();
 
@@ -452,14 +456,22 @@ k_fit_gaussians(long long N, const float* __restrict__ ends, const float* __rest
   }
   cp_async_wait<0>();
   __syncthreads();
-  if (act) sh_rotate_flipped_fast(Rs, s_sh + tid * SH_PITCH);
+  if (act) {
+    float4* row = s_sh4 + tid * FIT_PITCH4;
+    float v[SH_FLOATS];
+#pragma unroll
+    for (int c = 0; c < 12; c++) { const float4 x = row[c]; v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w; }
+    sh_rotate_flipped_fast(Rs, v);
+#pragma unroll
+    for (int c = 1; c < 12; c++) row[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    row[0].w = v[3];   // DC term (floats 0-2) is rotation invariant
+  }
   __syncthreads();
   float* osh = shs + g0 * SH_FLOATS;
-  for (int v = tid; v < rows * 12; v += FIT_TILE) {
-    const int r = v / 12, c4 = v - r * 12;
-    if (s_static[r]) continue;
-    const float* d = s_sh + r * SH_PITCH + c4 * 4;
-    st_stream4(osh + (size_t)v * 4, make_float4(d[0], d[1], d[2], d[3]));
+#pragma unroll
+  for (int t = 0; t < 12; t++) {
+    const int v = tid + t * FIT_TILE, r = v / 12, c4 = v - r * 12;
+    if (r < rows && !s_static[r]) st_stream4(osh + (size_t)v * 4, s_sh4[r * FIT_PITCH4 + c4]);
   }
 }
 
@@ -762,9 +774,20 @@ extern "C" int arapk_fit_gaussians(long long N, const float* ends, const float* 
                                    float* pos, float* rot, float* scale, float* shs, cudaStream_t st) {
   if (N <= 0) return ARAP_OK;
   int rc = ensure_sh_tables(); if (rc) return rc;
-  const size_t smem = sizeof(float) * FIT_TILE * (SH_PITCH + END_PITCH);
-  k_fit_gaussians<<<(unsigned)((N + FIT_TILE - 1) / FIT_TILE), FIT_TILE, smem, st>>>(N, ends, scale_backup, is_static, pos, rot,
-                                                                                     scale, shs);
+  const size_t smem = sizeof(float4) * FIT_TILE * FIT_PITCH4 + sizeof(float) * FIT_TILE * END_PITCH;
+  // resident CTAs per SM the register allocation is tuned for: 4 (128 registers, no spills; default), 5 or 6
+  static int minb = 0;
+  if (!minb) {
+    const char* ev = getenv("ARAP_FIT_CTAS"); minb = ev ? atoi(ev) : 4;
+    if (minb < 4 || minb > 6) minb = 4;
+    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_fit_gaussians<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_fit_gaussians<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_fit_gaussians<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  const unsigned grid = (unsigned)((N + FIT_TILE - 1) / FIT_TILE);
+  if (minb == 4) k_fit_gaussians<4><<<grid, FIT_TILE, smem, st>>>(N, ends, scale_backup, is_static, pos, rot, scale, shs);
+  else if (minb == 5) k_fit_gaussians<5><<<grid, FIT_TILE, smem, st>>>(N, ends, scale_backup, is_static, pos, rot, scale, shs);
+  else k_fit_gaussians<6><<<grid, FIT_TILE, smem, st>>>(N, ends, scale_backup, is_static, pos, rot, scale, shs);
   ARAP_KERNEL_CHECK();
   return ARAP_OK;
 }
