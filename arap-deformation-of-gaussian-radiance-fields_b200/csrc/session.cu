@@ -197,7 +197,7 @@ extern "C" int arap_default_params(arap_params* p) {
   if (!p) return ARAP_ERR_INVALID;
   p->grid_num = 64; p->padding = 1; p->knn_k = 10; p->node_num = 150; p->high_quality = 0; p->lpf_parameter = 0.2f;
   p->w_rot = 1.0; p->w_reg = 10.0; p->w_con = 100.0; p->max_gn_iters = 30; p->max_cg_iters = 4000; p->cg_tol = 1e-10;
-  p->skip_static_endpoints = 0; p->solver_global_memory = 0; p->lbs_mode = 0; p->newton_eta0 = 1e-6; p->warm_start = 1;
+  p->skip_static_endpoints = 0; p->solver_global_memory = 0; p->lbs_mode = 0; p->newton_eta0 = 1e-6; p->warm_start = 1; p->solver_ctas = 0;
   return ARAP_OK;
 }
 
@@ -759,7 +759,7 @@ extern "C" int arap_solve(arap_ctx* ctx, int on_center) {
   G.grp_off = cs.grp_off.p; G.grp_member = cs.grp_member.p; G.grp_aim = cs.grp_aim.p;
   G.cin_off = cs.cin_off.p; G.cin_grp = cs.cin_grp.p; G.cin_member = cs.cin_member.p; G.cin_slot = cs.cin_slot.p; G.n_cin_entries = cs.n_entries;
   ArapSolveParams P{ctx->prm.w_rot, ctx->prm.w_reg, ctx->prm.w_con, ctx->prm.max_gn_iters, ctx->prm.max_cg_iters, ctx->prm.cg_tol, ctx->prm.solver_global_memory, ctx->prm.newton_eta0,
-                    ctx->prm.warm_start ? ctx->warm_d.p : nullptr, ctx->prm.warm_start > 1 ? ctx->prm.warm_start - 1 : 0};
+                    ctx->prm.warm_start ? ctx->warm_d.p : nullptr, ctx->prm.solver_ctas, ctx->prm.warm_start > 1 ? ctx->prm.warm_start - 1 : 0};
   TRY(ctx->solve_ws.alloc(arapk_solve_workspace_bytes(G.M, G.k, G.n_groups)));
   TRY(arapk_solve(&G, &P, ctx->solve_ws.p, ctx->solve_ws.n, ctx->rot_d.p, ctx->trans_d.p, ctx->stats_d.p, st));
   ctx->solved = true;

@@ -507,7 +507,7 @@ extern "C" int arapk_solve(const ArapSolveGraph* G, const ArapSolveParams* P, vo
   S.warm = P->warm_buf;
   S.warm_systems = P->warm_systems > 0 ? std::min(P->warm_systems, SOLVE_WARM_MAX) : SOLVE_WARM_MAX;
   if (!P->force_global_kernel) {   // fast path: per-node state resident in shared memory (solve_smem.cu)
-    const int rc = launch_solve_smem(S, reinterpret_cast<unsigned*>(S.partial), st);   // barrier slots live in the partials area (2 x 148 x 64 B)
+    const int rc = launch_solve_smem(S, reinterpret_cast<unsigned*>(S.partial), st, P->max_ctas);   // barrier slots live in the partials area (2 x 148 x 64 B)
     if (rc >= 0) return rc;
   }
   int dev = 0, sms = 0, per_sm = 0;

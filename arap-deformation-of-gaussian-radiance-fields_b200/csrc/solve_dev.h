@@ -43,6 +43,6 @@ constexpr int SOLVE_WARM_MAX = 4;
 
 // solve_smem.cu: returns ARAP_OK if launched, a positive error code on CUDA failure, -1 if the per-CTA slice does not
 // fit in shared memory (the caller then runs the global-memory kernel).
-int launch_solve_smem(const SolveDev& S, unsigned* counter, cudaStream_t st);
+int launch_solve_smem(const SolveDev& S, unsigned* counter, cudaStream_t st, int max_ctas);
 
 }  // namespace arapgs

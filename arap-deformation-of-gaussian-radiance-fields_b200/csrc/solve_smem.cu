@@ -601,8 +601,9 @@ __device__ __noinline__ void barrier_skew(unsigned* counter, int ph, unsigned lo
 // Slice capacities are compile-time (NL nodes per CTA, GCAP / CCAP constraint-table entries): every shared-memory
 // array then sits at a constant address and the address arithmetic that made up ~12% of the instructions disappears.
 template <int K, int NL> struct SmCaps {
-  static constexpr int G = NL <= 112 ? (K <= 10 ? 768 : 640) : (K <= 10 ? 192 : 0);
-  static constexpr int C = NL <= 112 ? (K <= 10 ? 1280 : 1024) : (K <= 10 ? 320 : 0);
+  // NL = 136: the slice of a solve that leaves ~30 SMs to a concurrent kernel (arap_params.solver_ctas) at 16k nodes
+  static constexpr int G = NL <= 112 ? (K <= 10 ? 768 : 640) : NL <= 136 ? (K <= 10 ? 512 : 384) : (K <= 10 ? 192 : 0);
+  static constexpr int C = NL <= 112 ? (K <= 10 ? 1280 : 1024) : NL <= 136 ? (K <= 10 ? 768 : 640) : (K <= 10 ? 320 : 0);
 };
 template <int K, int NL>
 __global__ void __launch_bounds__(SM_THREADS, 1) k_solve_smem(SolveDev S, unsigned* counter) {
@@ -922,7 +923,7 @@ size_t solve_smem_bytes(int NL, int K, int gcap, int ccap) {
 }
 
 // returns ARAP_OK if launched, -1 if the slice does not fit (caller falls back to the global-memory kernel)
-int launch_solve_smem(const SolveDev& S, unsigned* counter, cudaStream_t st) {
+int launch_solve_smem(const SolveDev& S, unsigned* counter, cudaStream_t st, int max_ctas) {
   if (S.k != 8 && S.k != 10 && S.k != 12) return -1;
   int dev = 0, sms = 0, max_smem = 0;
   ARAP_CUDA_TRY(cudaGetDevice(&dev));
@@ -930,12 +931,14 @@ int launch_solve_smem(const SolveDev& S, unsigned* counter, cudaStream_t st) {
   ARAP_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   // small graphs: fewer CTAs (>= ~24 nodes each) make the barriers cheaper
   int grid = std::max(1, std::min(sms, (S.M + 23) / 24));
+  if (max_ctas > 0) grid = std::min(grid, max_ctas);   // SMs left to concurrent kernels (arap_params.solver_ctas)
   if (const char* ev = getenv("ARAP_SOLVE_GRID")) grid = std::max(1, std::min(sms, atoi(ev)));   // measurement aid
   const int NL = (S.M + grid - 1) / grid;
   void* kern = nullptr; size_t smem = 0;
   auto pick = [&](auto kc) {
     constexpr int KK = decltype(kc)::value;
     if (NL <= 112) { kern = (void*)k_solve_smem<KK, 112>; smem = solve_smem_bytes(112, KK, SmCaps<KK, 112>::G, SmCaps<KK, 112>::C); }
+    else if (NL <= 136) { kern = (void*)k_solve_smem<KK, 136>; smem = solve_smem_bytes(136, KK, SmCaps<KK, 136>::G, SmCaps<KK, 136>::C); }
     else if (NL <= 176) { kern = (void*)k_solve_smem<KK, 176>; smem = solve_smem_bytes(176, KK, SmCaps<KK, 176>::G, SmCaps<KK, 176>::C); }
   };
   if (S.k == 8) pick(std::integral_constant<int, 8>{});

@@ -131,6 +131,12 @@ def run_own(args):
     torch.cuda.set_device(local)
     if world > 1:
         opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)   # the gather must get its few CTAs ahead of the SH pass
+        # The solve is a cooperative kernel whose 512-thread CTAs fill an SM each: with one CTA per SM the all-gather of the
+        # previous step cannot run beside it and serialises with it (8 GPUs: 9.7 GB per rank per step).  Reserve SMs:
+        # NCCL is capped at NCCL_CTAS channels and the solve runs on the remaining SMs (arap_params.solver_ctas).
+        nccl_ctas = int(os.environ.get("ARAP_NCCL_CTAS", "24"))
+        if nccl_ctas > 0:
+            opts.config.max_ctas = nccl_ctas
         dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
     pkg = ge.load_package()
     scenes = importlib.import_module(ge.PKG + ".scenes")
@@ -143,6 +149,9 @@ def run_own(args):
     assert stream != 0
     s, sc, gi, setup = setup_session(pkg, scenes, args.workload, n, rank, world, stream)
     M, k, N, S = s.M, cfg["k"], s.N, gi["samples"]
+    if world > 1 and int(os.environ.get("ARAP_NCCL_CTAS", "24")) > 0:
+        sms = torch.cuda.get_device_properties(local).multi_processor_count
+        s.set_params(solver_ctas=sms - int(os.environ.get("ARAP_NCCL_CTAS", "24")))
     if args.newton_eta0 is not None:
         s.set_params(newton_eta0=args.newton_eta0)
     if args.max_cg is not None:
@@ -195,7 +204,7 @@ def run_own(args):
     # plus --set).  --variants "lbs_mode=1;lbs_mode=2,warm_start=0"
     def parse(spec):
         return {kv.split("=")[0]: (float(kv.split("=")[1]) if "." in kv or "e" in kv.split("=")[1] else int(kv.split("=")[1])) for kv in spec.split(",") if kv}
-    base = {kk: getattr(s.params, kk) for kk in ("lbs_mode", "warm_start", "newton_eta0")}
+    base = {kk: getattr(s.params, kk) for kk in ("lbs_mode", "warm_start", "newton_eta0", "solver_ctas")}
     for spec in [v for v in args.variants.split(";") if v]:
         s.set_params(**{**base, **parse(spec)})
         for _ in range(3):

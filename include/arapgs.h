@@ -68,6 +68,9 @@ typedef struct arap_params {
                           Gauss-Newton system (zero after arap_set_blocks / a graph build).  Same stopping rule, same answer to the
                           solver tolerance, fewer iterations while the drag is coherent.  0 = start from zero like the first step;
                           n > 1 = warm-start only the first n - 1 systems of a step. */
+  int solver_ctas;     /* 0 (default): the solve uses one CTA per SM.  n > 0: at most n CTAs, leaving the other SMs to kernels that run
+                          beside it — the multi-GPU driver reserves SMs for the NCCL all-gather of the previous step's SoA, which
+                          otherwise cannot overlap the solve (a 512-thread solver CTA fills an SM's register file). */
 } arap_params;
 
 typedef struct arap_solve_stats {

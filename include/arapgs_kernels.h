@@ -89,6 +89,7 @@ typedef struct ArapSolveParams {
   double newton_eta0;          // > 0: inexact Newton forcing (shared-memory kernel only), see arapgs.h
   double* warm_buf;            // device, arapk_solve_warm_doubles(M) doubles, zeroed by the caller whenever the unknown set changes;
                                // null = every PCG solve starts from 0.  See arapgs.h (arap_params.warm_start).
+  int max_ctas;                // 0 = one CTA per SM; n > 0 = at most n CTAs (shared-memory kernel)
   int warm_systems;            // 0 = all (SOLVE_WARM_MAX), n > 0 = only the first n Gauss-Newton systems of a step
 } ArapSolveParams;
 

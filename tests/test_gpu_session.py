@@ -142,6 +142,35 @@ def test_warm_start_and_lbs_kernels_agree(pkg, scenes):
     assert all(np.array_equal(outs[0][k], outs[2][k]) for k in outs[0])   # the two staged-record variants: identical bits
 
 
+def test_solver_on_fewer_ctas_agrees(pkg, scenes):
+    """arap_params.solver_ctas leaves SMs to a concurrent kernel (the multi-GPU all-gather): the solve then runs with more
+    nodes per CTA (the NL = 136 / 176 slices of the shared-memory kernel).  Same transforms to the solver tolerance."""
+    sc = scenes.make_scene("sphere1m", n=60000)
+    res = []
+    for ctas in (0, 24, 18):          # 3000 nodes: 21, 125 (NL = 136 slice) and 167 (NL = 176 slice) nodes per CTA
+        s = pkg.Session(device=0, grid_num=32, knn_k=10, node_num=3000)
+        s.set_params(solver_ctas=ctas)
+        s.set_gaussians(sc["pos"], sc["rot"], sc["scale"], sc["opacity"], sc["shs"])
+        s.grid_build()
+        g = s.graph_build_fps()
+        blocks, types = scenes.cap_blocks(g["node_pos"], lo=-0.3, hi=0.3)
+        s.set_blocks(blocks, types)
+        out = []
+        for step in range(2):
+            s.aim_translate([0.002, 0.0, 0.01])
+            s.solve(False)
+            st = s.solve_stats()
+            assert st["flags"] == 0 and st["grid_blocks"] == (ctas if ctas else min(148, (3000 + 23) // 24))
+            out.append((st["gn_iters"], s.download_nodes()[1:]))
+            s.apply()
+        res.append(out)
+        s.close()
+    for other in res[1:]:
+        for (gn0, (r0, t0)), (gn1, (r1, t1)) in zip(res[0], other):
+            assert gn0 == gn1
+            assert np.abs(r0 - r1).max() <= 2e-9 and np.abs(t0 - t1).max() <= 2e-9
+
+
 def test_twist_scale_and_excluded_blocks(pkg, scenes):
     sc, s, o, gi, og = _pair(pkg, scenes, n=20000, grid_num=32, knn_k=10, node_num=120)
     g = s.graph_build_fps(); o.graph_build_fps()
