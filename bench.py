@@ -129,12 +129,15 @@ def run_own(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
+    nccl_ctas = 0
     if world > 1:
         opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)   # the gather must get its few CTAs ahead of the SH pass
         # The solve is a cooperative kernel whose 512-thread CTAs fill an SM each: with one CTA per SM the all-gather of the
         # previous step cannot run beside it and serialises with it (8 GPUs: 9.7 GB per rank per step).  Reserve SMs:
         # NCCL is capped at NCCL_CTAS channels and the solve runs on the remaining SMs (arap_params.solver_ctas).
-        nccl_ctas = int(os.environ.get("ARAP_NCCL_CTAS", "24"))
+        # Measured on 8 GPUs (48M Gaussians): 27.9 -> 26.7 ms per step; at 2 GPUs the gather already hides behind the sample
+        # passes and the reservation would only slow the solve (4.06 -> 4.60 ms on 124 CTAs), so it is on from 8 ranks up.
+        nccl_ctas = int(os.environ.get("ARAP_NCCL_CTAS", "24" if world >= 8 else "0"))
         if nccl_ctas > 0:
             opts.config.max_ctas = nccl_ctas
         dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
@@ -149,9 +152,9 @@ def run_own(args):
     assert stream != 0
     s, sc, gi, setup = setup_session(pkg, scenes, args.workload, n, rank, world, stream)
     M, k, N, S = s.M, cfg["k"], s.N, gi["samples"]
-    if world > 1 and int(os.environ.get("ARAP_NCCL_CTAS", "24")) > 0:
+    if world > 1 and nccl_ctas > 0:
         sms = torch.cuda.get_device_properties(local).multi_processor_count
-        s.set_params(solver_ctas=sms - int(os.environ.get("ARAP_NCCL_CTAS", "24")))
+        s.set_params(solver_ctas=sms - nccl_ctas)
     if args.newton_eta0 is not None:
         s.set_params(newton_eta0=args.newton_eta0)
     if args.max_cg is not None:
