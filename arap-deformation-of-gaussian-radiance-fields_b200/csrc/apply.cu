@@ -118,20 +118,21 @@ k_lbs_points(const float* __restrict__ in, float* __restrict__ out, long long P,
 // per record per tile) and every (row, neighbour) pair reads its record from there through a one-byte slot number.
 // That replaces ten 112-byte L1 gathers per row (the global-memory kernel sits at 83-95 % l1tex throughput with
 // DRAM at 25-34 %) by shared-memory reads that mostly broadcast, and the id table shrinks from 2 to 1.2 bytes per pair.
-// Staged records sit at a 144-byte pitch: bank group of 16-byte part p of slot s is (s + p) mod 8.
+// Staged records sit at a 112-byte pitch: bank group of 16-byte part p of slot s is (p - s) mod 8.
 // A tile with more than `cap` distinct nodes has cnt = 0 and takes the global-memory path (same arithmetic).
 constexpr int LT_ROWS = 128;
 constexpr int LT_CAP = 96;
-constexpr int LT_PITCH = 9;   // 16-byte units per staged record (7 used)
+constexpr int LT_PITCH = 7;   // 16-byte units per staged record (6 used): bank group of part p of slot s = (p - s) mod 8
 constexpr int LT_WORDS = 3;   // slot words per row: 12 one-byte slots
 
 template <int K, bool MAGIC>
-__global__ void __launch_bounds__(LT_ROWS)
+__global__ void __launch_bounds__(LT_ROWS, 8)   // 64 registers: 8 CTAs per SM (72 registers / 7 CTAs measured 3 % slower on the samples)
 k_lbs_tiles(const float* __restrict__ in, float* __restrict__ out, long long P, int k_rt, const uint32_t* __restrict__ slots,
             const double* __restrict__ rw, const uint16_t* __restrict__ ridx, const uint16_t* __restrict__ tile_cnt,
             const uint16_t* __restrict__ tile_nodes, const NodeXf* __restrict__ nodes, const uint8_t* __restrict__ skip,
             int group) {
-  __shared__ double2 s_rec[LT_CAP * LT_PITCH];
+  __shared__ double2 s_rec[LT_CAP * LT_PITCH];   // A (9 doubles) and c (3 doubles) of every staged node
+  __shared__ float s_g[3 * LT_CAP];               // node positions, one array per component
   const int tid = threadIdx.x;
   const long long tile = blockIdx.x;
   const long long i = tile * LT_ROWS + tid;
@@ -145,7 +146,12 @@ k_lbs_tiles(const float* __restrict__ in, float* __restrict__ out, long long P, 
   const uint16_t* tn = tile_nodes + tile * LT_CAP;
   for (int v = tid; v < cnt * 7; v += LT_ROWS) {
     const int r = v / 7, part = v - r * 7;
-    s_rec[r * LT_PITCH + part] = __ldg(reinterpret_cast<const double2*>(nodes + tn[r]) + part);
+    const double2 x = __ldg(reinterpret_cast<const double2*>(nodes + tn[r]) + part);
+    if (part < 6) s_rec[r * LT_PITCH + part] = x;
+    else {
+      const float4 g = *reinterpret_cast<const float4*>(&x);
+      s_g[r] = g.x; s_g[LT_CAP + r] = g.y; s_g[2 * LT_CAP + r] = g.z;
+    }
   }
   // this row's streamed operands, all in flight before the barrier
   float c0 = 0.f, c1 = 0.f, c2 = 0.f;
@@ -169,8 +175,9 @@ k_lbs_tiles(const float* __restrict__ in, float* __restrict__ out, long long P, 
     const unsigned slot = (sw[j >> 2] >> ((j & 3) * 8)) & 0xffu;
     const double2* n = s_rec + slot * LT_PITCH;
     const double2 a01 = n[0], a23 = n[1], a45 = n[2], a67 = n[3], a8c0 = n[4], c12 = n[5];
-    const float4 g = *reinterpret_cast<const float4*>(n + 6);
-    lbs_neighbour<MAGIC>(c0, c1, c2, w[j], a01, a23, a45, a67, a8c0, c12, g, o);
+    // node position from three float arrays: 3 one-wavefront LDS.32 (conflict-free: bank = slot) instead of a fourth
+    // wavefront for 4 bytes of padding in an LDS.128 — the kernel is bound by exactly these wavefronts
+    lbs_neighbour<MAGIC>(c0, c1, c2, w[j], a01, a23, a45, a67, a8c0, c12, make_float4(s_g[slot], s_g[LT_CAP + slot], s_g[2 * LT_CAP + slot], 0.f), o);
   }
   out[3 * i] = (float)o.d0; out[3 * i + 1] = (float)o.d1; out[3 * i + 2] = (float)o.d2;
 }
@@ -179,7 +186,7 @@ k_lbs_tiles(const float* __restrict__ in, float* __restrict__ out, long long P, 
 // the tile touches, ranked by a popcount prefix.
 // Slot numbers are then chosen to avoid shared-memory bank conflicts in k_lbs_tiles: an LDS.128 is served one
 // quarter-warp (8 consecutive rows) at a time, and two records conflict there iff their slots are congruent mod 8
-// (144-byte pitch).  Nodes that are read by the same quarter-warp for the same neighbour position j are joined in a
+// (112-byte pitch).  Nodes that are read by the same quarter-warp for the same neighbour position j are joined in a
 // graph weighted by how often that happens, every node takes the colour (of 8) that costs the fewest conflicts with the
 // nodes placed before it, and slot = colour + 8 * (index within the colour).  Measured on the 6M-Gaussian workload: 5.8 -> ~4 wavefronts per LDS.128 for the end-point rows.
 // tile_cnt = number of slots to stage (highest slot + 1; unused slots repeat a node of the tile), 0 = too many nodes.
