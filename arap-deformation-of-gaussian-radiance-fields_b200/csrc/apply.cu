@@ -377,19 +377,13 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
-}
-
 // One 128-Gaussian tile per CTA.  The SH tile (24.5 KB) is fetched with 16-byte cp.async into rows at a 13-chunk pitch
 // (a thread's 12 LDS.128 / STS.128 on its own row are conflict-free, as in k_rotate_sample_shs) and lands while the pose
 // (centre, polar factor, quaternion, scale) is computed from the end points; waiting for it in registers before doing
 // anything else was 36 % of the kernel's stall samples.  The rotation itself runs on a register copy of the row.
 // (A first version copied the tile with 4-byte cp.async into odd-pitch rows for scalar access: that copy loop alone was
 // 25 % of the kernel's instructions.)
-template <int MINB>
-__global__ void __launch_bounds__(FIT_TILE, MINB)
+__global__ void __launch_bounds__(FIT_TILE, 4)   // 128 registers, no spills (5 / 6 CTAs per SM spill and measured no faster)
 k_fit_gaussians(long long N, const float* __restrict__ ends, const float* __restrict__ scale_backup,
                 const uint8_t* __restrict__ is_static, float* __restrict__ pos, float* __restrict__ rot,
                 float* __restrict__ scale, float* __restrict__ shs) {
@@ -782,19 +776,12 @@ extern "C" int arapk_fit_gaussians(long long N, const float* ends, const float* 
   if (N <= 0) return ARAP_OK;
   int rc = ensure_sh_tables(); if (rc) return rc;
   const size_t smem = sizeof(float4) * FIT_TILE * FIT_PITCH4 + sizeof(float) * FIT_TILE * END_PITCH;
-  // resident CTAs per SM the register allocation is tuned for: 4 (128 registers, no spills; default), 5 or 6
-  static int minb = 0;
-  if (!minb) {
-    const char* ev = getenv("ARAP_FIT_CTAS"); minb = ev ? atoi(ev) : 4;
-    if (minb < 4 || minb > 6) minb = 4;
-    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_fit_gaussians<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_fit_gaussians<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_fit_gaussians<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static bool attr_set = false;
+  if (!attr_set) {
+    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_fit_gaussians, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
   }
-  const unsigned grid = (unsigned)((N + FIT_TILE - 1) / FIT_TILE);
-  if (minb == 4) k_fit_gaussians<4><<<grid, FIT_TILE, smem, st>>>(N, ends, scale_backup, is_static, pos, rot, scale, shs);
-  else if (minb == 5) k_fit_gaussians<5><<<grid, FIT_TILE, smem, st>>>(N, ends, scale_backup, is_static, pos, rot, scale, shs);
-  else k_fit_gaussians<6><<<grid, FIT_TILE, smem, st>>>(N, ends, scale_backup, is_static, pos, rot, scale, shs);
+  k_fit_gaussians<<<(unsigned)((N + FIT_TILE - 1) / FIT_TILE), FIT_TILE, smem, st>>>(N, ends, scale_backup, is_static, pos, rot, scale, shs);
   ARAP_KERNEL_CHECK();
   return ARAP_OK;
 }
