@@ -65,7 +65,7 @@ typedef struct arap_params {
                           length); measured node-transform deviation from the reference's direct solves stays at the 1e-11 level
                           of the cg_tol-only rule with ~25% fewer PCG iterations (1e-4 is where the parity bar is reached). */
   int warm_start;      /* 1 (default): every PCG solve of a drag step starts from the solution the previous step found for the same
-                          Gauss-Newton system (zero after arap_set_blocks / a graph build).  Same stopping rule, same answer to the
+                          Gauss-Newton system, scaled by an exact line search (zero after arap_set_blocks / a graph build).  Same stopping rule, same answer to the
                           solver tolerance, fewer iterations while the drag is coherent.  0 = start from zero like the first step;
                           n > 1 = warm-start only the first n - 1 systems of a step. */
   int solver_ctas;     /* 0 (default): the solve uses one CTA per SM.  n > 0: at most n CTAs, leaving the other SMs to kernels that run
