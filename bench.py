@@ -86,7 +86,7 @@ def ncu_traffic(workload, n, key):
     """dram__bytes_read + dram__bytes_write of the pass from the committed ncu --set full capture (profiles/), per launch;
     None when the run is not the captured configuration."""
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_summary_r01c.json")) as f:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_summary_r01d.json")) as f:
             d = json.load(f)
         return d[key] if d["workload"] == workload and d["gaussians"] == n else None
     except (OSError, KeyError, ValueError):
@@ -311,7 +311,7 @@ def run_own(args):
                              "algorithmic_bytes_per_launch": sample_bytes, "ms_per_launch": round(sample_ms, 4)},
         "e2e": {"value": round(e2e_ms, 4), "unit": UNIT, "h2d_bytes_per_step": M * 12, "d2h_bytes_per_step": M * (12 + 72 + 24) + 64,
                 "what": "arap_aim_set(host aims) + arap_step + arap_download_nodes + arap_solve_stats_get per step"},
-        "gpu_launches": 10 * args.steps,   # per step: aim_translate, group_aims, solve, node_xf, 3 x lbs_tiles, fit, node_quats, rotate (profiles/launches_r01c.csv)
+        "gpu_launches": 10 * args.steps,   # per step: aim_translate, group_aims, solve, node_xf, 3 x lbs_tiles, fit, node_quats, rotate (profiles/launches_r01d.csv)
         "clocks": clk,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -3,7 +3,7 @@
 set -x
 mkdir -p gpurun_out
 W=${1:-shells6m}
-TAG=${2:-r01c}
+TAG=${2:-r01d}
 # (1) every launch of a short bench run with its device time (cold-cache, serialised: compare SHARES)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --workload $W --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/launches_$TAG.log 2>&1
