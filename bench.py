@@ -135,9 +135,10 @@ def run_own(args):
         # The solve is a cooperative kernel whose 512-thread CTAs fill an SM each: with one CTA per SM the all-gather of the
         # previous step cannot run beside it and serialises with it (8 GPUs: 9.7 GB per rank per step).  Reserve SMs:
         # NCCL is capped at NCCL_CTAS channels and the solve runs on the remaining SMs (arap_params.solver_ctas).
-        # Measured on 8 GPUs (48M Gaussians): 27.9 -> 26.7 ms per step; at 2 GPUs the gather already hides behind the sample
-        # passes and the reservation would only slow the solve (4.06 -> 4.60 ms on 124 CTAs), so it is on from 8 ranks up.
-        nccl_ctas = int(os.environ.get("ARAP_NCCL_CTAS", "24" if world >= 8 else "0"))
+        # Measured (ms per step, without -> with): 8 GPUs 27.9 -> 26.7, 4 GPUs 19.7 -> 18.1; at 2 GPUs the gather already hides
+        # behind the sample passes and the reservation only slows the solve and stretches the gather (14.8 -> 16.2), so it is
+        # on from 4 ranks up.
+        nccl_ctas = int(os.environ.get("ARAP_NCCL_CTAS", "24" if world >= 4 else "0"))
         if nccl_ctas > 0:
             opts.config.max_ctas = nccl_ctas
         dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
