@@ -411,10 +411,13 @@ k_fit_gaussians(long long N, const float* __restrict__ ends, const float* __rest
   if (tid < rows) { o4 = ldg4(rot + 4 * g); sb0 = scale_backup[3 * g]; sb1 = scale_backup[3 * g + 1]; sb2 = scale_backup[3 * g + 2]; }
   __syncthreads();
   const float4* gsh = reinterpret_cast<const float4*>(shs + g0 * SH_FLOATS);
+  const int cp_r0 = tid / 12, cp_c4 = tid - 12 * cp_r0;   // 120 threads x 13 passes of 10 rows: loop-invariant row / chunk
+  if (tid < 120) {
 #pragma unroll
-  for (int t = 0; t < 12; t++) {
-    const int v = tid + t * FIT_TILE, r = v / 12, c4 = v - r * 12;
-    if (r < rows && !s_static[r]) cp_async16(s_sh4 + r * FIT_PITCH4 + c4, gsh + v);
+    for (int t = 0; t < 13; t++) {
+      const int r = cp_r0 + 10 * t;
+      if (r < rows && !s_static[r]) cp_async16(s_sh4 + r * FIT_PITCH4 + cp_c4, gsh + tid + 120 * t);
+    }
   }
   cp_async_commit();
 
@@ -469,10 +472,12 @@ k_fit_gaussians(long long N, const float* __restrict__ ends, const float* __rest
   }
   __syncthreads();
   float* osh = shs + g0 * SH_FLOATS;
+  if (tid < 120) {
 #pragma unroll
-  for (int t = 0; t < 12; t++) {
-    const int v = tid + t * FIT_TILE, r = v / 12, c4 = v - r * 12;
-    if (r < rows && !s_static[r]) st_stream4(osh + (size_t)v * 4, s_sh4[r * FIT_PITCH4 + c4]);
+    for (int t = 0; t < 13; t++) {
+      const int r = cp_r0 + 10 * t;
+      if (r < rows && !s_static[r]) st_stream4(osh + (size_t)(tid + 120 * t) * 4, s_sh4[r * FIT_PITCH4 + cp_c4]);
+    }
   }
 }
 
@@ -554,16 +559,20 @@ k_rotate_sample_shs(long long S, long long ntiles, int k, const float* __restric
   const int STAGE16 = RS_STAGE4 + k * 32 + k * 16;   // 16-byte units
   extern __shared__ float4 s_tile[];
   const int tid = threadIdx.x;
+  const int cp_r0 = tid / 12, cp_c4 = tid - 12 * cp_r0;   // this thread's row (mod 10) and chunk in the tile copy loops
   auto issue = [&](long long tile, int stage) {
     const long long s0 = tile * RS_TILE;
     const int rows = (int)min((long long)RS_TILE, S - s0);
     const float4* g = reinterpret_cast<const float4*>(feature + s0 * SH_FLOATS);
     float4* d = s_tile + stage * STAGE16;
+    // 120 threads copy 10 rows x 12 chunks per pass: row and chunk of a thread are loop-invariant, every address is
+    // base + compile-time constant (the v / 12 form cost ~8 instructions per copy, this one 2)
+    if (tid < 120) {
+      const float4* gs = g + tid;
+      float4* ds = d + cp_r0 * RS_PITCH4 + cp_c4;
 #pragma unroll
-    for (int i = 0; i < 12; i++) {
-      const int v = tid + i * RS_TILE;
-      const int r = v / 12, c4 = v - r * 12;
-      if (r < rows) cp_async16(d + r * RS_PITCH4 + c4, g + v);
+      for (int i = 0; i < 13; i++)
+        if (cp_r0 + 10 * i < rows) cp_async16(ds + i * 10 * RS_PITCH4, gs + i * 120);
     }
     const int nblk = (rows + 31) >> 5;
     const float4* gw = reinterpret_cast<const float4*>(w + (s0 >> 5) * (long long)(k * 32));
@@ -640,11 +649,12 @@ k_rotate_sample_shs(long long S, long long ntiles, int k, const float* __restric
     }
     __syncthreads();
     float4* o = reinterpret_cast<float4*>(feature + s0 * SH_FLOATS);
+    if (tid < 120) {
+      float4* os = o + tid;
+      const float4* ss = st4 + cp_r0 * RS_PITCH4 + cp_c4;
 #pragma unroll
-    for (int i = 0; i < 12; i++) {
-      const int vv = tid + i * RS_TILE;
-      const int r = vv / 12, c4 = vv - r * 12;
-      if (r < rows) st_stream4(reinterpret_cast<float*>(o + vv), st4[r * RS_PITCH4 + c4]);
+      for (int i = 0; i < 13; i++)
+        if (cp_r0 + 10 * i < rows) st_stream4(reinterpret_cast<float*>(os + i * 120), ss[i * 10 * RS_PITCH4]);
     }
     __syncthreads();
   }
