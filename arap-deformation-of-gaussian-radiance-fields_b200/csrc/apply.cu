@@ -481,6 +481,64 @@ k_fit_gaussians(long long N, const float* __restrict__ ends, const float* __rest
   }
 }
 
+// ------------------------------------------------------------------ SH replay (multi-GPU receivers)
+// A receiver of another rank's deformed Gaussians does not need their SH rows (192 of the 232 bytes per Gaussian): it holds
+// last step's rows and rotations, receives the new rotations, and repeats the owner's SH update
+//   R_sh = (q_new * q_old^-1).normalized -> sh_rotate_flipped_fast                      (k_fit_gaussians, GV:3138-3154)
+// with the same inline arithmetic on the same float inputs, so its copy stays bit-identical to the owner's.
+__global__ void __launch_bounds__(FIT_TILE, 4)
+k_replay_shs(long long N, const float* __restrict__ rot_old, const float* __restrict__ rot_new,
+             const uint8_t* __restrict__ is_static, float* __restrict__ shs) {
+  extern __shared__ float4 s_sh4[];   // FIT_TILE x FIT_PITCH4 float4
+  __shared__ uint8_t s_static[FIT_TILE];
+  const long long g0 = (long long)blockIdx.x * FIT_TILE;
+  const int tid = threadIdx.x;
+  const int rows = (int)min((long long)FIT_TILE, N - g0);
+  const long long g = g0 + tid;
+  s_static[tid] = (tid < rows) ? (is_static ? is_static[g] : 0) : 1;
+  float4 o4 = make_float4(1.f, 0.f, 0.f, 0.f), n4 = o4;
+  if (tid < rows) { o4 = ldg4(rot_old + 4 * g); n4 = ldg4(rot_new + 4 * g); }
+  __syncthreads();
+  const float4* gsh = reinterpret_cast<const float4*>(shs + g0 * SH_FLOATS);
+  const int cp_r0 = tid / 12, cp_c4 = tid - 12 * cp_r0;
+  if (tid < 120) {
+#pragma unroll
+    for (int t = 0; t < 13; t++) {
+      const int r = cp_r0 + 10 * t;
+      if (r < rows && !s_static[r]) cp_async16(s_sh4 + r * FIT_PITCH4 + cp_c4, gsh + tid + 120 * t);
+    }
+  }
+  cp_async_commit();
+  const bool act = tid < rows && !s_static[tid];
+  float Rs[3][3];
+  if (act) {
+    const Quat oq{o4.x, o4.y, o4.z, o4.w}, q{n4.x, n4.y, n4.z, n4.w};
+    const Quat rq = quat_normalized(quat_mul(q, quat_inverse(oq)));
+    quat_to_matrix(rq, Rs);
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  if (act) {
+    float4* row = s_sh4 + tid * FIT_PITCH4;
+    float v[SH_FLOATS];
+#pragma unroll
+    for (int c = 0; c < 12; c++) { const float4 x = row[c]; v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w; }
+    sh_rotate_flipped_fast(Rs, v);
+#pragma unroll
+    for (int c = 1; c < 12; c++) row[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    row[0].w = v[3];
+  }
+  __syncthreads();
+  float* osh = shs + g0 * SH_FLOATS;
+  if (tid < 120) {
+#pragma unroll
+    for (int t = 0; t < 13; t++) {
+      const int r = cp_r0 + 10 * t;
+      if (r < rows && !s_static[r]) st_stream4(osh + (size_t)(tid + 120 * t) * 4, s_sh4[r * FIT_PITCH4 + cp_c4]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ node quaternions
 // FastgetOthogonalMatrix (helper.cpp:506-517): float Newton polar iteration,
 // returns the iterate BEFORE the one that met the 1e-6 max-abs test.
@@ -792,6 +850,21 @@ extern "C" int arapk_fit_gaussians(long long N, const float* ends, const float* 
     attr_set = true;
   }
   k_fit_gaussians<<<(unsigned)((N + FIT_TILE - 1) / FIT_TILE), FIT_TILE, smem, st>>>(N, ends, scale_backup, is_static, pos, rot, scale, shs);
+  ARAP_KERNEL_CHECK();
+  return ARAP_OK;
+}
+
+extern "C" int arapk_replay_shs(long long N, const float* rot_old, const float* rot_new, const uint8_t* is_static, float* shs,
+                                cudaStream_t st) {
+  if (N <= 0) return ARAP_OK;
+  int rc = ensure_sh_tables(); if (rc) return rc;
+  const size_t smem = sizeof(float4) * FIT_TILE * FIT_PITCH4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_replay_shs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  k_replay_shs<<<(unsigned)((N + FIT_TILE - 1) / FIT_TILE), FIT_TILE, smem, st>>>(N, rot_old, rot_new, is_static, shs);
   ARAP_KERNEL_CHECK();
   return ARAP_OK;
 }

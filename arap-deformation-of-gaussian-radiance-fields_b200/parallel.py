@@ -83,6 +83,52 @@ class SoAGatherPush:
         return self.outs
 
 
+class SoAGatherPose:
+    """All-gather that sends only the pose (pos 3 + rot 4 + scale 3 floats = 40 of the 232 bytes per Gaussian).
+
+    Every rank keeps last step's full SoA of all ranks.  The SH rows of the remote shards are not received: the receiver
+    repeats the owner's SH update — R = (q_new q_old^-1).normalized, `sh_rotate` — from the old and the new rotation with
+    the same kernel arithmetic (`arapk_replay_shs`), so its copy stays bit-identical to the owner's (checked against a full
+    NCCL gather in `bench.py` with ARAP_GATHER_CHECK=1).  8 GPUs x 6M Gaussians: 1.7 instead of 9.7 GB received per rank
+    per step.  Needs one call per drag step (a skipped step would skip a rotation) and `refresh_static()` after the
+    control blocks change (static Gaussians are not rotated by their owner).  Opt-in: `ARAP_GATHER=pose`."""
+
+    def __init__(self, parts: dict, world: int, rank: int, lib, static_flags=None):
+        import torch
+        import torch.distributed as dist
+        self.parts, self.world, self.rank, self.lib = parts, world, rank, lib
+        self.n = parts["pos"].shape[0]
+        self.outs = {k: torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device) for k, t in parts.items()}
+        for k, t in parts.items():                       # initial state: everything, once
+            dist.all_gather_into_tensor(self.outs[k], t)
+        self.rot_prev = torch.empty_like(self.outs["rot"])
+        self.static = torch.zeros(world * self.n, dtype=torch.uint8, device=parts["pos"].device)
+        if static_flags is not None:
+            self.refresh_static(static_flags)
+
+    def refresh_static(self, local_flags):
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(self.static, local_flags.contiguous())
+
+    def __call__(self):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        n, lo = self.n, self.rank * self.n
+        self.rot_prev.copy_(self.outs["rot"])
+        for k in ("pos", "rot", "scale"):
+            dist.all_gather_into_tensor(self.outs[k], self.parts[k])
+        self.outs["shs"][lo:lo + n].copy_(self.parts["shs"])          # own shard: the owner's rows
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for a, b in ((0, lo), (lo + n, self.world * n)):              # remote shards: replay the rotation
+            if b > a:
+                rc = self.lib.arapk_replay_shs(C.c_longlong(b - a), C.c_void_p(self.rot_prev[a:].data_ptr()), C.c_void_p(self.outs["rot"][a:].data_ptr()),
+                                               C.c_void_p(self.static[a:].data_ptr()), C.c_void_p(self.outs["shs"][a:].data_ptr()), st)
+                if rc != 0:
+                    raise RuntimeError(f"arapk_replay_shs failed ({rc})")
+        return self.outs
+
+
 def allgather_variable(local: "np.ndarray", world: int):
     """All-gather of unequal shards (host arrays, any backend): pads to the largest shard."""
     import torch

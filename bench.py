@@ -10,7 +10,8 @@ sample SH rotation.  Workload at N=1: configs[3] of BASELINE.json (the configura
 north_star target is quoted on): synthetic 6M-Gaussian scene, 128^3 grid, 16k nodes, k=10,
 per-node constraints on two box-selected caps, constant (0,0,0.002) drag.  With N>1 ranks the
 Gaussian-indexed stages are sharded (each rank owns a 6M-Gaussian shard, weak scaling), the node
-solve is replicated, and each step ends with an NCCL all-gather of the deformed SoA.
+solve is replicated, and each step ends with an exchange of the deformed Gaussians between all ranks (NCCL all-gather of the
+pose + SH rotation replayed on the receivers; ARAP_GATHER=nccl gathers the whole SoA).
 
 Prints ONE JSON line on rank 0.
 """
@@ -138,7 +139,8 @@ def run_own(args):
         # Measured (ms per step, without -> with): 8 GPUs 27.9 -> 26.7, 4 GPUs 19.7 -> 18.1; at 2 GPUs the gather already hides
         # behind the sample passes and the reservation only slows the solve and stretches the gather (14.8 -> 16.2), so it is
         # on from 4 ranks up.
-        nccl_ctas = int(os.environ.get("ARAP_NCCL_CTAS", "24" if world >= 4 else "0"))
+        # Only for the full-SoA gather (ARAP_GATHER=nccl); the default pose-only gather moves 6x less and needs no reservation.
+        nccl_ctas = int(os.environ.get("ARAP_NCCL_CTAS", "24" if world >= 4 and os.environ.get("ARAP_GATHER", "pose") == "nccl" else "0"))
         if nccl_ctas > 0:
             opts.config.max_ctas = nccl_ctas
         dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
@@ -166,10 +168,16 @@ def run_own(args):
         par = importlib.import_module(ge.PKG + ".parallel")
         v = s.device_view()
         parts = {name: torch.as_tensor(par.DevArray(getattr(v, name), (N, w)), device="cuda") for name, w in par.SOA_WIDTHS}
-        # NCCL all-gather (default) or peer stores through the copy engines (ARAP_GATHER=push).  Measured on 8 B200s:
+        # Whole-SoA variants: NCCL all-gather (ARAP_GATHER=nccl) or peer stores through the copy engines (ARAP_GATHER=push).  Measured on 8 B200s:
         # the copy engines sustain ~270 GB/s per rank for the 9.7 GB a rank sends per step (43.7 ms/step), NCCL's SM
         # kernels ~900 GB/s (28.7 ms/step); at 2 GPUs both hide behind the sample passes (22.5 / 22.1 ms/step).
-        if os.environ.get("ARAP_GATHER", "nccl") != "push":
+        # Default: pose-only gather + SH replay on the receivers (parallel.SoAGatherPose) — bit-identical to the full gather
+        # (ARAP_GATHER_CHECK=1; verified on 2 GPUs) and faster: 2 GPUs 14.8 -> 14.6 ms per step, 4 GPUs 18.1 -> 15.9.
+        # ARAP_GATHER=nccl: all-gather of the whole SoA (232 B / Gaussian); ARAP_GATHER=push: peer stores by the copy engines.
+        if os.environ.get("ARAP_GATHER", "pose") == "pose":
+            gs_static, _ = s.static_flags()
+            gather = par.SoAGatherPose(parts, world, rank, pkg.lib(), torch.from_numpy(np.ascontiguousarray(gs_static).astype(np.uint8)).cuda())
+        elif os.environ.get("ARAP_GATHER", "pose") != "push":
             gather = par.SoAGather(parts, world)
         else:
             gather = par.SoAGatherPush(parts, world, rank)
@@ -273,6 +281,15 @@ def run_own(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = float(te.item())
 
+    if gather is not None and os.environ.get("ARAP_GATHER_CHECK"):   # the gathered copy equals a full NCCL gather of the owners' SoA
+        barrier()
+        got = gather.outs
+        ref = par.SoAGather(parts, world)()
+        barrier()
+        bad = [kk for kk in ref if not torch.equal(ref[kk], got[kk])]
+        print(json.dumps({"gather_check": os.environ.get("ARAP_GATHER", "pose"), "rank": rank, "mismatch": bad,
+                          "max_abs_shs_diff": float((ref["shs"] - got["shs"]).abs().max())}), file=sys.stderr, flush=True)
+        assert not bad, bad
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -293,7 +310,7 @@ def run_own(args):
                    "grid": cfg["grid"], "samples_per_gpu": S, "valid_cells": gi["valid_cells"], "list_pairs": gi["pairs"],
                    "constraints": "per-node, two caps (|z|>0.4)", "active_nodes": setup["n_active"], "pinned_nodes": setup["n_pinned"],
                    "l2": "inputs (>1.4 GB SoA + tables per step) exceed the 126 MB L2",
-                   "parallelism": "replicated solve, Gaussians/samples sharded by index, NCCL all-gather of the deformed SoA on a high-priority side stream (starts when the six-point fit is done: overlaps the sample passes)" if world > 1 else "single GPU"},
+                   "parallelism": "replicated solve, Gaussians/samples sharded by index; every step all ranks exchange the deformed Gaussians on a high-priority side stream (starts when the six-point fit is done: overlaps the sample passes): NCCL all-gather of pos/rot/scale + bit-identical replay of the SH rotation on the receivers (ARAP_GATHER=nccl: all-gather of the whole SoA)" if world > 1 else "single GPU"},
         "stages_ms": {"solve": round(float(mean[0]), 4), "sample_advect": round(float(mean[1]), 4), "endpoint_lbs": round(float(mean[2]), 4),
                       "six_point_fit": round(float(mean[3]), 4), "sample_sh_rotate": round(float(mean[4]), 4)},
         "solve": {"gn_iters": st["gn_iters"], "cg_iters": st["cg_iters"], "flags": st["flags"], "grid_blocks": st["grid_blocks"],

@@ -35,6 +35,9 @@ int arapk_lbs_tiles(const float* in, float* out, long long P, int k, const uint3
 int arapk_end_points(long long N, const float* pos, const float* rot, const float* scale, float* ends, cudaStream_t st);
 int arapk_fit_gaussians(long long N, const float* ends, const float* scale_backup, const uint8_t* is_static, float* pos,
                         float* rot, float* scale, float* shs, cudaStream_t st);
+/* multi-GPU receivers: repeat the owner's SH update of k_fit_gaussians from (old rotation, new rotation) on a held copy */
+int arapk_replay_shs(long long N, const float* rot_old, const float* rot_new, const uint8_t* is_static, float* shs,
+                     cudaStream_t st);
 int arapk_node_quats(int M, const double* rot, float* q_xyzw, cudaStream_t st);
 int arapk_rotate_sample_shs(long long S, int k, const float* w, const uint16_t* idx, const float* q_xyzw,
                             const uint8_t* is_static, float* feature, cudaStream_t st);

@@ -199,6 +199,31 @@ def test_end_points_and_fit_match_oracle(pkg, orc, scenes):
     assert np.abs(out["shs"] - ref["shs"]).max() <= 2e-6
 
 
+def test_replay_shs_repeats_the_fit_bit_for_bit(pkg, scenes):
+    """Multi-GPU receivers rebuild remote SH rows from (old rotation, new rotation): same bits as the owner's fit."""
+    lib = pkg.lib()
+    sc = scenes.make_scene("sphere1m", n=40007)
+    N = sc["n"]
+    rng = np.random.default_rng(9)
+    d = {k: dev(sc[k]) for k in ("pos", "rot", "scale", "shs")}
+    d_ends = torch.zeros(N * 18, dtype=torch.float32, device="cuda")
+    pkg.check(lib.arapk_end_points(C.c_longlong(N), ptr(d["pos"]), ptr(d["rot"]), ptr(d["scale"]), ptr(d_ends), stream()))
+    static = dev((rng.uniform(size=N) < 0.2).astype(np.uint8))
+    held = {"rot": d["rot"].clone(), "shs": d["shs"].clone()}                      # what a receiver holds
+    d_sb = dev(sc["scale"])
+    for step in range(3):
+        A = np.eye(3) + rng.normal(size=(3, 3)) * 0.05
+        ends = (d_ends.cpu().numpy().reshape(-1, 3).astype(np.float64) @ A.T).astype(np.float32)
+        d_ends = dev(ends.reshape(-1))
+        pkg.check(lib.arapk_fit_gaussians(C.c_longlong(N), ptr(d_ends), ptr(d_sb), ptr(static), ptr(d["pos"]), ptr(d["rot"]), ptr(d["scale"]), ptr(d["shs"]), stream()))
+        rot_prev = held["rot"].clone()
+        held["rot"].copy_(d["rot"])                                                # the 16 bytes that travel
+        pkg.check(lib.arapk_replay_shs(C.c_longlong(N), ptr(rot_prev), ptr(held["rot"]), ptr(static), ptr(held["shs"]), stream()))
+        torch.cuda.synchronize()
+        assert torch.equal(held["shs"], d["shs"]), step
+    assert not torch.equal(d["shs"], dev(sc["shs"]))                               # the rows did change
+
+
 def test_sh_rotation_device_matches_oracle(pkg, orc):
     lib = pkg.lib()
     rng = np.random.default_rng(11)
