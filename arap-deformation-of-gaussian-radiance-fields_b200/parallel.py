@@ -93,10 +93,13 @@ class SoAGatherPose:
     per step.  Needs one call per drag step (a skipped step would skip a rotation) and `refresh_static()` after the
     control blocks change (static Gaussians are not rotated by their owner).  Opt-in: `ARAP_GATHER=pose`."""
 
-    def __init__(self, parts: dict, world: int, rank: int, lib, static_flags=None):
+    def __init__(self, parts: dict, world: int, rank: int, lib, static_flags=None, replay=None):
+        """`replay(rot_old, rot_new, static, shs)` updates `shs` in place for a contiguous index range; default: the CUDA kernel
+        `arapk_replay_shs` of `lib`.  (The gloo tests pass a host stand-in with the owner's update rule.)"""
         import torch
         import torch.distributed as dist
         self.parts, self.world, self.rank, self.lib = parts, world, rank, lib
+        self.replay = replay or self._replay_cuda
         self.n = parts["pos"].shape[0]
         self.outs = {k: torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device) for k, t in parts.items()}
         for k, t in parts.items():                       # initial state: everything, once
@@ -111,22 +114,25 @@ class SoAGatherPose:
         dist.all_gather_into_tensor(self.static, local_flags.contiguous())
 
     def __call__(self):
-        import ctypes as C
-        import torch
         import torch.distributed as dist
         n, lo = self.n, self.rank * self.n
         self.rot_prev.copy_(self.outs["rot"])
         for k in ("pos", "rot", "scale"):
             dist.all_gather_into_tensor(self.outs[k], self.parts[k])
         self.outs["shs"][lo:lo + n].copy_(self.parts["shs"])          # own shard: the owner's rows
-        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         for a, b in ((0, lo), (lo + n, self.world * n)):              # remote shards: replay the rotation
             if b > a:
-                rc = self.lib.arapk_replay_shs(C.c_longlong(b - a), C.c_void_p(self.rot_prev[a:].data_ptr()), C.c_void_p(self.outs["rot"][a:].data_ptr()),
-                                               C.c_void_p(self.static[a:].data_ptr()), C.c_void_p(self.outs["shs"][a:].data_ptr()), st)
-                if rc != 0:
-                    raise RuntimeError(f"arapk_replay_shs failed ({rc})")
+                self.replay(self.rot_prev[a:b], self.outs["rot"][a:b], self.static[a:b], self.outs["shs"][a:b])
         return self.outs
+
+    def _replay_cuda(self, rot_old, rot_new, static, shs):
+        import ctypes as C
+        import torch
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        rc = self.lib.arapk_replay_shs(C.c_longlong(rot_new.shape[0]), C.c_void_p(rot_old.data_ptr()), C.c_void_p(rot_new.data_ptr()),
+                                       C.c_void_p(static.data_ptr()), C.c_void_p(shs.data_ptr()), st)
+        if rc != 0:
+            raise RuntimeError(f"arapk_replay_shs failed ({rc})")
 
 
 def allgather_variable(local: "np.ndarray", world: int):

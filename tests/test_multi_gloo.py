@@ -38,6 +38,25 @@ def _worker(rank, world, port, q):
     parts = {k: torch.from_numpy(np.ascontiguousarray(v[rank * m:(rank + 1) * m])) for k, v in full.items()}
     outs = par.SoAGather(parts, world)()
     ok &= all(np.array_equal(outs[k].numpy(), full[k][:world * m]) for k in full)
+    # pose-only gather: remote SH rows are rebuilt from (old rot, new rot) with the owner's update rule; a host stand-in for
+    # that rule (the CUDA kernel is covered by test_replay_shs_repeats_the_fit_bit_for_bit) checks the orchestration:
+    # previous-rotation bookkeeping, own shard copied, remote shards replayed, static rows untouched
+    def sh_update(rot_old, rot_new, static, shs):
+        upd = shs * (1.0 + (rot_new - rot_old).sum(1, keepdim=True)) + rot_new[:, :1]
+        shs.copy_(torch.where(static[:, None].bool(), shs, upd))
+    static_full = torch.from_numpy((rng.uniform(size=world * m) < 0.25).astype(np.uint8))
+    mine = slice(rank * m, (rank + 1) * m)
+    local = {k: t.clone() for k, t in parts.items()}
+    pose = par.SoAGatherPose(local, world, rank, None, static_full[mine].clone(), replay=sh_update)
+    step_rng = np.random.default_rng(100 + rank)
+    for step in range(3):                               # the owner's step: new pose, SH updated from old -> new rotation
+        rot_old = local["rot"].clone()
+        for k in ("pos", "rot", "scale"):
+            local[k].add_(torch.from_numpy(step_rng.normal(size=tuple(local[k].shape)).astype(np.float32)))
+        sh_update(rot_old, local["rot"], static_full[mine], local["shs"])
+        got = pose()
+        ref = par.SoAGather(local, world)()
+        ok &= all(torch.equal(got[k], ref[k]) for k in ref)
     # max-over-ranks timing reduction as bench.py does it
     t = torch.tensor([1.0 + rank], dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
