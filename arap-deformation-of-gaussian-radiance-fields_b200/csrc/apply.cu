@@ -6,6 +6,8 @@
 //   node_quats      GaussianView::FastUpdateSamplesSH host part  (GaussianView.cpp:3169-3186)
 //   rotate_sample_shs  RotateSHs kernel                          (cudakdtree.cu:201-222)
 //   static_flags    CheckStaticSamples / CheckMovedGaussians     (GaussianView.cpp:2024-2109)
+//   lbs_tiles / lbs_build_tiles   the same LBS through per-tile staged node records (ours)
+//   replay_shs      the SH update of fit_gaussians repeated by a multi-GPU receiver (ours)
 //
 // HBM layout.  The rasteriser-facing SoA keeps the reference layout
 // (pos N x 3, rot N x 4 wxyz, scale N x 3, opacity N, shs N x 48 — the
@@ -13,7 +15,9 @@
 // tables are ours: skinning rows are stored in blocks of 32 rows,
 //   idx[(blk*K + j)*32 + lane]  (uint16)     w[(blk*K + j)*32 + lane]  (double)
 // so a warp reading neighbour j of 32 consecutive rows issues one 64 B and one
-// 256 B fully-coalesced request.
+// 256 B fully-coalesced request; the staged LBS kernel reads one-byte slot numbers
+//   slots[(blk*3 + m)*32 + lane]  (uint32 = 4 slots)
+// into a per-tile list of distinct nodes instead of the uint16 ids.
 #include <algorithm>
 #include <cstdlib>
 #include "device_math.cuh"
