@@ -329,7 +329,7 @@ def run_own(args):
                              "algorithmic_bytes_per_launch": sample_bytes, "ms_per_launch": round(sample_ms, 4)},
         "e2e": {"value": round(e2e_ms, 4), "unit": UNIT, "h2d_bytes_per_step": M * 12, "d2h_bytes_per_step": M * (12 + 72 + 24) + 64,
                 "what": "arap_aim_set(host aims) + arap_step + arap_download_nodes + arap_solve_stats_get per step"},
-        "gpu_launches": 10 * args.steps,   # per step: aim_translate, group_aims, solve, node_xf, 3 x lbs_tiles, fit, node_quats, rotate (profiles/launches_r01d.csv)
+        "gpu_launches": (10 + (1 if world > 1 and os.environ.get("ARAP_GATHER", "pose") == "pose" else 0)) * args.steps,   # rank 0, per step: (+ arapk_replay_shs on its one remote range when N > 1) aim_translate, group_aims, solve, node_xf, 3 x lbs_tiles, fit, node_quats, rotate (profiles/launches_r01d.csv)
         "clocks": clk,
     }
     if world == 1 and not args.no_cpu_baseline:
