@@ -2,7 +2,7 @@
 """CPU study (scipy, no GPU): PCG iteration counts of the first Gauss-Newton system of a drag step under different
 preconditioners, on the oracle's Jacobian (reference arithmetic) of a scene with the bench's node density.
 
-    python tools/precond_study.py [nodes=4000] [gaussians=200000]
+    python tests/studies/precond_study.py [nodes=4000] [gaussians=200000]
 
 Unknown order of the oracle's Jacobian = the reference's: 12 per free node (A column-major 9, t 3)."""
 import importlib, sys, time
@@ -10,7 +10,7 @@ from pathlib import Path
 import numpy as np
 import scipy.sparse as sp
 import scipy.sparse.linalg as spla
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 import __graft_entry__ as ge
 ge.load_package()
