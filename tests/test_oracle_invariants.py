@@ -141,6 +141,79 @@ def test_solve_first_step_matches_scipy_direct_solve(orc, scenes):
     assert np.isclose(f @ f, orc.energy(o.node_pos, o.nbr, o.anc_idx, o.anc_w, o.node_static, o.blocks, o.block_types, o.aim, False, I, Z))
 
 
+@pytest.mark.parametrize("on_center", [False, True])
+def test_jacobian_matches_finite_differences_of_the_residual(orc, scenes, on_center):
+    """The analytic Jacobian (Deform.cpp:180-376) is the derivative of the residual (Deform.cpp:378-581) at a generic x:
+    central differences of f over every unknown of a few nodes, per-node and centre constraints, with an excluded block."""
+    o = _session(scenes, n=3000, nodes=60, k=6)
+    rng = np.random.default_rng(3)
+    z = o.node_pos[:, 2]
+    blocks = [np.nonzero(z > 0.25)[0].astype(np.uint32), np.nonzero(z < -0.25)[0].astype(np.uint32),
+              np.nonzero(np.abs(z) < 0.05)[0].astype(np.uint32)[:3], np.nonzero(o.node_pos[:, 0] > 0.4)[0].astype(np.uint32)[:4]]
+    o.set_blocks(blocks, [1, 0, 0, -1])
+    o.aim_translate([0.01, 0.0, 0.03])
+    rot = np.tile(np.eye(3).reshape(-1), (o.M, 1)) + rng.normal(size=(o.M, 9)) * 0.05
+    trans = rng.normal(size=(o.M, 3)) * 0.02
+    args = (o.node_pos, o.nbr, o.anc_idx, o.anc_w, o.node_static, o.blocks, o.block_types, o.aim, on_center)
+    R, Cc, V, f0, (m, n) = orc.jacobian(*args, rot, trans)
+    J = np.zeros((m, n)); np.add.at(J, (R, Cc), V)
+    free = np.nonzero(o.node_static == 0)[0]
+    assert n == 12 * len(free)
+    x = np.concatenate([rot, trans], 1)
+    eps = 1e-6
+    for u in rng.choice(n, 40, replace=False):
+        node, comp = free[u // 12], u % 12
+        xp, xm = x.copy(), x.copy()
+        xp[node, comp] += eps; xm[node, comp] -= eps
+        fp = orc.jacobian(*args, xp[:, :9].copy(), xp[:, 9:].copy())[3]
+        fm = orc.jacobian(*args, xm[:, :9].copy(), xm[:, 9:].copy())[3]
+        assert np.allclose((fp - fm) / (2 * eps), J[:, u], atol=2e-7), (u, np.abs((fp - fm) / (2 * eps) - J[:, u]).max())
+
+
+def test_six_point_fit_recovers_a_rigid_motion_and_axis_stretch(orc, scenes):
+    """End points moved by x -> Q x + t: the fit returns rot = Q rot, same scales, pos = Q pos + t; stretched along the
+    Gaussian's own axes by (a, b, c): scale_i' = ((s_i + 1e-3) a_i - 1e-3 ... ) as GaussianView.cpp:3124-3132 defines it."""
+    sc = scenes.make_scene("sphere1m", n=500)
+    N = sc["n"]
+    ends = orc.end_points(sc["pos"], sc["rot"], sc["scale"]).reshape(N, 6, 3).astype(np.float64)
+    Q = Rotation.from_rotvec([0.3, -0.2, 0.5]).as_matrix(); t = np.array([0.1, -0.05, 0.2])
+    moved = (ends @ Q.T + t).astype(np.float32).reshape(N, 18)
+    out = {k: sc[k].copy() for k in ("pos", "rot", "scale", "shs")}
+    orc.fit_gaussians(moved, sc["scale"], np.zeros(N, np.uint8), out["pos"], out["rot"], out["scale"], out["shs"])
+    assert np.abs(out["pos"] - (sc["pos"].astype(np.float64) @ Q.T + t)).max() <= 2e-6
+    assert (np.abs(out["scale"] - sc["scale"]) / sc["scale"]).max() <= 2e-3          # float end points: 1e-7 / (2 s) relative
+    Rn = Rotation.from_quat(out["rot"][:, [1, 2, 3, 0]]).as_matrix()
+    R0 = Rotation.from_quat((sc["rot"] / np.linalg.norm(sc["rot"], axis=1, keepdims=True))[:, [1, 2, 3, 0]]).as_matrix()
+    assert np.abs(Rn - Q @ R0).max() <= 2e-4
+    # stretch along the Gaussian's first axis by 1.5: K_0 scales by 1.5, the others stay
+    c = ends.mean(1, keepdims=True)
+    d = ends - c
+    d[:, 0:2] *= 1.5
+    out2 = {k: sc[k].copy() for k in ("pos", "rot", "scale", "shs")}
+    orc.fit_gaussians((c + d).astype(np.float32).reshape(N, 18), sc["scale"], np.zeros(N, np.uint8), out2["pos"], out2["rot"], out2["scale"], out2["shs"])
+    s0 = sc["scale"].astype(np.float64)
+    want0 = 1.5 * (s0[:, 0] + 1e-3) * 2.0 / ((s0[:, 0] + 1e-3) * 2.0) * s0[:, 0]
+    assert (np.abs(out2["scale"][:, 0] - want0) / want0).max() <= 2e-3
+    assert (np.abs(out2["scale"][:, 1:] - sc["scale"][:, 1:]) / sc["scale"][:, 1:]).max() <= 2e-3
+
+
+def test_lbs_and_sample_sh_are_noops_for_identity_transforms(orc):
+    rng = np.random.default_rng(1)
+    M, P, k = 50, 2000, 6
+    nodes = rng.normal(size=(M, 3)).astype(np.float32)
+    pts = rng.normal(size=(P, 3)).astype(np.float32)
+    idx, w = orc.knn_weights(nodes, pts, k)
+    I = np.tile(np.eye(3).reshape(-1), (M, 1)); Z = np.zeros((M, 3))
+    out = orc.lbs_points(pts.copy(), idx[:, :k], w, nodes, I, Z)
+    assert np.abs(out - pts).max() <= 3e-7                                             # float accumulator, k roundings
+    q = orc.node_quats(I)
+    assert np.allclose(q, [0, 0, 0, 1], atol=1e-7)
+    feat = rng.normal(size=(P, 48)).astype(np.float32)
+    rot = feat.copy()
+    orc.rotate_sample_shs(w.astype(np.float32), idx[:, :k].astype(np.int32), q, np.zeros(P, np.int32), rot)
+    assert np.abs(rot - feat).max() <= 1e-6
+
+
 def test_excluded_nodes_keep_identity_and_static_flags(scenes):
     o = _session(scenes, with_samples=True)
     lo = np.nonzero(o.node_pos[:, 2] < -0.2)[0].astype(np.uint32)
