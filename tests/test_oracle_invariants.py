@@ -247,3 +247,36 @@ def test_grid_invariants(scenes):
     assert np.all(o.sample_pos[:64] > lo) and np.all(o.sample_pos[:64] < lo + o.gstep)
     # undeformed adaptive LPF = (step/4)^2 * 0.2 * I  (GaussianView.cpp:3881)
     assert np.allclose(o.ada_lpf[c].reshape(3, 3), np.eye(3) * (o.gstep / 4) ** 2 * 0.2, rtol=1e-3, atol=1e-12)
+
+
+def test_grid_eval_is_the_lpf_widened_mixture(scenes):
+    """Field evaluation (forward3d_grid is external): the oracle's value at a sample equals the definition
+    feature(x) = sum_g alpha_g exp(-1/2 (x - mu_g)^T (Sigma_g + LPF_cell)^-1 (x - mu_g)) SH_g over the cell's list, with the
+    1/255 footprint cut-off — recomputed here in float64 numpy for a few cells."""
+    o = _session(scenes, n=4000, with_samples=True)
+    o.grid_eval(0)
+    g = o.g
+    for ci in (0, len(o.valid) // 2, len(o.valid) - 1):
+        c = o.valid[ci]
+        b, e = (o.fp_prefix[c - 1] if c else 0), o.fp_prefix[c]
+        lpf = o.ada_lpf[c].reshape(3, 3).astype(np.float64)
+        x = o.sample_pos[ci * 64:(ci + 1) * 64].astype(np.float64)
+        feat, opa = np.zeros((64, 48)), np.zeros(64)
+        for gi in o.lists[b:e]:
+            a = float(g["opacity"][gi])
+            if a <= 1.0 / 255.0:
+                continue
+            q = g["rot"][gi].astype(np.float64); q /= np.linalg.norm(q)
+            R = Rotation.from_quat(q[[1, 2, 3, 0]]).as_matrix()
+            S = R @ np.diag(g["scale"][gi].astype(np.float64) ** 2) @ R.T + lpf
+            d = x - g["pos"][gi].astype(np.float64)
+            pw = -0.5 * np.einsum("si,ij,sj->s", d, np.linalg.inv(S), d)
+            wgt = np.where((pw <= 0) & (pw >= np.log(1.0 / 255.0 / a) + 1e-4), a * np.exp(pw), 0.0)   # margin: float cut-off ties
+            near_cut = np.abs(pw - np.log(1.0 / 255.0 / a)) < 1e-4
+            wgt = np.where(near_cut, np.nan, wgt)
+            opa += wgt; feat += wgt[:, None] * g["shs"][gi].astype(np.float64)
+        ok = np.isfinite(opa)
+        assert ok.sum() >= 48
+        got_o, got_f = o.aim_opacity[ci * 64:(ci + 1) * 64], o.aim_feature[ci * 64:(ci + 1) * 64]
+        assert np.allclose(got_o[ok], opa[ok], rtol=2e-4, atol=1e-6)
+        assert np.allclose(got_f[ok], feat[ok], rtol=2e-4, atol=2e-5)
