@@ -71,6 +71,37 @@ for na in (16, 64, 148, 256):
     res[f"two-level additive: Jacobi + {na} aggregates x 12"] = pcg(two_level(na, lambda r: r / d))
 res["two-level additive: block-Jacobi 12 + 64 aggregates"] = pcg(two_level(64, block_jacobi(12)))
 
+# aggregates a kernel can get for free: equal chunks of the nodes in Morton order (= spatially clustered CTA ownership)
+def morton_chunks(n_agg):
+    q = ((nodes - nodes.min(0)) / (nodes.max(0) - nodes.min(0) + 1e-9) * 1023).astype(np.int64)
+    def spread(v):
+        v = (v | (v << 16)) & 0x030000FF; v = (v | (v << 8)) & 0x0300F00F; v = (v | (v << 4)) & 0x030C30C3; return (v | (v << 2)) & 0x09249249
+    key = spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2)
+    lab = np.empty(M, np.int64); lab[np.argsort(key, kind="stable")] = np.arange(M) * n_agg // M
+    return lab
+def two_level_lab(lab, smoother, n_agg):
+    rows = np.arange(n); cols = lab[rows // 12] * 12 + rows % 12
+    P = sp.csr_matrix((np.ones(n), (rows, cols)), shape=(n, n_agg * 12))
+    lu = spla.splu((P.T @ H @ P).tocsc() + 1e-12 * sp.eye(n_agg * 12))
+    return lambda r: smoother(r) + P @ lu.solve(P.T @ r)
+def rcb(n_parts):   # recursive coordinate bisection with proportional splits: balanced, compact boxes (host set-up cost: O(M log M))
+    lab = np.zeros(M, np.int64)
+    def rec(ids, p0, p):
+        if p == 1:
+            lab[ids] = p0; return
+        pl = p // 2
+        ax = np.argmax(nodes[ids].max(0) - nodes[ids].min(0))
+        order = ids[np.argsort(nodes[ids, ax], kind="stable")]
+        cut = len(ids) * pl // p
+        rec(order[:cut], p0, pl); rec(order[cut:], p0 + pl, p - pl)
+    rec(np.arange(M), 0, n_parts)
+    return lab
+res["two-level additive: Jacobi + 148 RCB boxes x 12 (balanced)"] = pcg(two_level_lab(rcb(148), lambda r: r / d, 148))
+res["two-level additive: block-Jacobi 12 + 148 RCB boxes"] = pcg(two_level_lab(rcb(148), block_jacobi(12), 148))
+for na in (148, 296):
+    res[f"two-level additive: Jacobi + {na} Morton chunks x 12"] = pcg(two_level_lab(morton_chunks(na), lambda r: r / d, na))
+res["two-level additive: block-Jacobi 12 + 148 Morton chunks"] = pcg(two_level_lab(morton_chunks(148), block_jacobi(12), 148))
+
 # Chebyshev-accelerated Jacobi (degree 3) as preconditioner: 3 extra mat-vecs, no reductions
 lmax = spla.eigsh(sp.diags(1 / np.sqrt(d)) @ H @ sp.diags(1 / np.sqrt(d)), k=1, which="LA", return_eigenvectors=False)[0]
 def cheb(deg, lo_frac=0.06):
