@@ -47,6 +47,8 @@ __global__ void k_node_xf(int M, const double* __restrict__ rot, const double* _
 // ------------------------------------------------------------------ LBS
 // One thread per point.  Double products, float accumulator rounded after each
 // neighbour — exactly the reference's `Pos output += double_expr` sequence.
+// `in` and `out` may alias (the session skins end points / samples / mesh points in place: every element is read and
+// written by its own thread only), so neither is __restrict__.
 //
 // round_to_float: RN-even rounding of a double to float precision WITHOUT leaving the FP64 pipe.
 // M = 1.5 * 2^(e+29) (e = exponent of s) puts the unit in the last place of s + M at 2^(e-23), the float
@@ -84,7 +86,7 @@ __device__ __forceinline__ void lbs_neighbour(float c0, float c1, float c2, doub
 }
 
 template <int K>
-__device__ __forceinline__ void lbs_row_global(const float* __restrict__ in, float* __restrict__ out, long long i, int k,
+__device__ __forceinline__ void lbs_row_global(const float* in, float* out, long long i, int k,
                                                const uint16_t* __restrict__ ridx, const double* __restrict__ rw,
                                                const NodeXf* __restrict__ nodes) {
   const float c0 = in[3 * i], c1 = in[3 * i + 1], c2 = in[3 * i + 2];
@@ -106,7 +108,7 @@ __device__ __forceinline__ void lbs_row_global(const float* __restrict__ in, flo
 
 template <int K>
 __global__ void __launch_bounds__(256)
-k_lbs_points(const float* __restrict__ in, float* __restrict__ out, long long P, int k_rt,
+k_lbs_points(const float* in, float* out, long long P, int k_rt,
              const uint16_t* __restrict__ ridx, const double* __restrict__ rw,
              const NodeXf* __restrict__ nodes, const uint8_t* __restrict__ skip, int group) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -131,7 +133,7 @@ constexpr int LT_WORDS = 3;   // slot words per row: 12 one-byte slots
 
 template <int K, bool MAGIC>
 __global__ void __launch_bounds__(LT_ROWS, 8)   // 64 registers: 8 CTAs per SM (72 registers / 7 CTAs measured 3 % slower on the samples)
-k_lbs_tiles(const float* __restrict__ in, float* __restrict__ out, long long P, int k_rt, const uint32_t* __restrict__ slots,
+k_lbs_tiles(const float* in, float* out, long long P, int k_rt, const uint32_t* __restrict__ slots,
             const double* __restrict__ rw, const uint16_t* __restrict__ ridx, const uint16_t* __restrict__ tile_cnt,
             const uint16_t* __restrict__ tile_nodes, const NodeXf* __restrict__ nodes, const uint8_t* __restrict__ skip,
             int group) {

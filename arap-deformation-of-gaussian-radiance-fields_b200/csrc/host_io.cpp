@@ -14,6 +14,8 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <memory>
+#include <stdexcept>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -37,51 +39,78 @@ struct arap_history {
   std::vector<float> twist_axis;     // 4 per move
 };
 
-extern "C" int arap_history_load(const char* path, arap_history** out) {
-  if (!path || !out) { set_error("history_load: bad arguments"); return ARAP_ERR_INVALID; }
+// Counts come from an untrusted file: every count is bounded by the file size (each element takes at least two bytes of
+// text) before anything is resized, and the cross-section consistency the replay relies on is checked here, so that a
+// malformed file ends in ARAP_ERR_IO instead of an out-of-bounds read or a std::bad_alloc crossing the C boundary.
+static int history_load_impl(const char* path, arap_history** out) {
   std::ifstream in(path);
   if (!in.is_open()) { set_error(std::string("history_load: cannot open ") + path); return ARAP_ERR_IO; }
-  auto* h = new arap_history();
-  std::string name; int size = 0, inner = 0;
-  auto fail = [&](const char* what) { set_error(std::string("history_load: malformed file at ") + what); delete h; return ARAP_ERR_IO; };
+  in.seekg(0, std::ios::end);
+  const long long file_bytes = (long long)in.tellg();
+  in.seekg(0, std::ios::beg);
+  const long long max_count = file_bytes / 2 + 1;
+  std::unique_ptr<arap_history> hp(new arap_history());
+  arap_history* h = hp.get();
+  std::string name; long long size = 0, inner = 0;
+  auto fail = [&](const char* what) { set_error(std::string("history_load: malformed file at ") + what); return ARAP_ERR_IO; };
+  auto count_ok = [&](long long c, long long per) { return c >= 0 && c <= max_count / per; };
   if (!(in >> h->nodes_on_mesh)) return fail("node type");
-  if (!(in >> name >> size) || size < 0) return fail("Nodes:");
-  h->nodes.resize(size);
-  for (int i = 0; i < size; i++) if (!(in >> h->nodes[i])) return fail("node indices");
+  if (!(in >> name >> size) || !count_ok(size, 1)) return fail("Nodes:");
+  h->nodes.resize((size_t)size);
+  for (long long i = 0; i < size; i++) if (!(in >> h->nodes[i])) return fail("node indices");
   if (!(in >> name >> h->total_operations)) return fail("Total_Operations:");
   if (!(in >> name >> h->move_operations)) return fail("Move_Operations:");
-  if (!(in >> name >> size) || size < 0) return fail("Operation_Types:");
-  h->operation_types.resize(size);
-  for (int i = 0; i < size; i++) if (!(in >> h->operation_types[i])) return fail("operation types");
-  if (!(in >> name >> size) || size < 0) return fail("Block_Nodes:");
-  h->block_nodes.resize(size);
-  for (int i = 0; i < size; i++) {
-    if (!(in >> inner) || inner < 0) return fail("block size");
-    h->block_nodes[i].resize(inner);
-    for (int j = 0; j < inner; j++) if (!(in >> h->block_nodes[i][j])) return fail("block nodes");
+  if (!(in >> name >> size) || !count_ok(size, 1)) return fail("Operation_Types:");
+  h->operation_types.resize((size_t)size);
+  for (long long i = 0; i < size; i++) if (!(in >> h->operation_types[i])) return fail("operation types");
+  if (!(in >> name >> size) || !count_ok(size, 1)) return fail("Block_Nodes:");
+  h->block_nodes.resize((size_t)size);
+  for (long long i = 0; i < size; i++) {
+    if (!(in >> inner) || !count_ok(inner, 1)) return fail("block size");
+    h->block_nodes[i].resize((size_t)inner);
+    for (long long j = 0; j < inner; j++) if (!(in >> h->block_nodes[i][j])) return fail("block nodes");
   }
-  if (!(in >> name >> size) || size < 0) return fail("Mouse_Movements:");
-  h->mouse_movements.resize(size);
-  for (int i = 0; i < size; i++) {
-    if (!(in >> inner) || inner < 0) return fail("movement count");
+  if (!(in >> name >> size) || !count_ok(size, 1)) return fail("Mouse_Movements:");
+  h->mouse_movements.resize((size_t)size);
+  for (long long i = 0; i < size; i++) {
+    if (!(in >> inner) || !count_ok(inner, 3)) return fail("movement count");
     h->mouse_movements[i].resize((size_t)inner * 3);
-    for (int j = 0; j < inner * 3; j++) if (!(in >> h->mouse_movements[i][j])) return fail("movements");
+    for (long long j = 0; j < inner * 3; j++) if (!(in >> h->mouse_movements[i][j])) return fail("movements");
   }
-  if (!(in >> name >> size) || size < 0) return fail("Blocks_Types_Moves:");
-  h->blocks_types_moves.resize(size);
-  for (int i = 0; i < size; i++) {
-    if (!(in >> inner) || inner < 0) return fail("block types count");
-    h->blocks_types_moves[i].resize(inner);
-    for (int j = 0; j < inner; j++) if (!(in >> h->blocks_types_moves[i][j])) return fail("block types");
+  if (!(in >> name >> size) || !count_ok(size, 1)) return fail("Blocks_Types_Moves:");
+  h->blocks_types_moves.resize((size_t)size);
+  for (long long i = 0; i < size; i++) {
+    if (!(in >> inner) || !count_ok(inner, 1)) return fail("block types count");
+    h->blocks_types_moves[i].resize((size_t)inner);
+    for (long long j = 0; j < inner; j++) if (!(in >> h->blocks_types_moves[i][j])) return fail("block types");
   }
-  if (!(in >> name >> size) || size < 0) return fail("Energy_on_Center:");
-  h->energy_on_centers.resize(size);
-  for (int i = 0; i < size; i++) if (!(in >> h->energy_on_centers[i])) return fail("energy flags");
-  if (!(in >> name >> size) || size < 0) return fail("Twist_Axis:");
+  if (!(in >> name >> size) || !count_ok(size, 1)) return fail("Energy_on_Center:");
+  h->energy_on_centers.resize((size_t)size);
+  for (long long i = 0; i < size; i++) if (!(in >> h->energy_on_centers[i])) return fail("energy flags");
+  if (!(in >> name >> size) || !count_ok(size, 4)) return fail("Twist_Axis:");
   h->twist_axis.resize((size_t)size * 4);
-  for (int i = 0; i < size * 4; i++) if (!(in >> h->twist_axis[i])) return fail("twist axes");
-  *out = h;
+  for (long long i = 0; i < size * 4; i++) if (!(in >> h->twist_axis[i])) return fail("twist axes");
+  // RecordDeformation writes one entry of every per-move section per move operation (GV:4893-4932), and the replay
+  // indexes all of them with the same move counter (GV:1815-1899).
+  const size_t moves = h->mouse_movements.size();
+  if (h->blocks_types_moves.size() != moves || h->energy_on_centers.size() != moves || h->twist_axis.size() != 4 * moves)
+    return fail("per-move sections: Mouse_Movements / Blocks_Types_Moves / Energy_on_Center / Twist_Axis counts differ");
+  size_t n_add = 0, n_move = 0;
+  for (size_t i = 0; i < h->operation_types.size() && (long long)i < (long long)h->total_operations; i++) {
+    const int op = h->operation_types[i];
+    if (op > 4) return fail("operation types: unknown op");
+    n_add += op == 0; n_move += op > 0;
+  }
+  if (h->total_operations < 0 || (size_t)h->total_operations > h->operation_types.size()) return fail("Total_Operations exceeds the Operation_Types count");
+  if (n_add > h->block_nodes.size() || n_move > moves) return fail("operation types: more add / move ops than recorded blocks / movements");
+  *out = hp.release();
   return ARAP_OK;
+}
+
+extern "C" int arap_history_load(const char* path, arap_history** out) {
+  if (!path || !out) { set_error("history_load: bad arguments"); return ARAP_ERR_INVALID; }
+  try { return history_load_impl(path, out); }
+  catch (const std::exception& e) { set_error(std::string("history_load: ") + e.what()); return ARAP_ERR_IO; }
 }
 
 // Same token stream as RecordDeformation: default ostream float formatting, one space after every token.
@@ -379,7 +408,13 @@ extern "C" int arap_replay(arap_ctx* ctx, const arap_history* h, int rebuild_gra
         if ((rc = push_blocks(ctx, blocks, types))) return rc;
       }
       const auto& mv = h->mouse_movements[move_idx];
-      const float* axis = &h->twist_axis[4 * (size_t)move_idx];
+      static const float no_axis[4] = {0.f, 0.f, 0.f, 0.f};
+      const float* axis = no_axis;
+      if (op == 2) {   // the axis of a twist is read only for twists, and only when the file really has one for this move
+        if (h->twist_axis.size() < 4 * ((size_t)move_idx + 1)) { set_error("replay: twist move without a Twist_Axis entry"); return ARAP_ERR_IO; }
+        axis = &h->twist_axis[4 * (size_t)move_idx];
+        if (!(axis[0] * axis[0] + axis[1] * axis[1] + axis[2] * axis[2] > 0.f)) { set_error("replay: zero or non-finite twist axis"); return ARAP_ERR_IO; }
+      }
       for (size_t s = 0; s + 2 < mv.size() + 0 && s < mv.size(); s += 3) {
         int on_center = 0;
         if (op == 1) { if ((rc = arap_aim_translate(ctx, &mv[s]))) return rc; on_center = 1; }

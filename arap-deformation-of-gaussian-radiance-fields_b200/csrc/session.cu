@@ -351,8 +351,12 @@ extern "C" int arap_grid_build(arap_ctx* ctx) {
     DBuf<float> p2, r2, s2, o2, h2;
     TRY(p2.alloc(ctx->pos.n)); TRY(r2.alloc(ctx->rot.n)); TRY(s2.alloc(ctx->scale.n)); TRY(o2.alloc(ctx->opacity.n)); TRY(h2.alloc(ctx->shs.n));
     TRY(arapk_permute_gaussians(ctx->N, new_idx.p, ctx->pos.p, ctx->rot.p, ctx->scale.p, ctx->opacity.p, ctx->shs.p, p2.p, r2.p, s2.p, o2.p, h2.p, st));
-    ARAP_CUDA_TRY(cudaStreamSynchronize(st));
-    ctx->pos.swap(p2); ctx->rot.swap(r2); ctx->scale.swap(s2); ctx->opacity.swap(o2); ctx->shs.swap(h2);
+    // copied back rather than swapped: the pointers of arap_device_view stay valid from arap_set_gaussians on
+    const size_t n = (size_t)ctx->N * sizeof(float);
+    ARAP_CUDA_TRY(cudaMemcpyAsync(ctx->pos.p, p2.p, n * 3, cudaMemcpyDeviceToDevice, st)); ARAP_CUDA_TRY(cudaMemcpyAsync(ctx->rot.p, r2.p, n * 4, cudaMemcpyDeviceToDevice, st));
+    ARAP_CUDA_TRY(cudaMemcpyAsync(ctx->scale.p, s2.p, n * 3, cudaMemcpyDeviceToDevice, st)); ARAP_CUDA_TRY(cudaMemcpyAsync(ctx->opacity.p, o2.p, n, cudaMemcpyDeviceToDevice, st));
+    ARAP_CUDA_TRY(cudaMemcpyAsync(ctx->shs.p, h2.p, n * 48, cudaMemcpyDeviceToDevice, st));
+    ARAP_CUDA_TRY(cudaStreamSynchronize(st));   // the temporaries are freed on scope exit
   }
   ARAP_CUDA_TRY(cudaMemcpyAsync(ctx->scale_backup.p, ctx->scale.p, (size_t)ctx->N * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   // gs_init_grid_idx in the new order (GV:4136-4145)
@@ -649,12 +653,17 @@ extern "C" int arap_set_blocks(arap_ctx* ctx, int n_blocks, const int* block_off
   CTX_CHECK(ctx);
   if (!ctx->graph_ready) { set_error("set_blocks: graph not built"); return ARAP_ERR_STATE; }
   const int M = ctx->M, k = ctx->k; cudaStream_t st = ctx->stream;
+  if (n_blocks < 0 || (n_blocks > 0 && (!block_off || !block_nodes || !block_types))) { set_error("set_blocks: null block arrays"); return ARAP_ERR_INVALID; }
+  for (int b = 0; b < n_blocks; b++) {   // validate everything before any state changes
+    if (block_off[b] < 0 || block_off[b + 1] < block_off[b]) { set_error("set_blocks: block offsets must be non-decreasing"); return ARAP_ERR_INVALID; }
+    if (block_types[b] < -1 || block_types[b] > 1) { set_error("set_blocks: block type must be -1, 0 or 1"); return ARAP_ERR_INVALID; }
+    for (int t = block_off[b]; t < block_off[b + 1]; t++)
+      if (block_nodes[t] >= (uint32_t)M) { set_error("set_blocks: node index out of range"); return ARAP_ERR_INVALID; }
+  }
   ARAP_CUDA_TRY(cudaMemsetAsync(ctx->warm_d.p, 0, 8 * sizeof(double), st));   // the unknown set may change: no warm start for the next solve
   ctx->blocks.clear(); ctx->block_types.clear();
   for (int b = 0; b < n_blocks; b++) {
-    std::vector<uint32_t> v(block_nodes + block_off[b], block_nodes + block_off[b + 1]);
-    for (uint32_t x : v) if ((int)x >= M) { set_error("set_blocks: node index out of range"); return ARAP_ERR_INVALID; }
-    ctx->blocks.push_back(std::move(v)); ctx->block_types.push_back(block_types[b]);
+    ctx->blocks.emplace_back(block_nodes + block_off[b], block_nodes + block_off[b + 1]); ctx->block_types.push_back(block_types[b]);
   }
   std::vector<uint8_t> is_static(M, 0), is_free(M, 1);
   std::vector<int> mult(M, 0), entries;
@@ -810,8 +819,9 @@ extern "C" int arap_apply(arap_ctx* ctx) {
     TRY(arapk_rotate_sample_shs(ctx->S, k, ctx->sample_rows.wf.p, ctx->sample_rows.idx.p, ctx->node_q.p, ctx->sample_static.p, ctx->aim_feature.p, st));
   }
   if (tm) cudaEventRecord(ctx->ev[5], st);
-  ctx->node_pos.swap(ctx->node_next);
-  ARAP_CUDA_TRY(cudaMemcpyAsync(ctx->aim.p, ctx->node_pos.p, (size_t)M * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));  // ReloadAimPositions
+  // node_pos keeps its address (arap_device_view.node_pos may be cached by the viewer): the double buffer is copied back
+  ARAP_CUDA_TRY(cudaMemcpyAsync(ctx->node_pos.p, ctx->node_next.p, (size_t)M * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  ARAP_CUDA_TRY(cudaMemcpyAsync(ctx->aim.p, ctx->node_next.p, (size_t)M * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));  // ReloadAimPositions
   ctx->solved = false;  // resetRT: transforms are per-step increments (GV:1522)
   return ARAP_OK;
 }

@@ -420,6 +420,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveDev S) {
       }
     }
 
+    if (flag & 1) {   // numeric breakdown (uniform over the grid): take a zero step, see solve_smem.cu
+      for (int t = gthread; t < NU; t += nthreads) S.h[t] = 0.0;
+      grid.sync();
+    }
     // ---- step halving (Deform.cpp:144-156)
     bool accepted = false;
     for (double alpha_ls = 1.0; alpha_ls > 1e-15; alpha_ls *= 0.5) {
@@ -429,7 +433,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveDev S) {
       red[1] = hh_l; red[2] = 0.0;
       grid_reduce(grid, S, phase, red);
       const double E1 = red[0];
-      if (E1 > E0) {
+      if (!(E1 <= E0)) {   // also rejects a non-finite energy
         for (int t = gthread; t < NU; t += nthreads) S.h[t] *= 0.5;
         halvings++;
         normh = 0.5 * sqrt(red[1]);

@@ -856,6 +856,12 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_solve_smem(SolveDev S, unsign
         if (it == S.max_cg - 1) flag |= 2;
       }
     }
+    if (flag & 1) {   // numeric breakdown (uniform over the grid: pHp / rr come out of the grid reduction): h may hold NaN.  Take a zero
+      // step instead — x keeps the last good iterate (identity on the first system), the loop ends through the |h| test, the
+      // caller sees flag bit 0, and arap_apply gets finite transforms.
+      for (int t = tid; t < NU; t += SM_THREADS) L.hs[t] = 0.0;
+      __syncthreads();
+    }
     if (S.warm && gn < SOLVE_WARM_MAX)   // this system's solution (before step halving) seeds the next drag step
       for (int t = tid; t < NU; t += SM_THREADS) warm_h[(size_t)((t / 12) * B + b) * 12 + (t % 12)] = L.hs[t];
 
@@ -876,7 +882,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_solve_smem(SolveDev S, unsign
       red[0] = rows_smem<K, 0>(S, L, L.zs, S.x, nullptr, 0.0);
       barrier_reduce<1>(S, counter, phase, red);
       const double E1 = red[0];
-      if (E1 > E0) {
+      if (!(E1 <= E0)) {   // also rejects a non-finite energy (the reference's `>` would accept NaN)
         for (int t = tid; t < NU; t += SM_THREADS) L.hs[t] *= 0.5;
         halvings++;
         normh = 0.5 * sqrt(hh);

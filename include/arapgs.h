@@ -64,7 +64,8 @@ typedef struct arap_params {
                           system k reaches the result damped by the remaining Gauss-Newton steps, ~ newton_eta0 x (last step
                           length); measured node-transform deviation from the reference's direct solves stays at the 1e-11 level
                           of the cg_tol-only rule with ~25% fewer PCG iterations (1e-4 is where the parity bar is reached). */
-  int warm_start;      /* 1 (default): every PCG solve of a drag step starts from the solution the previous step found for the same
+  int warm_start;      /* (shared-memory solver only; the global-memory fallback kernel always starts from zero)
+                          1 (default): every PCG solve of a drag step starts from the solution the previous step found for the same
                           Gauss-Newton system, scaled by an exact line search (zero after arap_set_blocks / a graph build).  Same stopping rule, same answer to the
                           solver tolerance, fewer iterations while the drag is coherent.  0 = start from zero like the first step;
                           n > 1 = warm-start only the first n - 1 systems of a step. */
@@ -100,7 +101,13 @@ typedef struct arap_grid_info {
 } arap_grid_info;
 
 /* Borrowed device pointers: exactly the Rasterizer::forward /
- * forward3d_grid argument arrays (GV:1106-1112, 4159-4186). */
+ * forward3d_grid argument arrays (GV:1106-1112, 4159-4186).
+ * Validity: pos / rot / scale / opacity / shs keep their addresses from arap_set_gaussians until the next
+ * arap_set_gaussians or arap_destroy (arap_grid_build re-orders them in place, arap_apply / arap_step update them in place).
+ * node_pos / node_rot / node_trans are stable from a graph build (arap_graph_build_* / arap_replay with rebuild) until the
+ * next one; every arap_apply writes the new node positions to the same address.  The grid arrays (valid_grid ..
+ * ada_lpf_ratio, sample_pos, end_points) are re-allocated by arap_grid_build and arap_grid_update_lists; aim_feature /
+ * aim_opacity by arap_grid_build + arap_grid_eval.  Fetch the view again after any of those calls. */
 typedef struct arap_device_view {
   long long n_gaussians;
   float* pos;      /* N x 3 */

@@ -94,3 +94,29 @@ def test_errors_are_reported_not_fatal(pkg, tmp_path):
     (tmp_path / "bad.txt").write_text("0 Nodes: 3 1 2")
     with pytest.raises(pkg.ArapError):
         pkg.History.load(tmp_path / "bad.txt")
+
+
+def test_untrusted_deform_txt_is_rejected_with_a_status(pkg, golden, tmp_path):
+    """deform.txt is untrusted input: inconsistent per-move sections (e.g. fewer Twist_Axis rows than moves, which the replay
+    would index out of bounds) and absurd counts must end in ARAP_ERR_IO, never in a crash across the C boundary."""
+    import pytest
+    tok = open(golden / "pinocchio_deform.txt").read().split()
+    i = tok.index("Twist_Axis:")
+    short = tok[:i] + ["Twist_Axis:", "1"] + tok[i + 2:i + 6]                 # 3 moves, 1 axis
+    (tmp_path / "short_axis.txt").write_text(" ".join(short) + " ")
+    with pytest.raises(pkg.ArapError) as e:
+        pkg.History.load(tmp_path / "short_axis.txt")
+    assert e.value.code == 4 and "per-move sections" in str(e.value)
+    huge = list(tok); huge[tok.index("Block_Nodes:") + 2] = "2000000000"      # block size far beyond the file size
+    (tmp_path / "huge.txt").write_text(" ".join(huge) + " ")
+    with pytest.raises(pkg.ArapError) as e:
+        pkg.History.load(tmp_path / "huge.txt")
+    assert e.value.code == 4
+    huge2 = list(tok); huge2[tok.index("Nodes:") + 1] = "-5"
+    (tmp_path / "neg.txt").write_text(" ".join(huge2) + " ")
+    with pytest.raises(pkg.ArapError):
+        pkg.History.load(tmp_path / "neg.txt")
+    ops = list(tok); j = tok.index("Operation_Types:"); ops[j + 2] = "9"      # unknown op code
+    (tmp_path / "ops.txt").write_text(" ".join(ops) + " ")
+    with pytest.raises(pkg.ArapError):
+        pkg.History.load(tmp_path / "ops.txt")
