@@ -56,7 +56,8 @@ class DeviceView(C.Structure):
                 ("node_rot", C.c_void_p), ("node_trans", C.c_void_p), ("n_samples", C.c_longlong),
                 ("sample_pos", C.c_void_p), ("aim_feature", C.c_void_p), ("aim_opacity", C.c_void_p),
                 ("valid_grid", C.c_void_p), ("grid_gs_prefix_sum", C.c_void_p), ("grided_gs_idx", C.c_void_p),
-                ("gs_init_grid_idx", C.c_void_p), ("ada_lpf_ratio", C.c_void_p), ("end_points", C.c_void_p)]
+                ("gs_init_grid_idx", C.c_void_p), ("ada_lpf_ratio", C.c_void_p), ("end_points", C.c_void_p),
+                ("empty_grid", C.c_void_p), ("cur_feature", C.c_void_p), ("cur_opacity", C.c_void_p)]
 
 
 _lib = None
@@ -297,6 +298,20 @@ class Session:
         check(lib().arap_download_grid(self._ctx, *(_ptr(out[k]) for k in ("valid", "prefix", "lists", "sample_pos", "gs_init_grid_idx"))))
         return out
 
+    def ada_lpf_update(self):
+        check(lib().arap_ada_lpf_update(self._ctx))
+
+    def download_ada_lpf(self):
+        G = self.grid_info()["grid_num"]
+        out = np.zeros((G ** 3, 9), f32)
+        check(lib().arap_download_ada_lpf(self._ctx, _ptr(out)))
+        return out
+
+    def download_empty_grid(self):
+        out = np.zeros(self.grid_info()["valid_cells"], i32)
+        check(lib().arap_download_empty_grid(self._ctx, _ptr(out)))
+        return out
+
     def download_features(self, which=0):
         S = self.grid_info()["samples"]
         f, o = np.zeros((S, 48), f32), np.zeros(S, f32)
@@ -355,6 +370,11 @@ class Session:
         t = _np(types, i32) if len(blocks) else np.zeros(1, i32)
         check(lib().arap_set_blocks(self._ctx, len(blocks), _ptr(off), _ptr(nodes), _ptr(t)))
 
+    def download_end_points(self):
+        e = np.zeros((self.N, 18), f32)
+        check(lib().arap_download_end_points(self._ctx, _ptr(e)))
+        return e
+
     def static_flags(self):
         g, s = np.zeros(self.N, u8), np.zeros(self.grid_info()["samples"], u8)
         check(lib().arap_download_static_flags(self._ctx, _ptr(g), _ptr(s)))
@@ -410,6 +430,15 @@ class Session:
         pos, rot, trans = np.zeros((self.M, 3), f32), np.zeros((self.M, 9), f64), np.zeros((self.M, 3), f64)
         check(lib().arap_download_nodes(self._ctx, _ptr(pos), _ptr(rot), _ptr(trans)))
         return pos, rot, trans
+
+    SETUP_STAGES = ("scene_aabb", "cell_assign", "reorder", "footprint_lists", "samples", "grid_eval", "fps", "node_graph",
+                    "knn_ends", "knn_samples", "tile_tables")
+
+    def setup_timing(self):
+        """Device ms of the last run of every set-up / stroke-end stage (arap_setup_timing)."""
+        ms = np.zeros(len(self.SETUP_STAGES), f32)
+        check(lib().arap_setup_timing(self._ctx, _ptr(ms), len(ms)))
+        return {k: float(v) for k, v in zip(self.SETUP_STAGES, ms)}
 
     def enable_timing(self, on=True):
         check(lib().arap_enable_timing(self._ctx, int(bool(on))))

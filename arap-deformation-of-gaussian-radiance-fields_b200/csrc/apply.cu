@@ -28,7 +28,7 @@ namespace arapgs {
 
 // ------------------------------------------------------------------ node xf
 __global__ void k_node_xf(int M, const double* __restrict__ rot, const double* __restrict__ trans,
-                          const float* __restrict__ node_pos, NodeXf* __restrict__ out) {
+                          const float* __restrict__ node_pos, NodeXf* __restrict__ out, NodeXf32* __restrict__ out32) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M) return;
   NodeXf x;
@@ -42,6 +42,17 @@ __global__ void k_node_xf(int M, const double* __restrict__ rot, const double* _
   }
   x.pad = 0.f;
   out[i] = x;
+  if (out32) {   // tolerance-mode record: A - I (row-major), t, g as floats
+    NodeXf32 y;
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) y.dA[3 * r + c] = (float)(x.A[c * 3 + r] - (r == c ? 1.0 : 0.0));
+#pragma unroll
+    for (int t = 0; t < 3; t++) { y.t[t] = (float)trans[3 * i + t]; y.g[t] = x.g[t]; }
+    y.pad = 0.f;
+    out32[i] = y;
+  }
 }
 
 // ------------------------------------------------------------------ LBS
@@ -487,6 +498,411 @@ k_fit_gaussians(long long N, const float* __restrict__ ends, const float* __rest
   }
 }
 
+// ------------------------------------------------------------------ tolerance-mode skinning (lbs_mode = 3)
+// The bit-faithful kernels above reproduce the reference's `float += double` chain and are bound by the shared-memory
+// return path: every (point, neighbour) pair needs a 108-byte fp64 record in registers (27 wavefronts per warp and
+// neighbour).  north_star's bar for means / covariances is 1e-5 relative, not bit equality, so this mode evaluates the
+// same skinning  p' = sum_j w_j (A_j (p - g_j) + g_j + t_j)  as
+//     p' = p + sum_j w_j ((A_j - I)(p - c) + t_j - (A_j - I)(g_j - c))                   (sum_j w_j = 1)
+// with c a reference point next to p: every float operand is a small displacement (|A - I| ~ 1e-2, |p - c| ~ 1e-1,
+// |t| ~ 1e-3), so float rounding of the products is ~1e-10 absolute — 2-3 orders below the ulp of p — and the result is
+// the correctly rounded exact skinning in all but a few per cent of the coordinates.  It differs from the reference's
+// chain by the chain's own rounding noise (~1 ulp of p).
+//
+// The order of the neighbours no longer matters, which is what makes the kernels fast: neighbour sets of nearby points
+// overlap almost completely (measured on the 6M / 16k-node workload: the 60 (end point, neighbour) pairs of a Gaussian
+// touch 12.6 distinct nodes on average, max 20; the 320 pairs of 32 consecutive samples about as many), so the tables are
+// re-organised at set-up into UNIONS with dense float weights (zero where a point does not have the node):
+//   * samples: one union per 32-row block; every lane of the warp reads the same 48-byte record (shared-memory broadcast,
+//     one wavefront per LDS.128) and its own weight — ~14 x 3 wavefronts per warp instead of 10 x 27;
+//   * end points: one union per Gaussian, a thread skins its six end points against each record it loads.
+// Per-step float node records NodeXf32 = [A - I | t | g] are written next to the fp64 ones by k_node_xf.
+__device__ __forceinline__ void stage32(const NodeXf32* __restrict__ nd, float cx, float cy, float cz, float4& r0, float4& r1, float4& r2) {
+  const float4* n = reinterpret_cast<const float4*>(nd);
+  const float4 v0 = __ldg(n), v1 = __ldg(n + 1), v2 = __ldg(n + 2), v3 = __ldg(n + 3);
+  const float g0 = v3.x - cx, g1 = v3.y - cy, g2 = v3.z - cz;
+  r0 = make_float4(v0.x, v0.y, v0.z, v2.y - fmaf(v0.z, g2, fmaf(v0.y, g1, v0.x * g0)));
+  r1 = make_float4(v0.w, v1.x, v1.y, v2.z - fmaf(v1.y, g2, fmaf(v1.x, g1, v0.w * g0)));
+  r2 = make_float4(v1.z, v1.w, v2.x, v2.w - fmaf(v2.x, g2, fmaf(v1.w, g1, v1.z * g0)));
+}
+
+// ---- samples (and any other row family): one union per 32-row block ----------------------------------------------------
+// Tables: boff[nblk + 1] (rows of the block's union), blist[row] (uint16 node id), bw[row * 32 + lane] (float weight of the
+// row's node for the block's lane-th point, 0 if it is not among the point's k neighbours).
+constexpr int SU_WARPS = 4;
+constexpr int SU_CHUNK = 16;
+
+__global__ void __launch_bounds__(SU_WARPS * 32, 6)
+k_lbs_union32(const float* in, float* out, long long P, const int* __restrict__ boff, const uint16_t* __restrict__ blist,
+              const float* __restrict__ bw, const NodeXf32* __restrict__ nodes, const uint8_t* __restrict__ skip, int group) {
+  __shared__ float4 s_rec[SU_WARPS][SU_CHUNK * 3];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long blk = (long long)blockIdx.x * SU_WARPS + warp;
+  const long long i = blk * 32 + lane;
+  if (blk * 32 >= P) return;
+  const bool live = i < P && !(skip && skip[i / group]);
+  if (!__any_sync(0xffffffffu, live)) return;
+  const int off = boff[blk], cnt = boff[blk + 1] - off;
+  const float cx = in[3 * blk * 32], cy = in[3 * blk * 32 + 1], cz = in[3 * blk * 32 + 2];   // the block's reference point
+  float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+  if (live) { p0 = in[3 * i]; p1 = in[3 * i + 1]; p2 = in[3 * i + 2]; }
+  float4 T0 = make_float4(0.f, 0.f, 0.f, 0.f), T1 = T0, T2 = T0;
+  float4* rec = s_rec[warp];
+  const float* wrow = bw + (long long)off * 32 + lane;
+  // Chunks of SU_CHUNK union rows (one chunk covers almost every block).  All weights of a chunk are requested at once, the
+  // next chunk's before the current one is consumed: the kernel is a stream of independent 128-byte row reads and lives on
+  // how many of them are in flight, not on occupancy.
+  float wc[SU_CHUNK];
+#pragma unroll
+  for (int t = 0; t < SU_CHUNK; t++) wc[t] = t < cnt ? __ldg(wrow + (long long)t * 32) : 0.f;
+  for (int base = 0; base < cnt; base += SU_CHUNK) {
+    const int n = min(SU_CHUNK, cnt - base);
+    __syncwarp();
+    if (lane < n) {
+      float4 r0, r1, r2;
+      stage32(nodes + blist[off + base + lane], cx, cy, cz, r0, r1, r2);
+      rec[3 * lane] = r0; rec[3 * lane + 1] = r1; rec[3 * lane + 2] = r2;
+    }
+    float wn[SU_CHUNK];
+#pragma unroll
+    for (int t = 0; t < SU_CHUNK; t++) wn[t] = base + SU_CHUNK + t < cnt ? __ldg(wrow + (long long)(base + SU_CHUNK + t) * 32) : 0.f;
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < SU_CHUNK; t++) {
+      if (t < n) {
+        const float w = wc[t];
+        const float4 a = rec[3 * t], b = rec[3 * t + 1], c = rec[3 * t + 2];
+        T0.x = fmaf(w, a.x, T0.x); T0.y = fmaf(w, a.y, T0.y); T0.z = fmaf(w, a.z, T0.z); T0.w = fmaf(w, a.w, T0.w);
+        T1.x = fmaf(w, b.x, T1.x); T1.y = fmaf(w, b.y, T1.y); T1.z = fmaf(w, b.z, T1.z); T1.w = fmaf(w, b.w, T1.w);
+        T2.x = fmaf(w, c.x, T2.x); T2.y = fmaf(w, c.y, T2.y); T2.z = fmaf(w, c.z, T2.z); T2.w = fmaf(w, c.w, T2.w);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < SU_CHUNK; t++) wc[t] = wn[t];
+  }
+  if (!live) return;
+  const float q0 = p0 - cx, q1 = p1 - cy, q2 = p2 - cz;
+  out[3 * i] = p0 + fmaf(T0.z, q2, fmaf(T0.y, q1, fmaf(T0.x, q0, T0.w)));
+  out[3 * i + 1] = p1 + fmaf(T1.z, q2, fmaf(T1.y, q1, fmaf(T1.x, q0, T1.w)));
+  out[3 * i + 2] = p2 + fmaf(T2.z, q2, fmaf(T2.y, q1, fmaf(T2.x, q0, T2.w)));
+}
+
+// Set-up of the block unions.  One warp per 32-row block; the distinct node ids of the block's 32 k neighbours are
+// extracted in ascending order by repeated warp-minimum.  FILL = false: counts only (boff is their exclusive scan).
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+k_sunion_build(long long rows, int k, const uint16_t* __restrict__ ridx, const float* __restrict__ wf, const double* __restrict__ wd,
+               int* __restrict__ bcnt, const int* __restrict__ boff, uint16_t* __restrict__ blist, float* __restrict__ bw) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long blk = (long long)blockIdx.x * 4 + warp;
+  if (blk * 32 >= rows) return;
+  const long long i = blk * 32 + lane;
+  const long long base = blk * (long long)(k * 32) + lane;
+  int id[KNN_MAX]; float w[KNN_MAX];
+#pragma unroll
+  for (int j = 0; j < KNN_MAX; j++) {
+    const bool ok = j < k && i < rows;
+    id[j] = ok ? (int)ridx[base + j * 32] : 0x7fffffff;
+    w[j] = (FILL && ok) ? (wf ? wf[base + j * 32] : (float)wd[base + j * 32]) : 0.f;
+  }
+  int last = -1, cnt = 0;
+  const long long off = FILL ? boff[blk] : 0;
+  for (;;) {
+    int cand = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < KNN_MAX; j++) if (id[j] > last && id[j] < cand) cand = id[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+    if (cand == 0x7fffffff) break;
+    if (FILL) {
+      float mine = 0.f;
+#pragma unroll
+      for (int j = 0; j < KNN_MAX; j++) if (id[j] == cand) mine += w[j];
+      if (lane == 0) blist[off + cnt] = (uint16_t)cand;
+      bw[(off + cnt) * 32 + lane] = mine;
+    }
+    last = cand; cnt++;
+  }
+  if (!FILL && lane == 0) bcnt[blk] = cnt;
+}
+
+// ---- end points: one union per Gaussian, fused with the six-point fit and the SH rotation ------------------------------
+// Tables, blocked by 32 Gaussians (gblk = g / 32; rows = positions t of the union, padded to the block's longest union):
+//   uoff[ngblk + 1]                      first row of a block
+//   woff[ngblk + 1]                      first slot word of a block (ceil(rows / 4) words per block)
+//   usw[(woff + t / 4) * 32 + lane]      four one-byte slots per word: index into the tile's staged node list
+//   unode[(uoff + t) * 32 + lane]        the node id itself (read only by tiles whose node list overflows the staging area)
+//   uw[((uoff + t) * 6 + e) * 32 + lane] float weight of the row's node for end point e (0 if absent; padding rows are all 0)
+//   gtile_nodes[tile * GT_CAP + slot], gtile_cnt[tile]   distinct nodes of a 128-Gaussian tile (0 = more than GT_CAP)
+constexpr int GT_CAP = 256;
+constexpr int GU_MAX = 60;   // a Gaussian has 6 k <= 72 pairs; unions above GU_MAX rows fail the build (never seen: max 20 on the bench scene)
+
+// distinct nodes of the Gaussian's 6 k pairs, ascending, with the six weights of each; returns the count
+__device__ __forceinline__ int gaussian_union(long long g, int k, const uint16_t* __restrict__ ridx, const double* __restrict__ rw,
+                                              uint16_t* un, float (*uwt)[6]) {
+  int cnt = 0;
+  for (int e = 0; e < 6; e++) {
+    const long long row = g * 6 + e;
+    const long long base = (row >> 5) * (long long)(k * 32) + (row & 31);
+    for (int j = 0; j < k; j++) {
+      const uint16_t n = ridx[base + j * 32];
+      const float w = (float)rw[base + j * 32];
+      int pos = 0;
+      while (pos < cnt && un[pos] < n) pos++;
+      if (pos == cnt || un[pos] != n) {
+        if (cnt >= GU_MAX) return -1;
+        for (int m = cnt; m > pos; m--) { un[m] = un[m - 1]; for (int c = 0; c < 6; c++) uwt[m][c] = uwt[m - 1][c]; }
+        un[pos] = n; for (int c = 0; c < 6; c++) uwt[pos][c] = 0.f;
+        cnt++;
+      }
+      uwt[pos][e] += w;
+    }
+  }
+  return cnt;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+k_gunion_build(long long N, int k, const uint16_t* __restrict__ ridx, const double* __restrict__ rw, int* __restrict__ ucnt,
+               int* __restrict__ err, const int* __restrict__ uoff, const int* __restrict__ woff, uint32_t* __restrict__ usw,
+               uint16_t* __restrict__ unode, float* __restrict__ uw, uint16_t* __restrict__ gtile_cnt, uint16_t* __restrict__ gtile_nodes) {
+  __shared__ uint32_t bm[2048];
+  __shared__ uint16_t pre[2048];
+  __shared__ int wsum[4];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const long long tile = blockIdx.x;
+  const long long g = tile * 128 + tid;
+  const long long gblk = g >> 5;
+  uint16_t un[GU_MAX]; float uwt[GU_MAX][6];
+  int cnt = 0;
+  if (g < N) cnt = gaussian_union(g, k, ridx, rw, un, uwt);
+  if (cnt < 0) { atomicExch(err, 1); cnt = 0; }
+  int mx = cnt;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (!FILL) { if (lane == 0 && gblk * 32 < N) ucnt[gblk] = mx; return; }
+  // tile slot list: bitmap of the node ids, ranked by a popcount prefix (as k_build_tiles)
+  for (int v = tid; v < 2048; v += 128) bm[v] = 0u;
+  __syncthreads();
+  for (int t = 0; t < cnt; t++) atomicOr(&bm[un[t] >> 5], 1u << (un[t] & 31));
+  __syncthreads();
+  constexpr int WPT = 2048 / 128;
+  int c = 0;
+#pragma unroll
+  for (int v = 0; v < WPT; v++) c += __popc(bm[tid * WPT + v]);
+  int inc = c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+  if (lane == 31) wsum[tid >> 5] = inc;
+  __syncthreads();
+  int off = inc - c, total = 0;
+#pragma unroll
+  for (int v = 0; v < 4; v++) { if (v < (tid >> 5)) off += wsum[v]; total += wsum[v]; }
+  const bool ok = total <= GT_CAP;
+  int run = off;
+#pragma unroll
+  for (int v = 0; v < WPT; v++) {
+    const int wd = tid * WPT + v;
+    pre[wd] = (uint16_t)run;
+    uint32_t b = bm[wd];
+    while (b) {
+      const int bit = __ffs(b) - 1; b &= b - 1;
+      if (ok) gtile_nodes[tile * GT_CAP + run] = (uint16_t)(wd * 32 + bit);
+      run++;
+    }
+  }
+  if (tid == 0) gtile_cnt[tile] = ok ? (uint16_t)total : (uint16_t)0;
+  __syncthreads();
+  if (gblk * 32 >= N) return;
+  const long long r0 = uoff[gblk], w0 = woff[gblk];
+  uint32_t word = 0u;
+  for (int t = 0; t < mx; t++) {
+    const bool have = t < cnt;
+    const uint16_t n = have ? un[t] : (cnt ? un[0] : 0);
+    const int slot = (ok && (have || cnt)) ? pre[n >> 5] + __popc(bm[n >> 5] & ((1u << (n & 31)) - 1u)) : 0;
+    word |= (uint32_t)slot << ((t & 3) * 8);
+    if ((t & 3) == 3 || t == mx - 1) { usw[(w0 + (t >> 2)) * 32 + lane] = word; word = 0u; }
+    unode[(r0 + t) * 32 + lane] = n;
+    for (int e = 0; e < 6; e++) uw[((r0 + t) * 6 + e) * 32 + lane] = have ? uwt[t][e] : 0.f;
+  }
+}
+
+__global__ void k_words_of_rows(long long n, const int* __restrict__ rows, int* __restrict__ words) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) words[i] = (rows[i] + 3) >> 2;
+}
+
+__global__ void __launch_bounds__(FIT_TILE, 4)
+k_apply_union(long long N, const NodeXf32* __restrict__ nodes, const uint16_t* __restrict__ gtile_cnt,
+              const uint16_t* __restrict__ gtile_nodes, const int* __restrict__ uoff, const int* __restrict__ woff,
+              const uint32_t* __restrict__ usw, const uint16_t* __restrict__ unode, const float* __restrict__ uw, float* ends,
+              const float* __restrict__ scale_backup, const uint8_t* __restrict__ is_static, float* __restrict__ pos,
+              float* __restrict__ rot, float* __restrict__ scale, float* __restrict__ shs) {
+  extern __shared__ float4 s_sh4[];                                        // FIT_TILE x FIT_PITCH4 float4
+  float* s_end = reinterpret_cast<float*>(s_sh4 + FIT_TILE * FIT_PITCH4);  // FIT_TILE x END_PITCH
+  float4* s_rec = reinterpret_cast<float4*>(s_end + FIT_TILE * END_PITCH); // GT_CAP x 3 float4
+  __shared__ uint8_t s_static[FIT_TILE];
+
+  const long long tile = blockIdx.x;
+  const long long g0 = tile * FIT_TILE;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int rows = (int)min((long long)FIT_TILE, N - g0);
+  const long long g = g0 + tid;
+  s_static[tid] = (tid < rows) ? (is_static ? is_static[g] : 0) : 1;
+  const int tcnt = gtile_cnt[tile];
+  float* gend = ends + g0 * 18;
+  const float cx = gend[0], cy = gend[1], cz = gend[2];   // tile reference point: its first end point
+  for (int v = tid; v < tcnt; v += FIT_TILE) {
+    float4 r0, r1, r2;
+    stage32(nodes + gtile_nodes[tile * GT_CAP + v], cx, cy, cz, r0, r1, r2);
+    s_rec[3 * v] = r0; s_rec[3 * v + 1] = r1; s_rec[3 * v + 2] = r2;
+  }
+  const int nend = rows * 18;
+  for (int v = tid * 2; v < nend; v += FIT_TILE * 2) {
+    const int r = v / 18, c = v - r * 18;
+    const float2 x = *reinterpret_cast<const float2*>(gend + v);
+    s_end[r * END_PITCH + c] = x.x; s_end[r * END_PITCH + c + 1] = x.y;
+  }
+  float4 o4 = make_float4(1.f, 0.f, 0.f, 0.f);
+  float sb0 = 1.f, sb1 = 1.f, sb2 = 1.f;
+  const long long gblk = g >> 5;
+  const bool act = tid < rows && !s_static[tid];   // own flag: written by this thread above
+  int ur0 = 0, ucnt = 0, uw0 = 0;
+  if (tid < rows) { ur0 = uoff[gblk]; ucnt = uoff[gblk + 1] - ur0; uw0 = woff[gblk]; }
+  if (act) { o4 = ldg4(rot + 4 * g); sb0 = scale_backup[3 * g]; sb1 = scale_backup[3 * g + 1]; sb2 = scale_backup[3 * g + 2]; }
+  __syncthreads();
+  const float4* gsh = reinterpret_cast<const float4*>(shs + g0 * SH_FLOATS);
+  const int cp_r0 = tid / 12, cp_c4 = tid - 12 * cp_r0;
+  // The union rows are consumed in groups of four (one slot word); a group's 24 weights are requested one group ahead, the
+  // first group before the bulk SH copy (responses return roughly in issue order per SM).
+  const float* wrow = uw + (long long)ur0 * 6 * 32 + lane;
+  const uint32_t* srow = usw + (long long)uw0 * 32 + lane;
+  float wn[4][6];
+  uint32_t wordn = 0u;
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int ep = 0; ep < 6; ep++) wn[r][ep] = 0.f;
+  if (act && ucnt > 0) {
+    wordn = __ldg(srow);
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+      if (r < ucnt)
+#pragma unroll
+        for (int ep = 0; ep < 6; ep++) wn[r][ep] = __ldg(wrow + (r * 6 + ep) * 32);
+  }
+  if (tid < 120) {
+#pragma unroll
+    for (int t = 0; t < 13; t++) {
+      const int r = cp_r0 + 10 * t;
+      if (r < rows && !s_static[r]) cp_async16(s_sh4 + r * FIT_PITCH4 + cp_c4, gsh + tid + 120 * t);
+    }
+  }
+  cp_async_commit();
+
+  float Rs[3][3];
+  if (act) {
+    float* e = s_end + tid * END_PITCH;
+    // ---- end-point skinning (tolerance mode): p' = p + sum over the Gaussian's union of w (rec . [p - c; 1])
+    float q[18], sd[18];
+#pragma unroll
+    for (int v = 0; v < 18; v++) { q[v] = e[v] - (v % 3 == 0 ? cx : v % 3 == 1 ? cy : cz); sd[v] = 0.f; }
+    for (int tb = 0; tb < ucnt; tb += 4) {
+      float w[4][6];
+      const uint32_t word = wordn;
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int ep = 0; ep < 6; ep++) w[r][ep] = wn[r][ep];
+      if (tb + 4 < ucnt) {   // next group
+        wordn = __ldg(srow + (long long)((tb + 4) >> 2) * 32);
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+          if (tb + 4 + r < ucnt)
+#pragma unroll
+            for (int ep = 0; ep < 6; ep++) wn[r][ep] = __ldg(wrow + ((long long)(tb + 4 + r) * 6 + ep) * 32);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        if (tb + r < ucnt) {
+          const unsigned slot = (word >> (r * 8)) & 0xffu;
+          float4 a, b, c;
+          if (tcnt) { a = s_rec[3 * slot]; b = s_rec[3 * slot + 1]; c = s_rec[3 * slot + 2]; }
+          else stage32(nodes + unode[((long long)ur0 + tb + r) * 32 + lane], cx, cy, cz, a, b, c);   // tile's node list overflowed (uniform per CTA)
+#pragma unroll
+          for (int ep = 0; ep < 6; ep++) {
+            const float d0 = fmaf(a.z, q[3 * ep + 2], fmaf(a.y, q[3 * ep + 1], fmaf(a.x, q[3 * ep], a.w)));
+            const float d1 = fmaf(b.z, q[3 * ep + 2], fmaf(b.y, q[3 * ep + 1], fmaf(b.x, q[3 * ep], b.w)));
+            const float d2 = fmaf(c.z, q[3 * ep + 2], fmaf(c.y, q[3 * ep + 1], fmaf(c.x, q[3 * ep], c.w)));
+            sd[3 * ep] = fmaf(w[r][ep], d0, sd[3 * ep]); sd[3 * ep + 1] = fmaf(w[r][ep], d1, sd[3 * ep + 1]); sd[3 * ep + 2] = fmaf(w[r][ep], d2, sd[3 * ep + 2]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < 18; v++) e[v] = e[v] + sd[v];
+    // ---- six-point fit (UpdateAsSixPointsWithdrawBad, GV:3081-3166), as k_fit_gaussians
+    const Quat oq{o4.x, o4.y, o4.z, o4.w};
+    float c[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+      c[r] = ((e[r] + (e[3 + r] + e[6 + r])) + (e[9 + r] + (e[12 + r] + e[15 + r]))) / 6.0f;
+    double Md[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const float a = e[6 * i + r] - c[r], b = e[6 * i + 3 + r] - c[r];
+        Md[r][i] = (double)(0.5f * a + (-0.5f) * b);
+      }
+    double Rd[3][3];
+    polar_newton(Md, Rd);
+    float Rf[3][3], Kd[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+#pragma unroll
+      for (int j = 0; j < 3; j++) Rf[i][j] = (float)Rd[i][j];
+      Kd[i] = (float)fma(Rd[0][i], Md[0][i], fma(Rd[1][i], Md[1][i], Rd[2][i] * Md[2][i]));
+    }
+    const Quat qn = quat_normalized(quat_from_matrix(Rf));
+    *reinterpret_cast<float4*>(rot + 4 * g) = make_float4(qn.w, qn.x, qn.y, qn.z);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const float s0 = i == 0 ? sb0 : i == 1 ? sb1 : sb2;
+      scale[3 * g + i] = Kd[i] / ((s0 + 1e-3f) * 2.0f) * s0;
+      pos[3 * g + i] = c[i];
+    }
+    const Quat rq = quat_normalized(quat_mul(qn, quat_inverse(oq)));
+    quat_to_matrix(rq, Rs);
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  // deformed end points back to global (the next step's input), coalesced; rows of static Gaussians are unchanged and skipped
+  for (int v = tid * 2; v < nend; v += FIT_TILE * 2) {
+    const int r = v / 18, c = v - r * 18;
+    if (!s_static[r]) *reinterpret_cast<float2*>(gend + v) = make_float2(s_end[r * END_PITCH + c], s_end[r * END_PITCH + c + 1]);
+  }
+  if (act) {
+    float4* row = s_sh4 + tid * FIT_PITCH4;
+    float v[SH_FLOATS];
+#pragma unroll
+    for (int c = 0; c < 12; c++) { const float4 x = row[c]; v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w; }
+    sh_rotate_flipped_fast(Rs, v);
+#pragma unroll
+    for (int c = 1; c < 12; c++) row[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    row[0].w = v[3];
+  }
+  __syncthreads();
+  float* osh = shs + g0 * SH_FLOATS;
+  if (tid < 120) {
+#pragma unroll
+    for (int t = 0; t < 13; t++) {
+      const int r = cp_r0 + 10 * t;
+      if (r < rows && !s_static[r]) st_stream4(osh + (size_t)(tid + 120 * t) * 4, s_sh4[r * FIT_PITCH4 + cp_c4]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ SH replay (multi-GPU receivers)
 // A receiver of another rank's deformed Gaussians does not need their SH rows (192 of the 232 bytes per Gaussian): it holds
 // last step's rows and rotations, receives the new rotations, and repeats the owner's SH update
@@ -771,9 +1187,9 @@ static int ensure_sh_tables() {
 }
 
 extern "C" int arapk_node_xf(int M, const double* rot, const double* trans, const float* node_pos, void* node_xf,
-                             cudaStream_t st) {
+                             void* node_xf32, cudaStream_t st) {
   if (M <= 0) return ARAP_OK;
-  k_node_xf<<<(M + 127) / 128, 128, 0, st>>>(M, rot, trans, node_pos, (NodeXf*)node_xf);
+  k_node_xf<<<(M + 127) / 128, 128, 0, st>>>(M, rot, trans, node_pos, (NodeXf*)node_xf, (NodeXf32*)node_xf32);
   ARAP_KERNEL_CHECK();
   return ARAP_OK;
 }
@@ -856,6 +1272,100 @@ extern "C" int arapk_fit_gaussians(long long N, const float* ends, const float* 
     attr_set = true;
   }
   k_fit_gaussians<<<(unsigned)((N + FIT_TILE - 1) / FIT_TILE), FIT_TILE, smem, st>>>(N, ends, scale_backup, is_static, pos, rot, scale, shs);
+  ARAP_KERNEL_CHECK();
+  return ARAP_OK;
+}
+
+// ---- tolerance-mode (lbs_mode = 3) launchers
+extern "C" int arapk_scan_inclusive_i32(const int* in, int* out, long long n, int* sums_scratch, cudaStream_t st);   // grid.cu
+
+// Block unions of a row family.  Two passes around a scan; *rows_out = total union rows.  boff: ceil(rows/32) + 1 ints
+// (device).  blist / bw are allocated by the caller between the passes: call with blist == NULL first (counts + scan,
+// returns the total), then with the arrays.
+extern "C" int arapk_sunion_build(long long rows, int k, const uint16_t* ridx, const float* wf, const double* wd, int* boff,
+                                  uint16_t* blist, float* bw, long long* rows_out, int* scratch /* nblk + 8192 ints */,
+                                  cudaStream_t st) {
+  if (rows <= 0) { if (rows_out) *rows_out = 0; return ARAP_OK; }
+  if (k < 1 || k > KNN_MAX) { set_error("sunion_build: k out of range"); return ARAP_ERR_INVALID; }
+  const long long nblk = (rows + 31) / 32;
+  const unsigned grid = (unsigned)((nblk + 3) / 4);
+  if (!blist) {
+    int* cnt = scratch;
+    k_sunion_build<false><<<grid, 128, 0, st>>>(rows, k, ridx, nullptr, nullptr, cnt, nullptr, nullptr, nullptr);
+    ARAP_KERNEL_CHECK();
+    ARAP_CUDA_TRY(cudaMemsetAsync(boff, 0, sizeof(int), st));
+    int rc = arapk_scan_inclusive_i32(cnt, boff + 1, nblk, scratch + nblk, st); if (rc) return rc;
+    int total = 0;
+    ARAP_CUDA_TRY(cudaMemcpyAsync(&total, boff + nblk, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ARAP_CUDA_TRY(cudaStreamSynchronize(st));
+    if (rows_out) *rows_out = total;
+    return ARAP_OK;
+  }
+  k_sunion_build<true><<<grid, 128, 0, st>>>(rows, k, ridx, wf, wd, nullptr, boff, blist, bw);
+  ARAP_KERNEL_CHECK();
+  return ARAP_OK;
+}
+
+extern "C" int arapk_lbs_union32(const float* in, float* out, long long P, const int* boff, const uint16_t* blist, const float* bw,
+                                 const void* node_xf32, const uint8_t* skip, int group, cudaStream_t st) {
+  if (P <= 0) return ARAP_OK;
+  if (group < 1) group = 1;
+  const long long nblk = (P + 31) / 32;
+  k_lbs_union32<<<(unsigned)((nblk + SU_WARPS - 1) / SU_WARPS), SU_WARPS * 32, 0, st>>>(in, out, P, boff, blist, bw, (const NodeXf32*)node_xf32, skip, group);
+  ARAP_KERNEL_CHECK();
+  return ARAP_OK;
+}
+
+extern "C" long long arapk_gtile_count(long long n_gaussians) { return (n_gaussians + FIT_TILE - 1) / FIT_TILE; }
+extern "C" int arapk_gtile_cap(void) { return GT_CAP; }
+
+// Per-Gaussian unions of the end-point rows.  Same two-pass protocol as arapk_sunion_build: usw == NULL -> counts, scans
+// (uoff, woff: ceil(N/32) + 1 ints each) and totals (*rows_out union rows, *words_out slot words); then the fill.
+extern "C" int arapk_gunion_build(long long N, int k, const uint16_t* end_ridx, const double* end_rw, int* uoff, int* woff,
+                                  uint32_t* usw, uint16_t* unode, float* uw, uint16_t* gtile_cnt, uint16_t* gtile_nodes,
+                                  long long* rows_out, long long* words_out, int* scratch /* 2 * nblk + 8192 + 2 ints */, cudaStream_t st) {
+  if (N <= 0) return ARAP_OK;
+  if (k < 1 || k > KNN_MAX) { set_error("gunion_build: k out of range"); return ARAP_ERR_INVALID; }
+  const long long nblk = (N + 31) / 32;
+  const unsigned grid = (unsigned)arapk_gtile_count(N);
+  int* cnt = scratch; int* wcnt = scratch + nblk; int* sums = scratch + 2 * nblk; int* err = sums + 8192;
+  if (!usw) {
+    ARAP_CUDA_TRY(cudaMemsetAsync(err, 0, sizeof(int), st));
+    k_gunion_build<false><<<grid, 128, 0, st>>>(N, k, end_ridx, end_rw, cnt, err, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    k_words_of_rows<<<(unsigned)((nblk + 255) / 256), 256, 0, st>>>(nblk, cnt, wcnt);
+    ARAP_KERNEL_CHECK();
+    ARAP_CUDA_TRY(cudaMemsetAsync(uoff, 0, sizeof(int), st)); ARAP_CUDA_TRY(cudaMemsetAsync(woff, 0, sizeof(int), st));
+    int rc = arapk_scan_inclusive_i32(cnt, uoff + 1, nblk, sums, st); if (rc) return rc;
+    rc = arapk_scan_inclusive_i32(wcnt, woff + 1, nblk, sums, st); if (rc) return rc;
+    int h[3] = {0, 0, 0};
+    ARAP_CUDA_TRY(cudaMemcpyAsync(&h[0], uoff + nblk, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ARAP_CUDA_TRY(cudaMemcpyAsync(&h[1], woff + nblk, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ARAP_CUDA_TRY(cudaMemcpyAsync(&h[2], err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ARAP_CUDA_TRY(cudaStreamSynchronize(st));
+    if (h[2]) { set_error("gunion_build: a Gaussian touches more than 60 distinct nodes"); return ARAP_ERR_UNSUPPORTED; }
+    if (rows_out) *rows_out = h[0];
+    if (words_out) *words_out = h[1];
+    return ARAP_OK;
+  }
+  k_gunion_build<true><<<grid, 128, 0, st>>>(N, k, end_ridx, end_rw, nullptr, err, uoff, woff, usw, unode, uw, gtile_cnt, gtile_nodes);
+  ARAP_KERNEL_CHECK();
+  return ARAP_OK;
+}
+
+extern "C" int arapk_apply_union(long long N, const void* node_xf32, const uint16_t* gtile_cnt, const uint16_t* gtile_nodes,
+                                 const int* uoff, const int* woff, const uint32_t* usw, const uint16_t* unode, const float* uw,
+                                 float* ends, const float* scale_backup, const uint8_t* is_static, float* pos, float* rot,
+                                 float* scale, float* shs, cudaStream_t st) {
+  if (N <= 0) return ARAP_OK;
+  int rc = ensure_sh_tables(); if (rc) return rc;
+  const size_t smem = sizeof(float4) * FIT_TILE * FIT_PITCH4 + sizeof(float) * FIT_TILE * END_PITCH + sizeof(float4) * GT_CAP * 3;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_apply_union, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  k_apply_union<<<(unsigned)arapk_gtile_count(N), FIT_TILE, smem, st>>>(N, (const NodeXf32*)node_xf32, gtile_cnt, gtile_nodes, uoff, woff, usw,
+                                                                      unode, uw, ends, scale_backup, is_static, pos, rot, scale, shs);
   ARAP_KERNEL_CHECK();
   return ARAP_OK;
 }

@@ -52,6 +52,15 @@ struct __align__(16) NodeXf {
 };
 static_assert(sizeof(NodeXf) == 112, "NodeXf layout");
 
+// Float record of the tolerance-mode skinning kernels (arap_params.lbs_mode = 3): A - I row-major, t, g.  64 B.
+struct __align__(16) NodeXf32 {
+  float dA[9];
+  float t[3];
+  float g[3];
+  float pad;
+};
+static_assert(sizeof(NodeXf32) == 64, "NodeXf32 layout");
+
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 // streaming 128-bit load/store that bypass L1 allocation (data touched once)

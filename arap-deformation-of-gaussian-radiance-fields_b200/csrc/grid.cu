@@ -92,6 +92,13 @@ static int scan_inclusive(const int* in, int* out, long long n, int* sums_scratc
   return ARAP_OK;
 }
 
+}  // namespace arapgs
+// exported for the table builders of apply.cu; sums_scratch >= ceil(n / 4096) ints
+extern "C" int arapk_scan_inclusive_i32(const int* in, int* out, long long n, int* sums_scratch, cudaStream_t st) {
+  return arapgs::scan_inclusive(in, out, n, sums_scratch, st);
+}
+namespace arapgs {
+
 // ------------------------------------------------------------------ segmented in-place sort (ascending int)
 // Normalised bitonic network (all comparators point up) with virtual +inf
 // padding, so arbitrary segment lengths sort in place.
@@ -323,6 +330,34 @@ __global__ void k_ada_lpf(int V, const float* __restrict__ samples, const int* _
     }
 }
 
+// ------------------------------------------------------------------ empty cells
+// JudgeEmptyGrid (GaussianView.cpp:4272-4318).  Pass 1: a valid cell whose 64 aim opacities (summed in sample order, float)
+// exceed 1e-6 clears the "bad" mark of itself and of its six face neighbours (clamped at the grid border, like the
+// reference).  Pass 2: empty_grid[i] = bad[valid[i]].  The marks only ever go 1 -> 0, so the plain stores race benignly.
+__global__ void k_judge_mark(int V, const int* __restrict__ valid, const float* __restrict__ aim_opacity, int G,
+                             uint8_t* __restrict__ bad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= V) return;
+  const float* o = aim_opacity + (size_t)i * 64;
+  float total = 0.0f;
+  for (int j = 0; j < 64; j++) total += o[j];
+  if (!(total > 1e-6)) return;   // float compared with the double literal, as in the reference
+  const int idx = valid[i];
+  const int z = idx % G, y = (idx / G) % G, x = idx / (G * G);
+  bad[idx] = 0;
+  bad[max(x - 1, 0) * (G * G) + y * G + z] = 0;
+  bad[min(x + 1, G - 1) * (G * G) + y * G + z] = 0;
+  bad[x * (G * G) + max(y - 1, 0) * G + z] = 0;
+  bad[x * (G * G) + min(y + 1, G - 1) * G + z] = 0;
+  bad[x * (G * G) + y * G + max(z - 1, 0)] = 0;
+  bad[x * (G * G) + y * G + min(z + 1, G - 1)] = 0;
+}
+__global__ void k_judge_collect(int V, const int* __restrict__ valid, const uint8_t* __restrict__ bad, int* __restrict__ empty) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= V) return;
+  empty[i] = bad[valid[i]] ? 1 : 0;
+}
+
 // ------------------------------------------------------------------ field evaluation
 // forward3d_grid is EXTERNAL to the reference tree (XinhaoT/CudaRasterizer @
 // 96ea96c, source absent) — PARITY UNPINNED.  Implemented from the call-site
@@ -536,6 +571,20 @@ extern "C" int arapk_emit_samples(const int* valid, int V, const float* min3, fl
 extern "C" int arapk_ada_lpf(const float* samples, const int* valid, int V, float lpf_parameter, float* out, cudaStream_t st) {
   if (V <= 0) return ARAP_OK;
   k_ada_lpf<<<(V + 127) / 128, 128, 0, st>>>(V, samples, valid, lpf_parameter, out);
+  ARAP_KERNEL_CHECK();
+  return ARAP_OK;
+}
+
+// scratch: G^3 bytes (device)
+extern "C" int arapk_judge_empty_grid(const int* valid, int V, const float* aim_opacity, int G, int* empty_out, void* scratch,
+                                      size_t scratch_bytes, cudaStream_t st) {
+  if (V <= 0) return ARAP_OK;
+  const size_t gc = (size_t)G * G * G;
+  if (scratch_bytes < gc) { set_error("judge_empty_grid: scratch too small"); return ARAP_ERR_INVALID; }
+  uint8_t* bad = (uint8_t*)scratch;
+  ARAP_CUDA_TRY(cudaMemsetAsync(bad, 1, gc, st));
+  k_judge_mark<<<(V + 127) / 128, 128, 0, st>>>(V, valid, aim_opacity, G, bad);
+  k_judge_collect<<<(V + 127) / 128, 128, 0, st>>>(V, valid, bad, empty_out);
   ARAP_KERNEL_CHECK();
   return ARAP_OK;
 }

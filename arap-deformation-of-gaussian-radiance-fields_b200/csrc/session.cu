@@ -136,6 +136,10 @@ struct RowTable {  // blocked skinning rows of one query family
   DBuf<uint16_t> idx; DBuf<double> w; DBuf<float> wf;
   // per-tile distinct node lists + one-byte slots for the staged LBS kernel (apply.cu: k_lbs_tiles)
   DBuf<uint32_t> slots; DBuf<uint16_t> tile_cnt, tile_nodes;
+  // tolerance mode (lbs_mode = 3), apply.cu: block unions of a row family (k_lbs_union32) ...
+  DBuf<int> boff; DBuf<uint16_t> blist; DBuf<float> bw;
+  // ... and, for the end-point rows, per-Gaussian unions + per-128-Gaussian node lists (k_apply_union)
+  DBuf<int> uoff, woff; DBuf<uint32_t> usw; DBuf<uint16_t> unode, gtile_cnt, gtile_nodes; DBuf<float> uw;
   size_t entries() const { return (size_t)((rows + 31) / 32) * 32 * k; }
 };
 
@@ -156,6 +160,7 @@ struct arap_ctx {
   DBuf<int> cell_prefix, gs_init_grid_idx, fp_prefix, lists, valid;
   DBuf<float> sample_pos, ada_lpf, aim_feature, aim_opacity, cur_feature, cur_opacity, gs_aabb;
   DBuf<uint8_t> sample_static;
+  DBuf<int> empty_grid;
   DBuf<char> grid_scratch;
   // mesh points ("simplified_points")
   int Mp = 0; bool nodes_on_mesh = false; DBuf<float> mesh_pts;
@@ -176,7 +181,7 @@ struct arap_ctx {
   struct ConSet { int n_groups = 0; long long n_entries = 0; DBuf<int> grp_off, grp_member, aim_off, aim_nodes, cin_off, cin_grp, cin_member, cin_slot; DBuf<float> grp_aim; };
   ConSet con[2];
   // solve
-  DBuf<double> rot_d, trans_d, stats_d, warm_d; DBuf<char> solve_ws; DBuf<char> node_xf; DBuf<float> node_q;
+  DBuf<double> rot_d, trans_d, stats_d, warm_d; DBuf<char> solve_ws; DBuf<char> node_xf, node_xf32; DBuf<float> node_q;
   double* stats_h = nullptr;  // pinned
   cudaEvent_t ev_soa = nullptr;   // recorded after the six-point fit of every apply: the rasteriser-facing SoA is final
   cudaEvent_t ev_release = nullptr;  // caller's event (not owned): its reads of the SoA are done; the next fit waits for it
@@ -184,7 +189,21 @@ struct arap_ctx {
   // timing
   // timing: a ring of per-step event sets so a whole timed region can be read back afterwards
   static constexpr int TRING = 128;
+  // set-up / stroke-end stage times (device time between two events on the ctx stream, ms), see arap_setup_timing
+  float setup_ms[ARAP_SETUP_STAGES] = {0}; cudaEvent_t ev_st[2] = {nullptr, nullptr};
   bool timing = false; cudaEvent_t evr[TRING][7] = {{nullptr}}; cudaEvent_t* ev = evr[0]; long long tsteps = 0;
+};
+
+// Scoped stage timer: device time from construction to destruction on the ctx stream (set-up paths synchronise anyway).
+struct StageTimer {
+  arap_ctx* c; int slot; bool add;
+  StageTimer(arap_ctx* ctx, int s, bool accumulate = false) : c(ctx), slot(s), add(accumulate) { cudaEventRecord(c->ev_st[0], c->stream); }
+  ~StageTimer() {
+    cudaEventRecord(c->ev_st[1], c->stream);
+    float ms = 0.f;
+    if (cudaEventSynchronize(c->ev_st[1]) == cudaSuccess && cudaEventElapsedTime(&ms, c->ev_st[0], c->ev_st[1]) == cudaSuccess)
+      c->setup_ms[slot] = add ? c->setup_ms[slot] + ms : ms;
+  }
 };
 
 #define CTX_CHECK(c) do { if (!(c)) { set_error("null ctx"); return ARAP_ERR_INVALID; } cudaSetDevice((c)->device); } while (0)
@@ -222,6 +241,7 @@ extern "C" int arap_create(arap_ctx** out, int device, void* stream, const arap_
   ARAP_CUDA_TRY(cudaMallocHost((void**)&c->stats_h, 32 * sizeof(double)));
   for (auto& row : c->evr) for (auto& ev : row) ARAP_CUDA_TRY(cudaEventCreate(&ev));
   ARAP_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_soa, cudaEventDisableTiming));
+  ARAP_CUDA_TRY(cudaEventCreate(&c->ev_st[0])); ARAP_CUDA_TRY(cudaEventCreate(&c->ev_st[1]));
   *out = c.release();
   return ARAP_OK;
 }
@@ -233,6 +253,7 @@ extern "C" int arap_destroy(arap_ctx* ctx) {
   if (ctx->stats_h) cudaFreeHost(ctx->stats_h);
   for (auto& row : ctx->evr) for (auto& ev : row) if (ev) cudaEventDestroy(ev);
   if (ctx->ev_soa) cudaEventDestroy(ctx->ev_soa);
+  for (auto& ev : ctx->ev_st) if (ev) cudaEventDestroy(ev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return ARAP_OK;
@@ -289,6 +310,7 @@ extern "C" int arap_get_device_view(arap_ctx* ctx, arap_device_view* o) {
   o->n_samples = ctx->S; o->sample_pos = ctx->sample_pos.p; o->aim_feature = ctx->aim_feature.p; o->aim_opacity = ctx->aim_opacity.p;
   o->valid_grid = ctx->valid.p; o->grid_gs_prefix_sum = ctx->fp_prefix.p; o->grided_gs_idx = ctx->lists.p;
   o->gs_init_grid_idx = ctx->gs_init_grid_idx.p; o->ada_lpf_ratio = ctx->ada_lpf.p; o->end_points = ctx->ends.p;
+  o->empty_grid = ctx->empty_grid.p; o->cur_feature = ctx->cur_feature.p; o->cur_opacity = ctx->cur_opacity.p;
   return ARAP_OK;
 }
 
@@ -321,6 +343,7 @@ static int overall_aabb(arap_ctx* c) {
 
 static int build_lists(arap_ctx* c) {  // boxes -> count -> fill (GV:3961-4100 / 3634-3743)
   cudaStream_t st = c->stream;
+  StageTimer tmr(c, ARAP_ST_FOOTPRINT_LISTS);
   TRY(c->gs_aabb.alloc((size_t)c->N * 6));
   TRY(arapk_gs_aabbs(c->N, c->pos.p, c->rot.p, c->scale.p, c->opacity.p, c->gs_aabb.p, nullptr, nullptr, st));
   const size_t gc = (size_t)c->G * c->G * c->G;
@@ -340,14 +363,18 @@ extern "C" int arap_grid_build(arap_ctx* ctx) {
   ctx->G = ctx->prm.grid_num;
   if (ctx->G < 1 || ctx->G > 256) { set_error("grid_build: grid_num out of range"); return ARAP_ERR_INVALID; }
   const size_t gc = (size_t)ctx->G * ctx->G * ctx->G;
-  TRY(overall_aabb(ctx));
+  { StageTimer tmr(ctx, ARAP_ST_SCENE_AABB); TRY(overall_aabb(ctx)); }
   TRY(ctx->grid_scratch.alloc(arapk_grid_scratch_bytes(ctx->N, ctx->G)));
   TRY(ctx->cell_prefix.alloc(gc)); TRY(ctx->gs_init_grid_idx.alloc((size_t)ctx->N));
   // cell assignment + stable re-order (GV:3896-3953)
   DBuf<int> new_idx; TRY(new_idx.alloc((size_t)ctx->N));
-  TRY(arapk_cell_assign(ctx->pos.p, ctx->N, ctx->aabb, ctx->step, ctx->G, ctx->gs_init_grid_idx.p, ctx->cell_prefix.p, new_idx.p,
-                        ctx->grid_scratch.p, ctx->grid_scratch.n, st));
   {
+    StageTimer tmr(ctx, ARAP_ST_CELL_ASSIGN);
+    TRY(arapk_cell_assign(ctx->pos.p, ctx->N, ctx->aabb, ctx->step, ctx->G, ctx->gs_init_grid_idx.p, ctx->cell_prefix.p, new_idx.p,
+                          ctx->grid_scratch.p, ctx->grid_scratch.n, st));
+  }
+  {
+    StageTimer tmr(ctx, ARAP_ST_REORDER);
     DBuf<float> p2, r2, s2, o2, h2;
     TRY(p2.alloc(ctx->pos.n)); TRY(r2.alloc(ctx->rot.n)); TRY(s2.alloc(ctx->scale.n)); TRY(o2.alloc(ctx->opacity.n)); TRY(h2.alloc(ctx->shs.n));
     TRY(arapk_permute_gaussians(ctx->N, new_idx.p, ctx->pos.p, ctx->rot.p, ctx->scale.p, ctx->opacity.p, ctx->shs.p, p2.p, r2.p, s2.p, o2.p, h2.p, st));
@@ -360,9 +387,13 @@ extern "C" int arap_grid_build(arap_ctx* ctx) {
   }
   ARAP_CUDA_TRY(cudaMemcpyAsync(ctx->scale_backup.p, ctx->scale.p, (size_t)ctx->N * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   // gs_init_grid_idx in the new order (GV:4136-4145)
-  TRY(arapk_cell_assign(ctx->pos.p, ctx->N, ctx->aabb, ctx->step, ctx->G, ctx->gs_init_grid_idx.p, ctx->cell_prefix.p, nullptr,
-                        ctx->grid_scratch.p, ctx->grid_scratch.n, st));
+  {
+    StageTimer tmr(ctx, ARAP_ST_CELL_ASSIGN, true);
+    TRY(arapk_cell_assign(ctx->pos.p, ctx->N, ctx->aabb, ctx->step, ctx->G, ctx->gs_init_grid_idx.p, ctx->cell_prefix.p, nullptr,
+                          ctx->grid_scratch.p, ctx->grid_scratch.n, st));
+  }
   TRY(build_lists(ctx));
+  StageTimer tmr_samples(ctx, ARAP_ST_SAMPLES);
   // valid cells = non-empty padded lists (GV:4040-4053); 4^3 samples each (GV:4111-4133)
   TRY(ctx->valid.alloc(gc));
   int V = 0;
@@ -378,7 +409,7 @@ extern "C" int arap_grid_build(arap_ctx* ctx) {
   // endpoints (GetEndPoints, GV:4643-4668)
   TRY(ctx->ends.alloc((size_t)ctx->N * 18));
   TRY(arapk_end_points(ctx->N, ctx->pos.p, ctx->rot.p, ctx->scale.p, ctx->ends.p, st));
-  ctx->aim_feature.release(); ctx->aim_opacity.release(); ctx->cur_feature.release(); ctx->cur_opacity.release();
+  ctx->aim_feature.release(); ctx->aim_opacity.release(); ctx->cur_feature.release(); ctx->cur_opacity.release(); ctx->empty_grid.release();
   ctx->grid_ready = true; ctx->graph_ready = false;
   return ARAP_OK;
 }
@@ -386,7 +417,7 @@ extern "C" int arap_grid_build(arap_ctx* ctx) {
 extern "C" int arap_grid_update_lists(arap_ctx* ctx) {
   CTX_CHECK(ctx);
   if (!ctx->grid_ready) { set_error("grid_update_lists: grid not built"); return ARAP_ERR_STATE; }
-  TRY(overall_aabb(ctx));  // UpdateContainingRelationship recomputes the scene box and step (GV:3636-3644)
+  { StageTimer tmr(ctx, ARAP_ST_SCENE_AABB); TRY(overall_aabb(ctx)); }  // UpdateContainingRelationship recomputes the scene box and step (GV:3636-3644)
   return build_lists(ctx);
 }
 
@@ -396,8 +427,42 @@ extern "C" int arap_grid_eval(arap_ctx* ctx, int which) {
   DBuf<float>& f = which == 0 ? ctx->aim_feature : ctx->cur_feature;
   DBuf<float>& o = which == 0 ? ctx->aim_opacity : ctx->cur_opacity;
   TRY(f.alloc((size_t)std::max<long long>(ctx->S, 1) * 48)); TRY(o.alloc((size_t)std::max<long long>(ctx->S, 1)));
-  return arapk_grid_eval(ctx->valid.p, ctx->V, ctx->fp_prefix.p, ctx->lists.p, ctx->sample_pos.p, ctx->pos.p, ctx->rot.p, ctx->scale.p,
-                         ctx->opacity.p, ctx->shs.p, ctx->ada_lpf.p, f.p, o.p, ctx->stream);
+  StageTimer tmr(ctx, ARAP_ST_GRID_EVAL);
+  TRY(arapk_grid_eval(ctx->valid.p, ctx->V, ctx->fp_prefix.p, ctx->lists.p, ctx->sample_pos.p, ctx->pos.p, ctx->rot.p, ctx->scale.p,
+                      ctx->opacity.p, ctx->shs.p, ctx->ada_lpf.p, f.p, o.p, ctx->stream));
+  if (which == 0) {   // GPUSetupSamplesFeatures ends with JudgeEmptyGrid (GV:4268)
+    TRY(ctx->empty_grid.alloc((size_t)std::max(ctx->V, 1)));
+    TRY(arapk_judge_empty_grid(ctx->valid.p, ctx->V, o.p, ctx->G, ctx->empty_grid.p, ctx->grid_scratch.p, ctx->grid_scratch.n, ctx->stream));
+  }
+  return ARAP_OK;
+}
+
+// GetAdaLpfRatio on the CURRENT (deformed) sample positions — the reference recomputes it before the stage-II optimiser
+// (GV:1704-1706) and on reload (GV:958); arap_grid_build computes the rest-state value (GV:725).
+extern "C" int arap_ada_lpf_update(arap_ctx* ctx) {
+  CTX_CHECK(ctx);
+  if (!ctx->grid_ready) { set_error("ada_lpf_update: grid not built"); return ARAP_ERR_STATE; }
+  return arapk_ada_lpf(ctx->sample_pos.p, ctx->valid.p, ctx->V, ctx->prm.lpf_parameter, ctx->ada_lpf.p, ctx->stream);
+}
+extern "C" int arap_download_ada_lpf(arap_ctx* ctx, float* out) {
+  CTX_CHECK(ctx);
+  if (!ctx->grid_ready) { set_error("download_ada_lpf: grid not built"); return ARAP_ERR_STATE; }
+  TRY(download(out, ctx->ada_lpf.p, (size_t)ctx->G * ctx->G * ctx->G * 9, ctx->stream));
+  ARAP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return ARAP_OK;
+}
+extern "C" int arap_download_empty_grid(arap_ctx* ctx, int* out) {
+  CTX_CHECK(ctx);
+  if (!ctx->empty_grid.p) { set_error("download_empty_grid: aim features not evaluated (arap_grid_eval(ctx, 0))"); return ARAP_ERR_STATE; }
+  TRY(download(out, ctx->empty_grid.p, (size_t)ctx->V, ctx->stream));
+  ARAP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return ARAP_OK;
+}
+
+extern "C" int arap_setup_timing(arap_ctx* ctx, float* ms, int n) {
+  CTX_CHECK(ctx); if (!ms || n < 0) return ARAP_ERR_INVALID;
+  for (int i = 0; i < n && i < ARAP_SETUP_STAGES; i++) ms[i] = ctx->setup_ms[i];
+  return ARAP_OK;
 }
 
 extern "C" int arap_grid_info_get(arap_ctx* ctx, arap_grid_info* o) {
@@ -460,14 +525,47 @@ static int build_tiles(arap_ctx* c, RowTable& t) {
   return arapk_lbs_build_tiles(t.rows, t.k, t.idx.p, t.slots.p, t.tile_cnt.p, t.tile_nodes.p, c->stream);
 }
 
+// Tolerance-mode tables (lbs_mode = 3): block unions of the sample rows, per-Gaussian unions of the end-point rows.
+static int build_unions(arap_ctx* c) {
+  cudaStream_t st = c->stream; const int k = c->k;
+  DBuf<int> scratch;
+  {
+    RowTable& t = c->sample_rows;
+    t.boff.release(); t.blist.release(); t.bw.release();
+    if (t.rows > 0) {
+      const size_t nblk = (size_t)((t.rows + 31) / 32);
+      TRY(scratch.alloc(nblk + 8192)); TRY(t.boff.alloc(nblk + 1));
+      long long rows = 0;
+      TRY(arapk_sunion_build(t.rows, k, t.idx.p, t.wf.p, t.w.p, t.boff.p, nullptr, nullptr, &rows, scratch.p, st));
+      TRY(t.blist.alloc((size_t)std::max<long long>(rows, 1))); TRY(t.bw.alloc((size_t)std::max<long long>(rows, 1) * 32));
+      TRY(arapk_sunion_build(t.rows, k, t.idx.p, t.wf.p, t.w.p, t.boff.p, t.blist.p, t.bw.p, nullptr, scratch.p, st));
+    }
+  }
+  {
+    RowTable& t = c->end_rows;
+    const size_t nblk = (size_t)((c->N + 31) / 32), nt = (size_t)arapk_gtile_count(c->N);
+    TRY(scratch.alloc(2 * nblk + 8192 + 2)); TRY(t.uoff.alloc(nblk + 1)); TRY(t.woff.alloc(nblk + 1));
+    TRY(t.gtile_cnt.alloc(nt)); TRY(t.gtile_nodes.alloc(nt * (size_t)arapk_gtile_cap()));
+    long long rows = 0, words = 0;
+    TRY(arapk_gunion_build(c->N, k, t.idx.p, t.w.p, t.uoff.p, t.woff.p, nullptr, nullptr, nullptr, nullptr, nullptr, &rows, &words, scratch.p, st));
+    TRY(t.usw.alloc((size_t)std::max<long long>(words, 1) * 32)); TRY(t.unode.alloc((size_t)std::max<long long>(rows, 1) * 32));
+    TRY(t.uw.alloc((size_t)std::max<long long>(rows, 1) * 6 * 32));
+    TRY(arapk_gunion_build(c->N, k, t.idx.p, t.w.p, t.uoff.p, t.woff.p, t.usw.p, t.unode.p, t.uw.p, t.gtile_cnt.p, t.gtile_nodes.p, nullptr, nullptr, scratch.p, st));
+    ARAP_CUDA_TRY(cudaStreamSynchronize(st));   // scratch is freed on return
+  }
+  return ARAP_OK;
+}
+
 // LBS of one row family.  prm.lbs_mode: 0 = staged node records + FP64-pipe float rounding (default),
 // 1 = global-memory gathers (first version), 2 = staged records, rounding by conversion instructions.
 static int lbs_family(arap_ctx* c, const float* in, float* out, const RowTable& t, const uint8_t* skip, int group) {
   if (t.rows <= 0) return ARAP_OK;
+  if (c->prm.lbs_mode == 3 && t.boff.p)   // tolerance mode: block unions, float records and weights (the sample rows)
+    return arapk_lbs_union32(in, out, t.rows, t.boff.p, t.blist.p, t.bw.p, c->node_xf32.p, skip, group, c->stream);
   if (c->prm.lbs_mode == 1 || !t.slots.p)
     return arapk_lbs_points(in, out, t.rows, t.k, t.idx.p, t.w.p, c->node_xf.p, skip, group, c->stream);
   return arapk_lbs_tiles(in, out, t.rows, t.k, t.slots.p, t.w.p, t.idx.p, t.tile_cnt.p, t.tile_nodes.p, c->node_xf.p, skip, group,
-                         c->prm.lbs_mode == 0, c->stream);
+                         c->prm.lbs_mode == 0 || c->prm.lbs_mode == 3, c->stream);
 }
 
 static int finish_graph(arap_ctx* c, int k) {
@@ -485,6 +583,7 @@ static int finish_graph(arap_ctx* c, int k) {
   ARAP_CUDA_TRY(cudaMemcpyAsync(c->node_rest.p, c->node_pos.p, (size_t)M * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   ARAP_CUDA_TRY(cudaMemcpyAsync(c->aim.p, c->node_pos.p, (size_t)M * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));  // ReloadAimPositions
   // kNN index over the rest positions (findNearestNodes always measures against back_up_nodes, DH:155-165)
+  cudaEventRecord(c->ev_st[0], st);   // ARAP_ST_NODE_GRAPH: closed by hand after the node query below
   TRY(c->knn_ws.alloc(arapk_knn_workspace_bytes(M)));
   c->knn_index.resize(arapk_knn_index_struct_bytes());
   TRY(arapk_knn_build(c->node_rest.p, M, c->knn_ws.p, c->knn_ws.n, c->knn_index.data(), st));
@@ -514,16 +613,19 @@ static int finish_graph(arap_ctx* c, int k) {
     k_rows_to_blocked<<<(M + 127) / 128, 128, 0, st>>>(M, k, idx_p.p, w_p.p, c->node_rows.idx.p, c->node_rows.w.p);
     ARAP_KERNEL_CHECK();
     ARAP_CUDA_TRY(cudaStreamSynchronize(st));
+    cudaEventRecord(c->ev_st[1], st); cudaEventSynchronize(c->ev_st[1]); cudaEventElapsedTime(&c->setup_ms[ARAP_ST_NODE_GRAPH], c->ev_st[0], c->ev_st[1]);
   }
   // skinning rows per query family (setupWeightsforEnds / forSamples / forMesh, GV:2833-2918)
-  TRY(knn_family(c, c->ends.p, c->N * 6, k, c->end_rows, false));
-  TRY(knn_family(c, c->sample_pos.p, c->S, k, c->sample_rows, true));
+  { StageTimer tmr(c, ARAP_ST_KNN_ENDS); TRY(knn_family(c, c->ends.p, c->N * 6, k, c->end_rows, false)); }
+  { StageTimer tmr(c, ARAP_ST_KNN_SAMPLES); TRY(knn_family(c, c->sample_pos.p, c->S, k, c->sample_rows, true)); }
   TRY(knn_family(c, c->mesh_pts.p, c->Mp, k, c->mesh_rows, false));
+  StageTimer tmr_tiles(c, ARAP_ST_TILE_TABLES);
+  TRY(build_unions(c));
   TRY(build_tiles(c, c->end_rows)); TRY(build_tiles(c, c->sample_rows)); TRY(build_tiles(c, c->mesh_rows)); TRY(build_tiles(c, c->node_rows));
   // solve outputs
   TRY(c->rot_d.alloc((size_t)M * 9)); TRY(c->trans_d.alloc((size_t)M * 3)); TRY(c->stats_d.alloc(32));
   TRY(c->warm_d.alloc(arapk_solve_warm_doubles(M)));
-  TRY(c->node_xf.alloc((size_t)M * 112)); TRY(c->node_q.alloc((size_t)M * 4));
+  TRY(c->node_xf.alloc((size_t)M * 112)); TRY(c->node_xf32.alloc((size_t)M * 64)); TRY(c->node_q.alloc((size_t)M * 4));
   TRY(c->node_free.alloc((size_t)M)); TRY(c->node_static.alloc((size_t)M)); TRY(c->static_in_cnt.alloc((size_t)M)); TRY(c->active_mult.alloc((size_t)M));
   TRY(c->center_tmp.alloc(4));
   c->graph_ready = true; c->solved = false;
@@ -553,10 +655,13 @@ extern "C" int arap_graph_build_fps(arap_ctx* ctx, int node_num, int k) {
   DBuf<int> out; TRY(out.alloc((size_t)std::max(m, 1)));
   DBuf<char> scratch; TRY(scratch.alloc((size_t)nc * 4 + 65536 + 512));
   int cnt = 0;
-  TRY(arapk_fps(cand, nc, node_num, out.p, scratch.p, scratch.n, &cnt, st));
-  ctx->h_anchor.resize(cnt);
-  ARAP_CUDA_TRY(cudaMemcpyAsync(ctx->h_anchor.data(), out.p, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, st));
-  ARAP_CUDA_TRY(cudaStreamSynchronize(st));
+  {
+    StageTimer tmr(ctx, ARAP_ST_FPS);
+    TRY(arapk_fps(cand, nc, node_num, out.p, scratch.p, scratch.n, &cnt, st));
+    ctx->h_anchor.resize(cnt);
+    ARAP_CUDA_TRY(cudaMemcpyAsync(ctx->h_anchor.data(), out.p, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, st));
+    ARAP_CUDA_TRY(cudaStreamSynchronize(st));
+  }
   ctx->M = cnt;
   return finish_graph(ctx, k);
 }
@@ -697,6 +802,14 @@ extern "C" int arap_set_blocks(arap_ctx* ctx, int n_blocks, const int* block_off
   return ARAP_OK;
 }
 
+extern "C" int arap_download_end_points(arap_ctx* ctx, float* ends) {
+  CTX_CHECK(ctx);
+  if (!ctx->grid_ready) { set_error("download_end_points: grid not built"); return ARAP_ERR_STATE; }
+  TRY(download(ends, ctx->ends.p, (size_t)ctx->N * 18, ctx->stream));
+  ARAP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return ARAP_OK;
+}
+
 extern "C" int arap_download_static_flags(arap_ctx* ctx, uint8_t* gaussians, uint8_t* samples) {
   CTX_CHECK(ctx);
   TRY(download(gaussians, ctx->gs_static.p, (size_t)ctx->N, ctx->stream)); TRY(download(samples, ctx->sample_static.p, (size_t)ctx->S, ctx->stream));
@@ -803,13 +916,19 @@ extern "C" int arap_apply(arap_ctx* ctx) {
   cudaStream_t st = ctx->stream; const int M = ctx->M, k = ctx->k;
   const bool tm = ctx->timing;
   if (tm) cudaEventRecord(ctx->ev[1], st);
-  TRY(arapk_node_xf(M, ctx->rot_d.p, ctx->trans_d.p, ctx->node_pos.p, ctx->node_xf.p, st));
+  TRY(arapk_node_xf(M, ctx->rot_d.p, ctx->trans_d.p, ctx->node_pos.p, ctx->node_xf.p, ctx->node_xf32.p, st));
   if (ctx->Mp > 0) TRY(lbs_family(ctx, ctx->mesh_pts.p, ctx->mesh_pts.p, ctx->mesh_rows, nullptr, 1));
-  TRY(lbs_family(ctx, ctx->ends.p, ctx->ends.p, ctx->end_rows, ctx->prm.skip_static_endpoints ? ctx->gs_static.p : nullptr, 6));
+  const bool fused = ctx->prm.lbs_mode == 3 && ctx->end_rows.usw.p;
+  if (!fused) TRY(lbs_family(ctx, ctx->ends.p, ctx->ends.p, ctx->end_rows, ctx->prm.skip_static_endpoints ? ctx->gs_static.p : nullptr, 6));
   TRY(lbs_family(ctx, ctx->node_pos.p, ctx->node_next.p, ctx->node_rows, nullptr, 1));
   if (tm) cudaEventRecord(ctx->ev[2], st);
   if (ctx->ev_release) { ARAP_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_release, 0)); ctx->ev_release = nullptr; }
-  TRY(arapk_fit_gaussians(ctx->N, ctx->ends.p, ctx->scale_backup.p, ctx->gs_static.p, ctx->pos.p, ctx->rot.p, ctx->scale.p, ctx->shs.p, st));
+  if (fused) {   // tolerance mode: end-point skinning + fit + SH rotation in one pass (end points of static Gaussians stay put)
+    const RowTable& t = ctx->end_rows;
+    TRY(arapk_apply_union(ctx->N, ctx->node_xf32.p, t.gtile_cnt.p, t.gtile_nodes.p, t.uoff.p, t.woff.p, t.usw.p, t.unode.p, t.uw.p,
+                          ctx->ends.p, ctx->scale_backup.p, ctx->gs_static.p, ctx->pos.p, ctx->rot.p, ctx->scale.p, ctx->shs.p, st));
+  } else
+    TRY(arapk_fit_gaussians(ctx->N, ctx->ends.p, ctx->scale_backup.p, ctx->gs_static.p, ctx->pos.p, ctx->rot.p, ctx->scale.p, ctx->shs.p, st));
   ARAP_CUDA_TRY(cudaEventRecord(ctx->ev_soa, st));
   if (tm) cudaEventRecord(ctx->ev[3], st);
   if (ctx->S > 0) TRY(lbs_family(ctx, ctx->sample_pos.p, ctx->sample_pos.p, ctx->sample_rows, ctx->sample_static.p, 1));

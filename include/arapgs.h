@@ -48,7 +48,9 @@ typedef struct arap_params {
   int padding;         /* 1  (GV.hpp:446) */
   int knn_k;           /* 10 (GV.hpp:598; README: 8 to reproduce the paper) */
   int node_num;        /* 150 (GV.hpp:322) */
-  int high_quality;    /* config field 2; forwarded to the evaluator only */
+  int high_quality;    /* config field 2 (GV:459-487).  Recorded and reported back only: its sole consumers are inside the external
+                          CudaRasterizer fork (forward3d_grid / L1loss3d), whose source is not in the reference tree, and
+                          ExpandOpRange of the stage-II optimiser (GV:1700-1702, out of scope).  It changes nothing here. */
   float lpf_parameter; /* 0.2 (GV.hpp:482) */
   double w_rot, w_reg, w_con; /* 1, 10, 100 (DH:56-58) */
   int max_gn_iters;    /* 30 (DC:3) */
@@ -56,9 +58,14 @@ typedef struct arap_params {
   double cg_tol;       /* relative residual of the first linear system of a step */
   int skip_static_endpoints; /* 0 = reference behaviour (all endpoints skinned) */
   int solver_global_memory;  /* 1 = force the global-memory solver kernel (default 0: shared-memory-resident kernel when it fits) */
-  int lbs_mode;        /* skinning (LBS) kernel: 0 = node records staged per 128-row tile in shared memory + float rounding on the
-                          FP64 pipe (default), 1 = global-memory gathers, 2 = staged records + conversion instructions.
-                          All three produce identical bits. */
+  int lbs_mode;        /* skinning (LBS) kernels.  0 (default) = bit-faithful: the reference's `float += double` chain (DH:239-246) with node
+                          records staged per 128-row tile in shared memory and the float rounding on the FP64 pipe; 1 = the same from
+                          global memory; 2 = staged records + conversion instructions — 0, 1, 2 produce identical bits.
+                          3 = tolerance mode: end-point skinning fused into the six-point fit and sample skinning evaluated as
+                          p' = p + blend(A - I | t').(p - c; 1) in float (csrc/apply.cu) — the correctly rounded exact skinning in all
+                          but a few per cent of the coordinates, i.e. within ~1 float ulp of p of the reference's chain (which carries
+                          that much rounding noise of its own); end points of excluded-only Gaussians are not touched.
+                          Node and mesh-point positions always use the bit-faithful kernel. */
   double newton_eta0;  /* each Gauss-Newton linear system stops at relative residual newton_eta0 of its own right-hand side
                           or at the cg_tol target, whichever is looser (0 = cg_tol target only).  Default 1e-6: the error of
                           system k reaches the result damped by the remaining Gauss-Newton steps, ~ newton_eta0 x (last step
@@ -129,7 +136,29 @@ typedef struct arap_device_view {
   int* gs_init_grid_idx; /* N */
   float* ada_lpf_ratio;  /* G^3 x 9 */
   float* end_points;     /* N x 6 x 3 */
+  int* empty_grid;       /* V: JudgeEmptyGrid flags (GV:4272-4318), set by arap_grid_eval(ctx, 0); NULL before */
+  float* cur_feature;    /* S x 48: arap_grid_eval(ctx, 1) output (UpdateFeatures, GV:4159-4186); NULL before */
+  float* cur_opacity;    /* S */
 } arap_device_view;
+
+/* Device time (ms, CUDA events on the ctx stream) of the last run of each set-up / stroke-end stage, read with
+ * arap_setup_timing.  T_stroke = SCENE_AABB + FOOTPRINT_LISTS + GRID_EVAL of an arap_grid_update_lists +
+ * arap_grid_eval(ctx, 1) pair; T_graph = FPS + NODE_GRAPH + KNN_ENDS + KNN_SAMPLES + TILE_TABLES of a graph build. */
+enum {
+  ARAP_ST_SCENE_AABB = 0,     /* getOverallAABB */
+  ARAP_ST_CELL_ASSIGN = 1,    /* GetGsGrid + scan, both passes of arap_grid_build (a2) */
+  ARAP_ST_REORDER = 2,        /* cell-order permutation of the SoA (a2) */
+  ARAP_ST_FOOTPRINT_LISTS = 3,/* cutoff boxes + count + scan + fill + per-cell order (a3-a5) */
+  ARAP_ST_SAMPLES = 4,        /* valid cells, sample emit, rest-state adaptive LPF, end points (a6, a8, d1) */
+  ARAP_ST_GRID_EVAL = 5,      /* forward3d_grid (+ JudgeEmptyGrid for the aim field) (a7) */
+  ARAP_ST_FPS = 6,            /* farthest_control_points_sampling (b5) */
+  ARAP_ST_NODE_GRAPH = 7,     /* bucket index + node kNN + edges (b3) */
+  ARAP_ST_KNN_ENDS = 8,       /* setupWeightsforEnds: 6N queries (b1, b2, b4) */
+  ARAP_ST_KNN_SAMPLES = 9,    /* setupWeightsforSamples: S queries */
+  ARAP_ST_TILE_TABLES = 10,   /* per-tile node lists / slots of the skinning kernels (ours) */
+  ARAP_SETUP_STAGES = 11
+};
+int arap_setup_timing(arap_ctx* ctx, float* ms, int n /* <= ARAP_SETUP_STAGES */);
 
 /* ---- lifecycle ----------------------------------------------------------- */
 const char* arap_last_error(void);
@@ -156,6 +185,12 @@ int arap_grid_build(arap_ctx* ctx);
 int arap_grid_update_lists(arap_ctx* ctx);
 /* Rasterizer::forward3d_grid call sites (GV:4159-4186 cur, 4222-4249 aim). which: 0 = aim, 1 = current. */
 int arap_grid_eval(arap_ctx* ctx, int which);
+/* GetAdaLpfRatio (GV:4670-4751) on the current, deformed sample positions (call sites GV:958, 1704-1706);
+ * arap_grid_build computes the rest-state value (GV:725). */
+int arap_ada_lpf_update(arap_ctx* ctx);
+int arap_download_ada_lpf(arap_ctx* ctx, float* out /* G^3 x 9 */);
+/* JudgeEmptyGrid (GV:4272-4318), evaluated on device at the end of arap_grid_eval(ctx, 0). */
+int arap_download_empty_grid(arap_ctx* ctx, int* out /* V */);
 int arap_grid_info_get(arap_ctx* ctx, arap_grid_info* out);
 int arap_download_grid(arap_ctx* ctx, int* valid, int* prefix, int* lists, float* sample_pos, int* gs_init_grid_idx);
 int arap_download_features(arap_ctx* ctx, int which, float* feature, float* opacity);
@@ -178,6 +213,8 @@ int arap_download_rows(arap_ctx* ctx, int family /*0 ends,1 samples,2 mesh,3 nod
 /* blocks as CSR over node ids; types: 1 active, 0 pinned, -1 excluded. Absorbs UpdateIndicies + CheckStaticSamples. */
 int arap_set_blocks(arap_ctx* ctx, int n_blocks, const int* block_off, const uint32_t* block_nodes, const int* block_types);
 int arap_download_static_flags(arap_ctx* ctx, uint8_t* gaussians, uint8_t* samples);
+/* the six end points per Gaussian (GetEndPoints GV:4643-4668, skinned every step GV:3021-3040): N x 18 floats */
+int arap_download_end_points(arap_ctx* ctx, float* ends);
 
 /* ---- aims (GV:2920-2983, 5240-5247) ---------------------------------------- */
 int arap_aim_translate(arap_ctx* ctx, const float delta[3]);                 /* UpdateAimPosition */

@@ -22,7 +22,8 @@ extern "C" {
  *   arapk_fit_gaussians                                  GaussianView::UpdateAsSixPointsWithdrawBad, GaussianView.cpp:3081-3166
  *   arapk_node_quats / arapk_rotate_sample_shs           FastUpdateSamplesSH + RotateSHs, GaussianView.cpp:3169-3186, cudakdtree.cu:201-222
  *   arapk_static_flags                                   CheckStaticSamples / CheckMovedGaussians, GaussianView.cpp:2024-2109 */
-int arapk_node_xf(int M, const double* rot, const double* trans, const float* node_pos, void* node_xf, cudaStream_t st);
+int arapk_node_xf(int M, const double* rot, const double* trans, const float* node_pos, void* node_xf,
+                  void* node_xf32 /* M x 64 B, may be null */, cudaStream_t st);
 int arapk_lbs_points(const float* in, float* out, long long P, int k, const uint16_t* ridx, const double* rw,
                      const void* node_xf, const uint8_t* skip, int group, cudaStream_t st);
 long long arapk_lbs_tile_count(long long rows);
@@ -35,6 +36,24 @@ int arapk_lbs_tiles(const float* in, float* out, long long P, int k, const uint3
 int arapk_end_points(long long N, const float* pos, const float* rot, const float* scale, float* ends, cudaStream_t st);
 int arapk_fit_gaussians(long long N, const float* ends, const float* scale_backup, const uint8_t* is_static, float* pos,
                         float* rot, float* scale, float* shs, cudaStream_t st);
+/* tolerance mode (arap_params.lbs_mode = 3): neighbour UNIONS with dense float weights and float records, same reference
+ * interfaces as above (DeformGraph::predict_mesh / predict_samples, Deform.hpp:230-268; UpdateAsSixPointsWithdrawBad,
+ * GaussianView.cpp:3081-3166).  arapk_sunion_build / arapk_gunion_build: two-pass set-up (first call with the table pointers
+ * NULL returns the sizes); arapk_lbs_union32: a row family; arapk_apply_union: end-point skinning + six-point fit + SH rotation
+ * in one pass.  node_xf32 = the float records arapk_node_xf writes next to the fp64 ones (64 B per node). */
+int arapk_sunion_build(long long rows, int k, const uint16_t* ridx, const float* wf, const double* wd, int* boff, uint16_t* blist,
+                       float* bw, long long* rows_out, int* scratch, cudaStream_t st);
+int arapk_lbs_union32(const float* in, float* out, long long P, const int* boff, const uint16_t* blist, const float* bw,
+                      const void* node_xf32, const uint8_t* skip, int group, cudaStream_t st);
+long long arapk_gtile_count(long long n_gaussians);
+int arapk_gtile_cap(void);
+int arapk_gunion_build(long long N, int k, const uint16_t* end_ridx, const double* end_rw, int* uoff, int* woff, uint32_t* usw,
+                       uint16_t* unode, float* uw, uint16_t* gtile_cnt, uint16_t* gtile_nodes, long long* rows_out,
+                       long long* words_out, int* scratch, cudaStream_t st);
+int arapk_apply_union(long long N, const void* node_xf32, const uint16_t* gtile_cnt, const uint16_t* gtile_nodes, const int* uoff,
+                      const int* woff, const uint32_t* usw, const uint16_t* unode, const float* uw, float* ends,
+                      const float* scale_backup, const uint8_t* is_static, float* pos, float* rot, float* scale, float* shs,
+                      cudaStream_t st);
 /* multi-GPU receivers: repeat the owner's SH update of k_fit_gaussians from (old rotation, new rotation) on a held copy */
 int arapk_replay_shs(long long N, const float* rot_old, const float* rot_new, const uint8_t* is_static, float* shs,
                      cudaStream_t st);
@@ -128,6 +147,9 @@ int arapk_valid_cells(const int* prefix, int G, int* valid_out, int* count_host,
 int arapk_emit_samples(const int* valid, int V, const float* min3_host, float step, int G, float* out, cudaStream_t st);
 int arapk_ada_lpf(const float* samples, const int* valid, int V, float lpf_parameter, float* out /* G^3 x 9 */,
                   cudaStream_t st);
+/* JudgeEmptyGrid, GaussianView.cpp:4272-4318; scratch >= G^3 bytes */
+int arapk_judge_empty_grid(const int* valid, int V, const float* aim_opacity, int G, int* empty_out, void* scratch,
+                           size_t scratch_bytes, cudaStream_t st);
 int arapk_grid_eval(const int* valid, int V, const int* prefix, const int* lists, const float* samples, const float* pos,
                     const float* rot, const float* scale, const float* opacity, const float* shs, const float* ada_lpf,
                     float* out_feature, float* out_opacity, cudaStream_t st);

@@ -64,11 +64,15 @@ class OracleSession:
         self.gstep = O.grid_step(self.aabb, self.G)
         self._build_lists()
 
+    def ada_lpf_update(self):  # GetAdaLpfRatio on the deformed samples (GV:958, 1704-1706)
+        self.ada_lpf = O.ada_lpf(self.sample_pos, self.valid, self.G, self.lpf_parameter)
+
     def grid_eval(self, which=0):
         g = self.g
         f, o = O.grid_eval(self.valid, self.fp_prefix, self.lists, self.sample_pos, g["pos"], g["rot"], g["scale"], g["opacity"], g["shs"], self.ada_lpf)
         if which == 0:
             self.aim_feature, self.aim_opacity = f, o
+            self.empty_grid = O.judge_empty(self.valid, self.G, o)   # GPUSetupSamplesFeatures -> JudgeEmptyGrid (GV:4268)
         else:
             self.cur_feature, self.cur_opacity = f, o
         return f, o

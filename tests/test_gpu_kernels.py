@@ -96,7 +96,7 @@ def test_lbs_points_bit_exact(pkg, orc, k):
     bi, bw = _blocked(idx, w, k)
     xf = torch.empty(M * 112, dtype=torch.uint8, device="cuda")
     d_rot, d_trans, d_nodes, d_pts = dev(rot), dev(trans), dev(nodes), dev(pts)
-    pkg.check(lib.arapk_node_xf(M, ptr(d_rot), ptr(d_trans), ptr(d_nodes), ptr(xf), stream()))
+    pkg.check(lib.arapk_node_xf(M, ptr(d_rot), ptr(d_trans), ptr(d_nodes), ptr(xf), None, stream()))
     d_bi, d_bw, d_skip = dev(bi), dev(bw), dev(skip)
     pkg.check(lib.arapk_lbs_points(ptr(d_pts), ptr(d_pts), C.c_longlong(P), k, ptr(d_bi), ptr(d_bw), ptr(xf), ptr(d_skip), 1, stream()))
     torch.cuda.synchronize()
@@ -129,7 +129,7 @@ def test_lbs_tiles_bit_exact(pkg, orc, k):
     bi, bw = _blocked(idx, w, k)
     xf = torch.empty(M * 112, dtype=torch.uint8, device="cuda")
     d_rot, d_trans, d_nodes = dev(rot), dev(trans), dev(nodes)
-    pkg.check(lib.arapk_node_xf(M, ptr(d_rot), ptr(d_trans), ptr(d_nodes), ptr(xf), stream()))
+    pkg.check(lib.arapk_node_xf(M, ptr(d_rot), ptr(d_trans), ptr(d_nodes), ptr(xf), None, stream()))
     d_bi, d_bw, d_skip = dev(bi), dev(bw), dev(skip)
     nt, cap = lib.arapk_lbs_tile_count(P), lib.arapk_lbs_tile_cap()
     d_slots = torch.zeros(((P + 31) // 32) * 32 * 3, dtype=torch.int32, device="cuda")
