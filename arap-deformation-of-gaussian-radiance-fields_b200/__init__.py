@@ -36,7 +36,7 @@ class Params(C.Structure):
                 ("w_rot", C.c_double), ("w_reg", C.c_double), ("w_con", C.c_double),
                 ("max_gn_iters", C.c_int), ("max_cg_iters", C.c_int), ("cg_tol", C.c_double),
                 ("skip_static_endpoints", C.c_int), ("solver_global_memory", C.c_int), ("lbs_mode", C.c_int),
-                ("newton_eta0", C.c_double), ("warm_start", C.c_int), ("solver_ctas", C.c_int)]
+                ("newton_eta0", C.c_double), ("warm_start", C.c_int), ("solver_ctas", C.c_int), ("fps_mode", C.c_int)]
 
 
 class SolveStats(C.Structure):
@@ -58,6 +58,11 @@ class DeviceView(C.Structure):
                 ("valid_grid", C.c_void_p), ("grid_gs_prefix_sum", C.c_void_p), ("grided_gs_idx", C.c_void_p),
                 ("gs_init_grid_idx", C.c_void_p), ("ada_lpf_ratio", C.c_void_p), ("end_points", C.c_void_p),
                 ("empty_grid", C.c_void_p), ("cur_feature", C.c_void_p), ("cur_opacity", C.c_void_p)]
+
+
+class GatheredView(C.Structure):
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("n_per_rank", C.c_longlong), ("pos", C.c_void_p), ("rot", C.c_void_p),
+                ("scale", C.c_void_p), ("shs", C.c_void_p), ("side_stream", C.c_void_p)]
 
 
 _lib = None
@@ -95,6 +100,13 @@ def _np(a, dtype):
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the C ABI (rank 0; hand the 128 bytes to the other ranks out of band)."""
+    buf = C.create_string_buffer(128)
+    check(lib().arap_comm_unique_id(buf))
+    return buf.raw
 
 
 def default_params(**kw) -> Params:
@@ -330,6 +342,19 @@ class Session:
         p = _np(pts, f32).reshape(-1, 3)
         check(lib().arap_set_mesh_points(self._ctx, _ptr(p), len(p), int(bool(nodes_on_mesh))))
 
+    def set_points(self, family, pts):
+        """family 0 = textured-mesh points, 1 = soup points (arap_set_points); skinned every step."""
+        p = _np(pts, f32).reshape(-1, 3)
+        self._npts = getattr(self, "_npts", {})
+        self._npts[int(family)] = len(p)
+        check(lib().arap_set_points(self._ctx, int(family), _ptr(p), C.c_longlong(len(p))))
+
+    def download_points(self, family, n=None):
+        n = self._npts[int(family)] if n is None else n
+        out = np.zeros((n, 3), f32)
+        check(lib().arap_download_points(self._ctx, int(family), _ptr(out)))
+        return out
+
     def graph_build_fps(self, node_num=None, k=None):
         check(lib().arap_graph_build_fps(self._ctx, int(node_num or self.params.node_num), int(k or self.params.knn_k)))
         return self.download_graph()
@@ -439,6 +464,27 @@ class Session:
         ms = np.zeros(len(self.SETUP_STAGES), f32)
         check(lib().arap_setup_timing(self._ctx, _ptr(ms), len(ms)))
         return {k: float(v) for k, v in zip(self.SETUP_STAGES, ms)}
+
+    # -- multi-GPU exchange (arap_comm_*)
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        check(lib().arap_comm_init(self._ctx, C.c_char_p(unique_id), int(rank), int(world)))
+
+    def comm_exchange(self):
+        check(lib().arap_comm_exchange(self._ctx))
+
+    def comm_materialize_sh(self):
+        check(lib().arap_comm_materialize_sh(self._ctx))
+
+    def comm_sync(self):
+        check(lib().arap_comm_sync(self._ctx))
+
+    def comm_view(self) -> GatheredView:
+        v = GatheredView()
+        check(lib().arap_comm_view(self._ctx, C.byref(v)))
+        return v
+
+    def comm_destroy(self):
+        check(lib().arap_comm_destroy(self._ctx))
 
     def enable_timing(self, on=True):
         check(lib().arap_enable_timing(self._ctx, int(bool(on))))

@@ -62,7 +62,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 4))) as ex:
         list(ex.map(_compile, jobs))
     if jobs or not SO.exists():
-        _compile([NVCC, *ARCH, "-shared", "-o", str(SO), *map(str, objs), "-lcudart"])
+        _compile([NVCC, *ARCH, "-shared", "-o", str(SO), *map(str, objs), "-lcudart", "-ldl"])
     # headless replay CLI (tools/arap_replay.cpp): plain C++ over the C ABI, linked against the library next to it
     cli_src = HERE.parent / "tools" / "arap_replay.cpp"
     if cli_src.exists() and (jobs or not CLI.exists() or cli_src.stat().st_mtime > CLI.stat().st_mtime):

@@ -149,11 +149,20 @@ k_segsort_warp(long long ncell, const int* __restrict__ prefix, int* __restrict_
   for (int i = lane; i < n; i += 32) data[b + i] = a[i];
 }
 
-__global__ void __launch_bounds__(512)
+// cells longer than SEG_WARP_CAP: one CTA per cell, sorted in shared memory when the list fits (SEG_BLOCK_CAP entries),
+// else in place in global memory
+constexpr int SEG_BLOCK_CAP = 49152;   // 192 KB of dynamic shared memory
+__global__ void __launch_bounds__(1024)
 k_segsort_block(const int* __restrict__ big_list, const int* __restrict__ prefix, int* __restrict__ data) {
+  extern __shared__ int s_seg[];
   const int c = big_list[blockIdx.x];
   const int b = c ? prefix[c - 1] : 0, e = prefix[c];
-  bitonic_steps(data + b, e - b, threadIdx.x, blockDim.x, true);
+  const int n = e - b;
+  if (n > SEG_BLOCK_CAP) { bitonic_steps(data + b, n, threadIdx.x, blockDim.x, true); return; }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s_seg[i] = data[b + i];
+  __syncthreads();
+  bitonic_steps(s_seg, n, threadIdx.x, blockDim.x, true);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) data[b + i] = s_seg[i];
 }
 
 // ------------------------------------------------------------------ cell assignment
@@ -476,7 +485,11 @@ static int sort_segments(long long ncell, const int* prefix, int* data, int* big
   int nbig = 0;
   ARAP_CUDA_TRY(cudaMemcpyAsync(&nbig, big, sizeof(int), cudaMemcpyDeviceToHost, st));
   ARAP_CUDA_TRY(cudaStreamSynchronize(st));
-  if (nbig > 0) { k_segsort_block<<<nbig, 512, 0, st>>>(big + 1, prefix, data); ARAP_KERNEL_CHECK(); }
+  if (nbig > 0) {
+    static bool attr_set = false;
+    if (!attr_set) { ARAP_CUDA_TRY(cudaFuncSetAttribute(k_segsort_block, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_BLOCK_CAP * (int)sizeof(int))); attr_set = true; }
+    k_segsort_block<<<nbig, 1024, SEG_BLOCK_CAP * sizeof(int), st>>>(big + 1, prefix, data); ARAP_KERNEL_CHECK();
+  }
   return ARAP_OK;
 }
 }  // namespace

@@ -15,6 +15,7 @@
 // k_knn_slow).
 #include <cooperative_groups.h>
 #include <cfloat>
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -116,6 +117,219 @@ __global__ void k_fps_first(const float* __restrict__ pos, long long N, FpsBest*
     FpsBest b = s_best[0];
     for (int t = 1; t < (int)(blockDim.x >> 5); t++) b = comb(b, s_best[t]);
     block_best[blockIdx.x] = b;
+  }
+}
+
+// ------------------------------------------------------------------ FPS, pruned by the density grid
+// After the first passes the update of a selection step is local: a point's minimum distance can only drop if the new node
+// is closer to it than its current value, and every current value is <= the distance at which the new node was picked.
+// The candidate points are the cell-ordered Gaussians (cell c = [prefix[c-1], prefix[c])), so per-cell maxima
+// (value, first index) and per-supercell maxima (SG^3 cells) are kept next to the per-point distances; a step visits only
+// the supercells / cells whose box is closer to the new node than their maximum, updates their points with the exact
+// reference expression and repairs the two maxima.  The arg-max is the reduction of the supercell maxima with the
+// reference's first-maximum tie-break (value, then lowest index), so the selected sequence is the reference's, bit for bit.
+// One CTA runs the whole loop (a step is ~2 us of dependent loads; a grid-wide barrier per step would cost more than that).
+struct FpsGrid { float min[3]; float step; int G, SG, ns; };
+constexpr int FPS_LIST = 3072;   // marked cells of one selection step (shared-memory list); more -> the per-supercell walk   // ns = supercells per axis, SG = cells per supercell axis
+
+__device__ __forceinline__ FpsBest fps_better_or_empty(FpsBest a, FpsBest b) {   // v < 0 marks "no point"
+  if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
+  return a;
+}
+
+// conservative lower bound of the distance from p to the box [lo, hi]^3 of cells (rounded float arithmetic on both sides)
+__device__ __forceinline__ float fps_box_mind(const float* p, const FpsGrid& g, int x0, int y0, int z0, int x1, int y1, int z1) {
+  const int lo[3] = {x0, y0, z0}, hi[3] = {x1, y1, z1};
+  float s = 0.f;
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    const float bl = g.min[a] + lo[a] * g.step, bh = g.min[a] + (hi[a] + 1) * g.step;
+    const float gap = fmaxf(0.f, fmaxf(bl - p[a], p[a] - bh));
+    s += gap * gap;
+  }
+  return fmaxf(0.f, sqrtf(s) - 1e-4f * g.step) * 0.99999f;
+}
+
+__global__ void k_fps_cellmax(long long ncell, const int* __restrict__ prefix, const float* __restrict__ dist, FpsBest* __restrict__ cm) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  const int b = c ? prefix[c - 1] : 0, e = prefix[c];
+  FpsBest best{-1.0f, 0x7fffffff};
+  for (int j = b; j < e; j++) best = fps_better_or_empty(best, FpsBest{dist[j], j});
+  cm[c] = best;
+}
+
+__global__ void __launch_bounds__(1024)
+k_fps_pruned(const float* __restrict__ pos, FpsGrid g, const int* __restrict__ prefix, float* __restrict__ dist, FpsBest* __restrict__ cm,
+             int m0, int m, int* __restrict__ out) {
+  __shared__ FpsBest s_sm[4096];       // supercell maxima
+  __shared__ FpsBest s_w[32];
+  __shared__ int s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ns = g.ns, nsup = ns * ns * ns, G = g.G, SG = g.SG, cps = SG * SG * SG;
+  const int sgs = 31 - __clz(SG);    // SG is a power of two
+  // supercell maxima from the cell maxima
+  for (int s = warp; s < nsup; s += 32) {
+    const int sx = s / (ns * ns), sy = (s / ns) % ns, sz = s % ns;
+    FpsBest best{-1.0f, 0x7fffffff};
+    for (int t = lane; t < cps; t += 32) {
+      const int x = sx * SG + t / (SG * SG), y = sy * SG + (t / SG) % SG, z = sz * SG + t % SG;
+      if (x < G && y < G && z < G) best = fps_better_or_empty(best, cm[((long long)x * G + y) * G + z]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = fps_better_or_empty(best, FpsBest{__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.i, o)});
+    if (lane == 0) s_sm[s] = best;
+  }
+  __shared__ float s_rad;
+  __shared__ int s_list[FPS_LIST];
+  __shared__ int s_nlist;
+  __syncthreads();
+  {   // radius of the first pruned step: the current maximum of the minimum distances (the value out[m0 - 1] was picked at)
+    float v = -1.0f;
+    for (int s = tid; s < nsup; s += 1024) v = fmaxf(v, s_sm[s].v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) s_w[warp].v = v;
+    __syncthreads();
+    if (tid == 0) {
+      float r = -1.0f;
+      for (int w = 0; w < 32; w++) r = fmaxf(r, s_w[w].v);
+      s_rad = r; s_last = out[m0 - 1];
+    }
+  }
+  __syncthreads();
+  for (int c = m0; c < m; c++) {
+    const int last = s_last;
+    const float p[3] = {pos[3LL * last], pos[3LL * last + 1], pos[3LL * last + 2]};
+    // every current minimum distance is <= the value at which `last` was picked: only supercells meeting that ball matter
+    const float R = s_rad;
+    int slo[3], shi[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const float ext = SG * g.step;
+      slo[a] = R > 1e30f ? 0 : max(0, min(ns - 1, (int)floorf((p[a] - R - g.min[a]) / ext) - 1));
+      shi[a] = R > 1e30f ? ns - 1 : max(0, min(ns - 1, (int)floorf((p[a] + R - g.min[a]) / ext) + 1));
+    }
+    const int by = shi[1] - slo[1] + 1, bz = shi[2] - slo[2] + 1, nbox = (shi[0] - slo[0] + 1) * by * bz;
+    // (1) mark: every cell of the supercells in the box whose own box is closer to the new node than its maximum
+    if (tid == 0) s_nlist = 0;
+    __syncthreads();
+    // one warp per supercell of the box; a supercell farther from the new node than its own maximum is skipped as a whole
+    // (the selection loop runs on ONE SM: it is bound by instructions issued, so cells are only looked at where they can matter)
+    for (int t = warp; t < nbox; t += 32) {
+      const int sx = slo[0] + t / (by * bz), sy = slo[1] + (t / bz) % by, sz = slo[2] + t % bz;
+      const FpsBest sb = s_sm[(sx * ns + sy) * ns + sz];
+      if (sb.v < 0.f) continue;
+      const int x0 = sx << sgs, y0 = sy << sgs, z0 = sz << sgs;
+      if (fps_box_mind(p, g, x0, y0, z0, min(x0 + SG, G) - 1, min(y0 + SG, G) - 1, min(z0 + SG, G) - 1) >= sb.v) continue;
+      for (int u = lane; u < cps; u += 32) {
+        const int x = x0 + (u >> (2 * sgs)), y = y0 + ((u >> sgs) & (SG - 1)), z = z0 + (u & (SG - 1));
+        if (x >= G || y >= G || z >= G) continue;
+        const float md = fps_box_mind(p, g, x, y, z, x, y, z);
+        if (md >= sb.v) continue;
+        const int cell = (x * G + y) * G + z;
+        const FpsBest cb = cm[cell];
+        if (cb.v >= 0.f && md < cb.v) {
+          const int slot = atomicAdd(&s_nlist, 1);
+          if (slot < FPS_LIST) s_list[slot] = cell;
+        }
+      }
+    }
+    __syncthreads();
+    const int nlist = s_nlist;
+    if (nlist <= FPS_LIST) {
+      // (2) update: eight lanes per marked cell
+      const int sub = tid & 7;
+      for (int base = 0; base < nlist; base += 128) {     // warp-uniform trip count: the group reductions below use full-warp shuffles
+        const int ci = base + (tid >> 3);
+        const bool have = ci < nlist;
+        const long long cc = have ? s_list[ci] : 0;
+        const int b = have ? (cc ? prefix[cc - 1] : 0) : 0, e = have ? prefix[cc] : 0;
+        FpsBest best{-1.0f, 0x7fffffff};
+        for (int j = b + sub; j < e; j += 8) {
+          const double dx = (double)(p[0] - pos[3LL * j]), dy = (double)(p[1] - pos[3LL * j + 1]), dz = (double)(p[2] - pos[3LL * j + 2]);
+          const float dd = (float)sqrt(dx * dx + dy * dy + dz * dz);
+          float cur = dist[j];
+          if (dd < cur) { cur = dd; dist[j] = dd; }
+          best = fps_better_or_empty(best, FpsBest{cur, j});
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) best = fps_better_or_empty(best, FpsBest{__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.i, o)});
+        if (sub == 0 && have) cm[cc] = best;
+      }
+      __syncthreads();
+      // (3) repair the maxima of the supercells in the box
+      for (int t = warp; t < nbox; t += 32) {
+        const int sx = slo[0] + t / (by * bz), sy = slo[1] + (t / bz) % by, sz = slo[2] + t % bz;
+        const int s = (sx * ns + sy) * ns + sz;
+        const float sv = s_sm[s].v;
+        if (sv < 0.f) continue;
+        const int x0 = sx << sgs, y0 = sy << sgs, z0 = sz << sgs;
+        if (fps_box_mind(p, g, x0, y0, z0, min(x0 + SG, G) - 1, min(y0 + SG, G) - 1, min(z0 + SG, G) - 1) >= sv) continue;   // untouched in (1)
+        FpsBest sup{-1.0f, 0x7fffffff};
+        for (int u = lane; u < cps; u += 32) {
+          const int x = sx * SG + u / (SG * SG), y = sy * SG + (u / SG) % SG, z = sz * SG + u % SG;
+          if (x < G && y < G && z < G) sup = fps_better_or_empty(sup, cm[((long long)x * G + y) * G + z]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sup = fps_better_or_empty(sup, FpsBest{__shfl_xor_sync(0xffffffffu, sup.v, o), __shfl_xor_sync(0xffffffffu, sup.i, o)});
+        if (lane == 0) s_sm[s] = sup;
+      }
+    } else
+    // the marked cells do not fit the list (early steps, large radius): one warp per supercell walks its cells
+    for (int t = warp; t < nbox; t += 32) {
+      const int sx = slo[0] + t / (by * bz), sy = slo[1] + (t / bz) % by, sz = slo[2] + t % bz;
+      const int s = (sx * ns + sy) * ns + sz;
+      const FpsBest sb = s_sm[s];
+      if (sb.v < 0.f) continue;
+      const int x0 = sx * SG, y0 = sy * SG, z0 = sz * SG;
+      if (fps_box_mind(p, g, x0, y0, z0, min(x0 + SG, G) - 1, min(y0 + SG, G) - 1, min(z0 + SG, G) - 1) >= sb.v) continue;   // warp-uniform
+      FpsBest sup{-1.0f, 0x7fffffff};
+      for (int tb = 0; tb < cps; tb += 32) {
+        const int t2 = tb + lane;
+        const int x = x0 + t2 / (SG * SG), y = y0 + (t2 / SG) % SG, z = z0 + t2 % SG;
+        const bool in = t2 < cps && x < G && y < G && z < G;
+        const long long cell = ((long long)x * G + y) * G + z;
+        FpsBest cb{-1.0f, 0x7fffffff};
+        if (in) cb = cm[cell];
+        const bool need = in && cb.v >= 0.f && fps_box_mind(p, g, x, y, z, x, y, z) < cb.v;
+        unsigned todo = __ballot_sync(0xffffffffu, need);
+        while (todo) {     // the warp updates the points of one marked cell at a time
+          const int src = __ffs(todo) - 1; todo &= todo - 1;
+          const long long cc = __shfl_sync(0xffffffffu, cell, src);
+          const int b = cc ? prefix[cc - 1] : 0, e = prefix[cc];
+          FpsBest best{-1.0f, 0x7fffffff};
+          for (int j = b + lane; j < e; j += 32) {
+            const double dx = (double)(p[0] - pos[3LL * j]), dy = (double)(p[1] - pos[3LL * j + 1]), dz = (double)(p[2] - pos[3LL * j + 2]);
+            const float dd = (float)sqrt(dx * dx + dy * dy + dz * dz);
+            float cur = dist[j];
+            if (dd < cur) { cur = dd; dist[j] = dd; }
+            best = fps_better_or_empty(best, FpsBest{cur, j});
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) best = fps_better_or_empty(best, FpsBest{__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.i, o)});
+          if (lane == src) { cb = best; cm[cc] = best; }
+        }
+        sup = fps_better_or_empty(sup, cb);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sup = fps_better_or_empty(sup, FpsBest{__shfl_xor_sync(0xffffffffu, sup.v, o), __shfl_xor_sync(0xffffffffu, sup.i, o)});
+      if (lane == 0) s_sm[s] = sup;
+    }
+    __syncthreads();
+    FpsBest best{-1.0f, 0x7fffffff};
+    for (int s = tid; s < nsup; s += 1024) best = fps_better_or_empty(best, s_sm[s]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = fps_better_or_empty(best, FpsBest{__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.i, o)});
+    if (lane == 0) s_w[warp] = best;
+    __syncthreads();
+    if (warp == 0) {
+      FpsBest b = s_w[lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) b = fps_better_or_empty(b, FpsBest{__shfl_xor_sync(0xffffffffu, b.v, o), __shfl_xor_sync(0xffffffffu, b.i, o)});
+      if (lane == 0) { s_last = b.i; s_rad = b.v; out[c] = b.i; }
+    }
+    __syncthreads();
   }
 }
 
@@ -236,20 +450,14 @@ __device__ __forceinline__ void knn_store(const KnnOut& o, long long q, int k, c
   }
 }
 
-// KQ = compile-time capacity (k+1 <= KQ)
+// Ring search of one query over the node buckets: expands Chebyshev rings until the (k+1)-th distance is provably final.
+// d / id: ascending (k+1) best; tie: two candidates at the same distance among / at the rim of the best (exact replay needed).
 template <int KQ>
-__global__ void __launch_bounds__(128)
-k_knn_fast(const float* __restrict__ queries, long long Q, int k, BucketGrid bg, const int* __restrict__ cell_start,
-           const float4* __restrict__ sorted, KnnOut out, int* __restrict__ slow_count, long long* __restrict__ slow_list,
-           float* __restrict__ slow_thr) {
-  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= Q) return;
-  const int kq = k + 1;
-  const float qx = queries[3 * q], qy = queries[3 * q + 1], qz = queries[3 * q + 2];
-  float d[KQ]; int id[KQ];
+__device__ __forceinline__ void knn_ring_search(float qx, float qy, float qz, int kq, const BucketGrid& bg, const int* __restrict__ cell_start,
+                                                const float4* __restrict__ sorted, float (&d)[KQ], int (&id)[KQ], bool& tie) {
 #pragma unroll
   for (int j = 0; j < KQ; j++) { d[j] = FLT_MAX; id[j] = -1; }
-  bool tie = false;
+  tie = false;
   int found = 0;
   const int cx = bucket_coord(qx, bg.min[0], bg.inv_h, bg.dim[0]);
   const int cy = bucket_coord(qy, bg.min[1], bg.inv_h, bg.dim[1]);
@@ -273,8 +481,6 @@ k_knn_fast(const float* __restrict__ queries, long long Q, int k, BucketGrid bg,
             const float4 n = __ldg(sorted + t);
             const float dd = knn_dist(qx, qy, qz, n.x, n.y, n.z);
             found++;
-            const float worst = d[KQ - 1 < kq - 1 ? KQ - 1 : kq - 1];
-            (void)worst;
             float dw = FLT_MAX;
 #pragma unroll
             for (int j = 0; j < KQ; j++) if (j == kq - 1) dw = d[j];
@@ -310,6 +516,21 @@ k_knn_fast(const float* __restrict__ queries, long long Q, int k, BucketGrid bg,
       if (dw < bound - 1e-5f * (fabsf(bound) + bg.h)) break;
     }
   }
+}
+
+// first version: one thread per query, every query walks the buckets on its own (kept as the fallback of k_knn_tile and
+// for the few-query calls: node graph, bucket bounds)
+template <int KQ>
+__global__ void __launch_bounds__(128)
+k_knn_fast(const float* __restrict__ queries, long long Q, int k, BucketGrid bg, const int* __restrict__ cell_start,
+           const float4* __restrict__ sorted, KnnOut out, int* __restrict__ slow_count, long long* __restrict__ slow_list,
+           float* __restrict__ slow_thr) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  const int kq = k + 1;
+  const float qx = queries[3 * q], qy = queries[3 * q + 1], qz = queries[3 * q + 2];
+  float d[KQ]; int id[KQ]; bool tie;
+  knn_ring_search<KQ>(qx, qy, qz, kq, bg, cell_start, sorted, d, id, tie);
   if (tie) {
     float dw = FLT_MAX;
 #pragma unroll
@@ -320,6 +541,180 @@ k_knn_fast(const float* __restrict__ queries, long long Q, int k, BucketGrid bg,
     return;
   }
   knn_store<KQ>(out, q, k, d, id);
+}
+
+// Upper bound of the (KNN_MAX + 1)-th neighbour distance at every bucket centre (index build): for ANY point q,
+//   d_(k+1)(q) <= |q - centre_b| + D_b     (triangle inequality, k <= KNN_MAX),
+// which is what lets a tile of queries agree on one candidate set before looking at a single node.
+__global__ void __launch_bounds__(128)
+k_bucket_bounds(int ncell, int kq, BucketGrid bg, const int* __restrict__ cell_start, const float4* __restrict__ sorted,
+                float* __restrict__ bound) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  const int z = c % bg.dim[2], y = (c / bg.dim[2]) % bg.dim[1], x = c / (bg.dim[2] * bg.dim[1]);
+  const float qx = bg.min[0] + (x + 0.5f) * bg.h, qy = bg.min[1] + (y + 0.5f) * bg.h, qz = bg.min[2] + (z + 0.5f) * bg.h;
+  float d[KNN_MAX + 1]; int id[KNN_MAX + 1]; bool tie;
+  knn_ring_search<KNN_MAX + 1>(qx, qy, qz, kq, bg, cell_start, sorted, d, id, tie);
+  float dw = FLT_MAX;
+#pragma unroll
+  for (int j = 0; j < KNN_MAX + 1; j++) if (j == kq - 1) dw = d[j];
+  bound[c] = dw;
+}
+
+// ------------------------------------------------------------------ kNN, one candidate set per tile of queries
+// Query families arrive in cell order (end points of cell-ordered Gaussians, the 64 samples of a cell), so a tile of 128
+// consecutive queries is a compact cloud.  Each query bounds its own (k+1)-th distance by B(q) = |q - centre_b| + D_b;
+// every node that can enter ANY of the tile's results lies in the tile's bounding box grown by max B.  The CTA collects
+// the nodes of the buckets meeting that box once into shared memory (a few dozen), and every thread then selects its
+// k+1 nearest from the staged list: broadcast shared-memory reads and no per-query bucket walk.  Arithmetic and tie
+// handling are those of the per-query kernel (exact float distance expression, ties replayed by k_knn_slow); a tile
+// whose candidate list does not fit falls back to the per-query walk.
+constexpr int KT_TILE = 128;
+constexpr int KT_CAP = 1024;   // staged candidates (power of two: sorted in place by a bitonic network)
+
+// KQ = k + 1 at compile time (9, 11, 13 for k = 8, 10, 12; other k run with the next larger KQ and a run-time kq).
+template <int KQ, bool EXACT_KQ>
+__global__ void __launch_bounds__(KT_TILE)
+k_knn_tile(const float* __restrict__ queries, long long Q, int k, BucketGrid bg, const int* __restrict__ cell_start,
+           const float4* __restrict__ sorted, const float* __restrict__ bucket_bound, KnnOut out, int* __restrict__ slow_count,
+           long long* __restrict__ slow_list, float* __restrict__ slow_thr) {
+  __shared__ float4 s_cand[KT_CAP];
+  __shared__ float s_key[KT_CAP];       // distance of a candidate to the tile centre (sort key)
+  __shared__ float s_red[7][KT_TILE / 32];
+  __shared__ int s_cnt;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long q = (long long)blockIdx.x * KT_TILE + tid;
+  const bool live = q < Q;
+  const int kq = EXACT_KQ ? KQ : k + 1;
+  float qx = 0.f, qy = 0.f, qz = 0.f, B = 0.f;
+  float r[7] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX, 0.f};   // bbox min, bbox max, max B
+  if (live) {
+    qx = queries[3 * q]; qy = queries[3 * q + 1]; qz = queries[3 * q + 2];
+    const int cx = bucket_coord(qx, bg.min[0], bg.inv_h, bg.dim[0]);
+    const int cy = bucket_coord(qy, bg.min[1], bg.inv_h, bg.dim[1]);
+    const int cz = bucket_coord(qz, bg.min[2], bg.inv_h, bg.dim[2]);
+    const float ux = qx - (bg.min[0] + (cx + 0.5f) * bg.h), uy = qy - (bg.min[1] + (cy + 0.5f) * bg.h), uz = qz - (bg.min[2] + (cz + 0.5f) * bg.h);
+    const float Db = bucket_bound[(cx * bg.dim[1] + cy) * bg.dim[2] + cz];
+    B = (sqrtf(ux * ux + uy * uy + uz * uz) + Db) * 1.00001f + 1e-6f * bg.h;   // margin: rounded float arithmetic on both sides
+    r[0] = qx; r[1] = qy; r[2] = qz; r[3] = qx; r[4] = qy; r[5] = qz; r[6] = B;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) { r[c] = fminf(r[c], __shfl_xor_sync(0xffffffffu, r[c], o)); r[3 + c] = fmaxf(r[3 + c], __shfl_xor_sync(0xffffffffu, r[3 + c], o)); }
+    r[6] = fmaxf(r[6], __shfl_xor_sync(0xffffffffu, r[6], o));
+  }
+  if (lane == 0)
+#pragma unroll
+    for (int c = 0; c < 7; c++) s_red[c][warp] = r[c];
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < KT_TILE / 32; w++) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) { r[c] = fminf(r[c], s_red[c][w]); r[3 + c] = fmaxf(r[3 + c], s_red[3 + c][w]); }
+    r[6] = fmaxf(r[6], s_red[6][w]);
+  }
+  const float Bmax = r[6];
+  bool fits = Bmax < 1e30f;
+  int lo[3], hi[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    lo[c] = bucket_coord(r[c] - Bmax, bg.min[c], bg.inv_h, bg.dim[c]);
+    hi[c] = bucket_coord(r[3 + c] + Bmax, bg.min[c], bg.inv_h, bg.dim[c]);
+  }
+  const int ny = hi[1] - lo[1] + 1, nz = hi[2] - lo[2] + 1;
+  const int nb = (hi[0] - lo[0] + 1) * ny * nz;
+  if (nb > 8192) fits = false;
+  const float mx = 0.5f * (r[0] + r[3]), my = 0.5f * (r[1] + r[4]), mz = 0.5f * (r[2] + r[5]);   // tile centre
+  if (fits) {
+    for (int t = tid; t < nb; t += KT_TILE) {
+      const int x = lo[0] + t / (ny * nz), y = lo[1] + (t / nz) % ny, z = lo[2] + t % nz;
+      const int c = (x * bg.dim[1] + y) * bg.dim[2] + z;
+      const int b = cell_start[c], e = cell_start[c + 1];
+      if (e > b) {
+        const int p0 = atomicAdd(&s_cnt, e - b);
+        if (p0 + (e - b) <= KT_CAP)
+          for (int u = b; u < e; u++) {
+            const float4 n = __ldg(sorted + u);
+            const float ax = n.x - mx, ay = n.y - my, az = n.z - mz;
+            s_cand[p0 + u - b] = n; s_key[p0 + u - b] = ax * ax + ay * ay + az * az;
+          }
+      }
+    }
+  }
+  __syncthreads();
+  const int cnt = s_cnt;
+  const bool staged = fits && cnt <= KT_CAP;
+  if (staged && cnt > 1) {
+    // candidates in ascending distance from the tile centre: a query's first k+1 candidates are then (nearly) its nearest,
+    // the running (k+1)-th distance is tight at once and almost every later candidate fails the first comparison.
+    // The order is only a speed-up: without ties the result is the ascending-distance list whatever the scan order.
+    int np = 2; while (np < cnt) np <<= 1;
+    for (int t = cnt + tid; t < np; t += KT_TILE) s_key[t] = FLT_MAX;
+    __syncthreads();
+    for (int kk = 2; kk <= np; kk <<= 1)
+      for (int j = kk >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < np; i += KT_TILE) {
+          const int p = i ^ j;
+          if (p > i) {
+            const bool up = (i & kk) == 0;
+            const float a = s_key[i], b = s_key[p];
+            if ((a > b) == up) { s_key[i] = b; s_key[p] = a; const float4 t4 = s_cand[i]; s_cand[i] = s_cand[p]; s_cand[p] = t4; }
+          }
+        }
+        __syncthreads();
+      }
+  }
+  if (!live) return;
+  float d[KQ]; int id[KQ]; bool tie = false;
+  if (!staged) {
+    knn_ring_search<KQ>(qx, qy, qz, kq, bg, cell_start, sorted, d, id, tie);
+  } else {
+#pragma unroll
+    for (int j = 0; j < KQ; j++) { d[j] = FLT_MAX; id[j] = -1; }
+    float dw = B;    // B >= this query's (k+1)-th distance: farther nodes can neither enter nor tie; then the running (k+1)-th distance
+    bool full = false;
+    for (int t = 0; t < cnt; t++) {
+      const float4 n = s_cand[t];
+      const float dd = knn_dist(qx, qy, qz, n.x, n.y, n.z);
+      if (dd > dw) continue;
+      if (full && dd == dw) { tie = true; continue; }
+      float cd = dd; int ci = __float_as_int(n.w);
+#pragma unroll
+      for (int j = 0; j < KQ; j++) {
+        if (EXACT_KQ || j < kq) {
+          if (cd == d[j] && cd != FLT_MAX) tie = true;   // empty slots hold FLT_MAX and must not count as ties
+          if (cd < d[j]) { const float td = d[j]; const int ti = id[j]; d[j] = cd; id[j] = ci; cd = td; ci = ti; }
+        }
+      }
+      float last = d[KQ - 1];
+      if (!EXACT_KQ) {
+#pragma unroll
+        for (int j = 0; j < KQ; j++) if (j == kq - 1) last = d[j];
+      }
+      if (last != FLT_MAX) { dw = last; full = true; }
+    }
+  }
+  if (tie) {
+    float dw = d[KQ - 1];
+    if (!EXACT_KQ) {
+#pragma unroll
+      for (int j = 0; j < KQ; j++) if (j == kq - 1) dw = d[j];
+    }
+    const int slot = atomicAdd(slow_count, 1);
+    slow_list[slot] = q;
+    slow_thr[slot] = dw;
+    return;
+  }
+  if (EXACT_KQ && KQ < KNN_MAX + 1) {   // knn_store works on the full-width arrays
+    float df[KNN_MAX + 1]; int idf[KNN_MAX + 1];
+#pragma unroll
+    for (int j = 0; j < KNN_MAX + 1; j++) { df[j] = j < KQ ? d[j < KQ ? j : 0] : FLT_MAX; idf[j] = j < KQ ? id[j < KQ ? j : 0] : -1; }
+    knn_store<KNN_MAX + 1>(out, q, k, df, idf);
+  } else {
+    knn_store<KQ>(out, q, k, d, id);
+  }
 }
 
 // ------------------------------------------------------------------ kNN exact slow path
@@ -455,6 +850,34 @@ extern "C" int arapk_fps(const float* pos, long long N, int node_num, int* out_i
   return ARAP_OK;
 }
 
+// FPS over cell-ordered points with the density grid as the pruning structure (see k_fps_pruned).  prefix = inclusive
+// per-cell point counts (G^3), min3 / step / G = the grid of arap_grid_build.  scratch: N floats + 64 KB + G^3 * 8 bytes.
+extern "C" size_t arapk_fps_grid_scratch_bytes(long long N, int G) {
+  return (((size_t)N * 4 + 255) / 256) * 256 + 65536 + (size_t)G * G * G * sizeof(FpsBest) + 256;
+}
+extern "C" int arapk_fps_grid(const float* pos, long long N, int node_num, const int* cell_prefix, const float* min3_host, float step,
+                              int G, int* out_idx_dev, void* scratch, size_t scratch_bytes, int* out_count_host, cudaStream_t st) {
+  const int m = (int)std::min<long long>(node_num, N);
+  const int M0 = 128;   // full passes before the pruned loop takes over (the first steps touch most of the cloud)
+  if (scratch_bytes < arapk_fps_grid_scratch_bytes(N, G)) { set_error("fps_grid: scratch too small"); return ARAP_ERR_INVALID; }
+  int cnt = 0;
+  int rc = arapk_fps(pos, N, std::min(m, M0), out_idx_dev, scratch, (((size_t)N * 4 + 255) / 256) * 256 + 65536, &cnt, st);
+  if (rc) return rc;
+  if (out_count_host) *out_count_host = m;
+  if (m <= M0) return ARAP_OK;
+  float* dist = (float*)scratch;
+  FpsBest* cm = (FpsBest*)((char*)scratch + (((size_t)N * 4 + 255) / 256) * 256 + 65536);
+  const long long ncell = (long long)G * G * G;
+  k_fps_cellmax<<<(unsigned)((ncell + 255) / 256), 256, 0, st>>>(ncell, cell_prefix, dist, cm);
+  ARAP_KERNEL_CHECK();
+  FpsGrid g; g.min[0] = min3_host[0]; g.min[1] = min3_host[1]; g.min[2] = min3_host[2]; g.step = step; g.G = G;
+  g.SG = 1; while (g.SG * 16 < G) g.SG <<= 1;     // power of two with at most 16 supercells per axis (4096 in shared memory)
+  g.ns = (G + g.SG - 1) / g.SG;
+  k_fps_pruned<<<1, 1024, 0, st>>>(pos, g, cell_prefix, dist, cm, M0, m, out_idx_dev);
+  ARAP_KERNEL_CHECK();
+  return ARAP_OK;
+}
+
 namespace {
 struct BucketState {
   BucketGrid bg; int ncell;
@@ -465,12 +888,12 @@ struct BucketState {
 //   [cell_cnt ncell][cell_start ncell+1][fill ncell][node_cell M][sorted M float4][minmax 6 floats][slow_count][err]
 extern "C" size_t arapk_knn_workspace_bytes(int M) {
   const size_t max_cells = 128 * 128 * 128;
-  return (max_cells * 3 + 16) * sizeof(int) + (size_t)M * sizeof(int) + (size_t)M * sizeof(float4) + 4096;
+  return (max_cells * 4 + 16) * sizeof(int) + (size_t)M * sizeof(int) + (size_t)M * sizeof(float4) + 4096;
 }
 
 struct ArapKnnIndex {
   BucketGrid bg; int ncell; int M;
-  int *cell_cnt, *cell_start, *fill, *node_cell; float4* sorted; float* minmax; int* counters;
+  int *cell_cnt, *cell_start, *fill, *node_cell; float4* sorted; float* minmax; int* counters; float* bucket_bound;
   const float* nodes;
 };
 
@@ -486,6 +909,7 @@ extern "C" int arapk_knn_build(const float* nodes_dev, int M, void* workspace, s
   ix->cell_cnt = (int*)p; p += max_cells * sizeof(int);
   ix->cell_start = (int*)p; p += (max_cells + 16) * sizeof(int);
   ix->fill = (int*)p; p += max_cells * sizeof(int);
+  ix->bucket_bound = (float*)p; p += max_cells * sizeof(float);
   ix->node_cell = (int*)p; p += (((size_t)M * sizeof(int) + 255) / 256) * 256;
   ix->sorted = (float4*)p; p += (size_t)M * sizeof(float4);
   p = (char*)((((uintptr_t)p + 255) / 256) * 256);
@@ -517,6 +941,8 @@ extern "C" int arapk_knn_build(const float* nodes_dev, int M, void* workspace, s
   ARAP_KERNEL_CHECK();
   k_bucket_fill<<<(M + 255) / 256, 256, 0, st>>>(M, nodes_dev, ix->node_cell, ix->cell_start, ix->fill, ix->sorted);
   ARAP_KERNEL_CHECK();
+  k_bucket_bounds<<<(ix->ncell + 127) / 128, 128, 0, st>>>(ix->ncell, std::min(M, KNN_MAX + 1), bg, ix->cell_start, ix->sorted, ix->bucket_bound);
+  ARAP_KERNEL_CHECK();
   return ARAP_OK;
 }
 
@@ -536,8 +962,19 @@ extern "C" int arapk_knn_query(const void* index, const float* queries_dev, long
   KnnOut out{idx_plain, w_plain, idx_blk, w_blk, wf_blk, idx_kq};
   ARAP_CUDA_TRY(cudaMemsetAsync(ix->counters, 0, 2 * sizeof(int), st));
   const unsigned grid = (unsigned)((Q + 127) / 128);
-  k_knn_fast<KNN_MAX + 1><<<grid, 128, 0, st>>>(queries_dev, Q, k, ix->bg, ix->cell_start, ix->sorted, out, ix->counters,
-                                                slow_list, slow_thr);
+  static int mode = -1;   // ARAP_KNN_TILE=0: the per-query bucket walk of the first version for every call (measurement aid)
+  if (mode < 0) { const char* ev = getenv("ARAP_KNN_TILE"); mode = ev ? atoi(ev) : 1; }
+  if (mode && ix->M >= KNN_MAX + 1) {
+#define ARAP_KNN_TILE_ARGS queries_dev, Q, k, ix->bg, ix->cell_start, ix->sorted, ix->bucket_bound, out, ix->counters, slow_list, slow_thr
+    if (k == 8) k_knn_tile<9, true><<<grid, KT_TILE, 0, st>>>(ARAP_KNN_TILE_ARGS);
+    else if (k == 10) k_knn_tile<11, true><<<grid, KT_TILE, 0, st>>>(ARAP_KNN_TILE_ARGS);
+    else if (k == 12) k_knn_tile<13, true><<<grid, KT_TILE, 0, st>>>(ARAP_KNN_TILE_ARGS);
+    else k_knn_tile<KNN_MAX + 1, false><<<grid, KT_TILE, 0, st>>>(ARAP_KNN_TILE_ARGS);
+#undef ARAP_KNN_TILE_ARGS
+  }
+  else
+    k_knn_fast<KNN_MAX + 1><<<grid, 128, 0, st>>>(queries_dev, Q, k, ix->bg, ix->cell_start, ix->sorted, out, ix->counters,
+                                                  slow_list, slow_thr);
   ARAP_KERNEL_CHECK();
   int h[2] = {0, 0};
   ARAP_CUDA_TRY(cudaMemcpyAsync(h, ix->counters, sizeof(h), cudaMemcpyDeviceToHost, st));

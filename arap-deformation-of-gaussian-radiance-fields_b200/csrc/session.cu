@@ -4,6 +4,7 @@
 // device resident; the host keeps only graph topology and block bookkeeping.
 //
 // Reference call sites are cited per function (GV = GaussianView.cpp).
+#include <dlfcn.h>
 #include <array>
 #include <cstdarg>
 #include <cstring>
@@ -117,9 +118,9 @@ __global__ void k_blocked_to_rows(long long Q, int k, const uint16_t* __restrict
 // ------------------------------------------------------------------ device buffer helper
 template <typename T>
 struct DBuf {
-  T* p = nullptr; size_t n = 0;
+  T* p = nullptr; size_t n = 0; bool owned = true;
   ~DBuf() { release(); }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void release() { if (p && owned) cudaFree(p); p = nullptr; n = 0; owned = true; }
   int alloc(size_t count) {
     if (count <= n && p) return ARAP_OK;
     release();
@@ -128,7 +129,8 @@ struct DBuf {
     if (e != cudaSuccess) { set_error(std::string("cudaMalloc(") + std::to_string(count * sizeof(T)) + "): " + cudaGetErrorString(e)); return ARAP_ERR_CUDA; }
     n = count; return ARAP_OK;
   }
-  void swap(DBuf& o) { std::swap(p, o.p); std::swap(n, o.n); }
+  void view(T* ptr, size_t count) { release(); p = ptr; n = count; owned = false; }   // borrowed range of another allocation
+  void swap(DBuf& o) { std::swap(p, o.p); std::swap(n, o.n); std::swap(owned, o.owned); }
 };
 
 struct RowTable {  // blocked skinning rows of one query family
@@ -164,6 +166,9 @@ struct arap_ctx {
   DBuf<char> grid_scratch;
   // mesh points ("simplified_points")
   int Mp = 0; bool nodes_on_mesh = false; DBuf<float> mesh_pts;
+  // further point families skinned every step with predict_mesh (GV:2989-3020): [0] mesh_points of the textured mesh
+  // (setupWeightsforMesh, GV:2834-2845), [1] soup_points of <ply>_soup.obj (setupWeightsforSoup, GV:2862-2873)
+  struct Extra { long long n = 0; DBuf<float> pts; RowTable rows; } extra[ARAP_POINT_FAMILIES];
   // graph
   bool graph_ready = false;
   int M = 0, k = 0;
@@ -186,6 +191,13 @@ struct arap_ctx {
   cudaEvent_t ev_soa = nullptr;   // recorded after the six-point fit of every apply: the rasteriser-facing SoA is final
   cudaEvent_t ev_release = nullptr;  // caller's event (not owned): its reads of the SoA are done; the next fit waits for it
   bool solved = false;
+  // multi-GPU exchange (arap_comm_*): gathered arrays of all ranks; this rank's SoA lives inside them
+  struct Comm {
+    void* nccl = nullptr;            // ncclComm_t
+    int rank = 0, world = 1;
+    DBuf<float> pos_all, rot_all, scale_all, shs_all, rot_base;
+    cudaStream_t side = nullptr; cudaEvent_t ev_done = nullptr;
+  } comm;
   // timing
   // timing: a ring of per-step event sets so a whole timed region can be read back afterwards
   static constexpr int TRING = 128;
@@ -209,6 +221,7 @@ struct StageTimer {
 #define CTX_CHECK(c) do { if (!(c)) { set_error("null ctx"); return ARAP_ERR_INVALID; } cudaSetDevice((c)->device); } while (0)
 #define TRY(x) do { int _rc = (x); if (_rc != ARAP_OK) return _rc; } while (0)
 
+static void comm_destroy(arap_ctx* ctx);
 extern "C" const char* arap_last_error(void) { return g_err.c_str(); }
 extern "C" int arap_version(void) { return 100; }
 
@@ -216,7 +229,7 @@ extern "C" int arap_default_params(arap_params* p) {
   if (!p) return ARAP_ERR_INVALID;
   p->grid_num = 64; p->padding = 1; p->knn_k = 10; p->node_num = 150; p->high_quality = 0; p->lpf_parameter = 0.2f;
   p->w_rot = 1.0; p->w_reg = 10.0; p->w_con = 100.0; p->max_gn_iters = 30; p->max_cg_iters = 4000; p->cg_tol = 1e-10;
-  p->skip_static_endpoints = 0; p->solver_global_memory = 0; p->lbs_mode = 0; p->newton_eta0 = 1e-6; p->warm_start = 1; p->solver_ctas = 0;
+  p->skip_static_endpoints = 0; p->solver_global_memory = 0; p->lbs_mode = 0; p->newton_eta0 = 1e-6; p->warm_start = 1; p->solver_ctas = 0; p->fps_mode = 0;
   return ARAP_OK;
 }
 
@@ -250,6 +263,7 @@ extern "C" int arap_destroy(arap_ctx* ctx) {
   if (!ctx) return ARAP_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  comm_destroy(ctx);
   if (ctx->stats_h) cudaFreeHost(ctx->stats_h);
   for (auto& row : ctx->evr) for (auto& ev : row) if (ev) cudaEventDestroy(ev);
   if (ctx->ev_soa) cudaEventDestroy(ctx->ev_soa);
@@ -281,6 +295,7 @@ extern "C" int arap_set_gaussians(arap_ctx* ctx, long long n, const float* pos, 
   CTX_CHECK(ctx);
   if (n <= 0 || !pos || !rot || !scale || !opacity || !shs) { set_error("set_gaussians: bad arguments"); return ARAP_ERR_INVALID; }
   const bool d = src_is_device != 0; cudaStream_t st = ctx->stream;
+  if (ctx->comm.nccl) { set_error("set_gaussians: not while a multi-GPU exchange is initialised (arap_comm_destroy first)"); return ARAP_ERR_STATE; }
   ctx->N = n;
   TRY(upload(ctx->pos, pos, (size_t)n * 3, d, st)); TRY(upload(ctx->rot, rot, (size_t)n * 4, d, st));
   TRY(upload(ctx->scale, scale, (size_t)n * 3, d, st)); TRY(upload(ctx->opacity, opacity, (size_t)n, d, st));
@@ -556,6 +571,19 @@ static int build_unions(arap_ctx* c) {
   return ARAP_OK;
 }
 
+// Skinning tables of the active lbs_mode (built once per graph): union tables for mode 3; per-tile node lists / slots for the
+// bit-faithful staged kernels (modes 0 and 2), which the node and mesh-point rows use in every mode.
+static int ensure_tables(arap_ctx* c) {
+  const int mode = c->prm.lbs_mode;
+  if (mode == 3 && !c->end_rows.usw.p) TRY(build_unions(c));
+  if (mode != 1) {
+    if (!c->node_rows.slots.p) { TRY(build_tiles(c, c->node_rows)); TRY(build_tiles(c, c->mesh_rows)); }
+    for (auto& x : c->extra) if (x.n > 0 && !x.rows.slots.p) TRY(build_tiles(c, x.rows));
+    if (mode != 3 && !c->end_rows.slots.p) { TRY(build_tiles(c, c->end_rows)); TRY(build_tiles(c, c->sample_rows)); }
+  }
+  return ARAP_OK;
+}
+
 // LBS of one row family.  prm.lbs_mode: 0 = staged node records + FP64-pipe float rounding (default),
 // 1 = global-memory gathers (first version), 2 = staged records, rounding by conversion instructions.
 static int lbs_family(arap_ctx* c, const float* in, float* out, const RowTable& t, const uint8_t* skip, int group) {
@@ -619,9 +647,11 @@ static int finish_graph(arap_ctx* c, int k) {
   { StageTimer tmr(c, ARAP_ST_KNN_ENDS); TRY(knn_family(c, c->ends.p, c->N * 6, k, c->end_rows, false)); }
   { StageTimer tmr(c, ARAP_ST_KNN_SAMPLES); TRY(knn_family(c, c->sample_pos.p, c->S, k, c->sample_rows, true)); }
   TRY(knn_family(c, c->mesh_pts.p, c->Mp, k, c->mesh_rows, false));
+  for (auto& x : c->extra) { x.rows.slots.release(); TRY(knn_family(c, x.pts.p, x.n, k, x.rows, false)); }
   StageTimer tmr_tiles(c, ARAP_ST_TILE_TABLES);
-  TRY(build_unions(c));
-  TRY(build_tiles(c, c->end_rows)); TRY(build_tiles(c, c->sample_rows)); TRY(build_tiles(c, c->mesh_rows)); TRY(build_tiles(c, c->node_rows));
+  // per-mode skinning tables: the ones of the configured lbs_mode now, the others on first use (ensure_tables)
+  for (RowTable* t : {&c->end_rows, &c->sample_rows, &c->mesh_rows, &c->node_rows}) { t->slots.release(); t->boff.release(); t->usw.release(); }
+  TRY(ensure_tables(c));
   // solve outputs
   TRY(c->rot_d.alloc((size_t)M * 9)); TRY(c->trans_d.alloc((size_t)M * 3)); TRY(c->stats_d.alloc(32));
   TRY(c->warm_d.alloc(arapk_solve_warm_doubles(M)));
@@ -643,6 +673,27 @@ extern "C" int arap_set_mesh_points(arap_ctx* ctx, const float* pts, int n, int 
   return ARAP_OK;
 }
 
+// mesh_points (family 0) / soup_points (family 1): skinned every step like the reference's UpdatePosition (GV:2989-3020).
+// Set before the graph build (their kNN rows are computed with the other families, GV:4846-4850); a later call needs a rebuild.
+extern "C" int arap_set_points(arap_ctx* ctx, int family, const float* pts, long long n) {
+  CTX_CHECK(ctx);
+  if (family < 0 || family >= ARAP_POINT_FAMILIES || n < 0 || (n > 0 && !pts)) { set_error("set_points: bad arguments"); return ARAP_ERR_INVALID; }
+  arap_ctx::Extra& x = ctx->extra[family];
+  x.n = n;
+  TRY(upload(x.pts, pts, (size_t)n * 3, false, ctx->stream));
+  ARAP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->graph_ready = false;
+  return ARAP_OK;
+}
+extern "C" int arap_download_points(arap_ctx* ctx, int family, float* pts) {
+  CTX_CHECK(ctx);
+  if (family < -1 || family >= ARAP_POINT_FAMILIES) { set_error("download_points: bad family"); return ARAP_ERR_INVALID; }
+  if (family == -1) TRY(download(pts, ctx->mesh_pts.p, (size_t)ctx->Mp * 3, ctx->stream));     // simplified_points (arap_set_mesh_points)
+  else TRY(download(pts, ctx->extra[family].pts.p, (size_t)ctx->extra[family].n * 3, ctx->stream));
+  ARAP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return ARAP_OK;
+}
+
 extern "C" int arap_graph_build_fps(arap_ctx* ctx, int node_num, int k) {
   CTX_CHECK(ctx);
   if (!ctx->grid_ready) { set_error("graph_build: call arap_grid_build first (the graph indexes the re-ordered Gaussians)"); return ARAP_ERR_STATE; }
@@ -653,11 +704,14 @@ extern "C" int arap_graph_build_fps(arap_ctx* ctx, int node_num, int k) {
   if (ctx->nodes_on_mesh) node_num = ctx->Mp;  // LoadMeshForGraph: node_num = simplified_points.size() (GV:4952-4954)
   const int m = (int)std::min<long long>(node_num, nc);
   DBuf<int> out; TRY(out.alloc((size_t)std::max(m, 1)));
-  DBuf<char> scratch; TRY(scratch.alloc((size_t)nc * 4 + 65536 + 512));
+  // Gaussian centres are in cell order after arap_grid_build: the grid prunes the selection loop (same sequence, bit for bit)
+  const bool pruned = !ctx->nodes_on_mesh && ctx->prm.fps_mode == 0;
+  DBuf<char> scratch; TRY(scratch.alloc(pruned ? arapk_fps_grid_scratch_bytes(nc, ctx->G) : (size_t)nc * 4 + 65536 + 512));
   int cnt = 0;
   {
     StageTimer tmr(ctx, ARAP_ST_FPS);
-    TRY(arapk_fps(cand, nc, node_num, out.p, scratch.p, scratch.n, &cnt, st));
+    if (pruned) TRY(arapk_fps_grid(cand, nc, node_num, ctx->cell_prefix.p, ctx->aabb, ctx->step, ctx->G, out.p, scratch.p, scratch.n, &cnt, st));
+    else TRY(arapk_fps(cand, nc, node_num, out.p, scratch.p, scratch.n, &cnt, st));
     ctx->h_anchor.resize(cnt);
     ARAP_CUDA_TRY(cudaMemcpyAsync(ctx->h_anchor.data(), out.p, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, st));
     ARAP_CUDA_TRY(cudaStreamSynchronize(st));
@@ -916,8 +970,10 @@ extern "C" int arap_apply(arap_ctx* ctx) {
   cudaStream_t st = ctx->stream; const int M = ctx->M, k = ctx->k;
   const bool tm = ctx->timing;
   if (tm) cudaEventRecord(ctx->ev[1], st);
+  TRY(ensure_tables(ctx));
   TRY(arapk_node_xf(M, ctx->rot_d.p, ctx->trans_d.p, ctx->node_pos.p, ctx->node_xf.p, ctx->node_xf32.p, st));
   if (ctx->Mp > 0) TRY(lbs_family(ctx, ctx->mesh_pts.p, ctx->mesh_pts.p, ctx->mesh_rows, nullptr, 1));
+  for (auto& x : ctx->extra) if (x.n > 0) TRY(lbs_family(ctx, x.pts.p, x.pts.p, x.rows, nullptr, 1));
   const bool fused = ctx->prm.lbs_mode == 3 && ctx->end_rows.usw.p;
   if (!fused) TRY(lbs_family(ctx, ctx->ends.p, ctx->ends.p, ctx->end_rows, ctx->prm.skip_static_endpoints ? ctx->gs_static.p : nullptr, 6));
   TRY(lbs_family(ctx, ctx->node_pos.p, ctx->node_next.p, ctx->node_rows, nullptr, 1));
@@ -1002,6 +1058,163 @@ extern "C" int arap_download_nodes(arap_ctx* ctx, float* node_pos, double* rot, 
   TRY(download(node_pos, ctx->node_pos.p, (size_t)ctx->M * 3, ctx->stream));
   TRY(download(rot, ctx->rot_d.p, (size_t)ctx->M * 9, ctx->stream)); TRY(download(trans, ctx->trans_d.p, (size_t)ctx->M * 3, ctx->stream));
   ARAP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return ARAP_OK;
+}
+
+// ------------------------------------------------------------------ multi-GPU exchange
+// Stages (a), (b), (d) shard by Gaussian index, the node solve is replicated (deterministic), so the only data-path collective
+// of a drag step is the exchange of the deformed Gaussians.  Here it is an in-place NCCL all-gather of pos / rot / scale
+// (40 of the 232 bytes per Gaussian): after arap_comm_init this rank's SoA lives INSIDE the gathered arrays (the fit kernel
+// writes its shard straight into them), one grouped all-gather per step runs on a high-priority side stream as soon as the
+// six-point fit is done (ev_soa) and overlaps the two sample passes; the next fit waits for it.  The SH rows (192 bytes) are
+// not sent: a receiver holds each remote row at the rotation it was valid for (rot_base) and, when a consumer on this rank
+// needs the rows (arap_comm_materialize_sh), rotates them once by q_now * q_base^-1 — the composition of the owner's
+// per-step rotations (GV:3138-3154); the copies agree with the owner's to float rounding (~1e-6 after hundreds of steps).
+// NCCL is loaded at run time (libnccl.so.2): the library has no link-time dependency on it.
+struct Id128 { char b[128]; };   // ncclUniqueId (passed by value to ncclCommInitRank)
+namespace {
+struct NcclApi {
+  void* h = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr; int (*GroupEnd)() = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+}  // namespace
+static NcclApi g_nccl;
+static int nccl_load() {
+  if (g_nccl.h) return ARAP_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) { set_error(std::string("arap_comm: cannot load libnccl.so.2: ") + dlerror()); return ARAP_ERR_UNSUPPORTED; }
+  NcclApi a; a.h = h;
+  a.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+  a.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(h, "ncclCommInitRank");
+  a.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+  a.GroupStart = (int (*)())dlsym(h, "ncclGroupStart"); a.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
+  a.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+  a.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  if (!a.GetUniqueId || !a.CommInitRank || !a.AllGather || !a.GroupStart || !a.GroupEnd || !a.CommDestroy) { set_error("arap_comm: libnccl lacks a required symbol"); return ARAP_ERR_UNSUPPORTED; }
+  g_nccl = a;
+  return ARAP_OK;
+}
+#define NCCL_TRY(x) do { int _r = (x); if (_r != 0) { set_error(std::string(#x) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "nccl error")); return ARAP_ERR_CUDA; } } while (0)
+constexpr int kNcclFloat = 7;   // ncclFloat32
+
+extern "C" int arap_comm_unique_id(char id_out[128]) {
+  if (!id_out) return ARAP_ERR_INVALID;
+  TRY(nccl_load());
+  NCCL_TRY(g_nccl.GetUniqueId(id_out));
+  return ARAP_OK;
+}
+
+extern "C" int arap_comm_init(arap_ctx* ctx, const char id[128], int rank, int world) {
+  CTX_CHECK(ctx);
+  if (!id || world < 1 || rank < 0 || rank >= world) { set_error("comm_init: bad arguments"); return ARAP_ERR_INVALID; }
+  if (ctx->N <= 0) { set_error("comm_init: set the Gaussians first (every rank the same count)"); return ARAP_ERR_STATE; }
+  if (ctx->comm.nccl) { set_error("comm_init: already initialised"); return ARAP_ERR_STATE; }
+  TRY(nccl_load());
+  arap_ctx::Comm& cm = ctx->comm;
+  Id128 uid; memcpy(uid.b, id, 128);
+  NCCL_TRY(g_nccl.CommInitRank(&cm.nccl, world, uid, rank));
+  cm.rank = rank; cm.world = world;
+  const size_t n = (size_t)ctx->N, W = (size_t)world;
+  TRY(cm.pos_all.alloc(W * n * 3)); TRY(cm.rot_all.alloc(W * n * 4)); TRY(cm.scale_all.alloc(W * n * 3)); TRY(cm.shs_all.alloc(W * n * 48));
+  TRY(cm.rot_base.alloc(W * n * 4));
+  int lo = 0, hi = 0;
+  ARAP_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  ARAP_CUDA_TRY(cudaStreamCreateWithPriority(&cm.side, cudaStreamNonBlocking, hi));
+  ARAP_CUDA_TRY(cudaEventCreateWithFlags(&cm.ev_done, cudaEventDisableTiming));
+  cudaStream_t st = ctx->stream;
+  // move this rank's SoA into its slot of the gathered arrays; from here on the session's arrays are views of them
+  auto move = [&](DBuf<float>& own, DBuf<float>& all, size_t w) -> int {
+    float* dst = all.p + (size_t)rank * n * w;
+    ARAP_CUDA_TRY(cudaMemcpyAsync(dst, own.p, n * w * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    ARAP_CUDA_TRY(cudaStreamSynchronize(st));
+    own.view(dst, n * w);
+    return ARAP_OK;
+  };
+  TRY(move(ctx->pos, cm.pos_all, 3)); TRY(move(ctx->rot, cm.rot_all, 4)); TRY(move(ctx->scale, cm.scale_all, 3)); TRY(move(ctx->shs, cm.shs_all, 48));
+  // initial state: everything, once (in-place all-gathers)
+  NCCL_TRY(g_nccl.GroupStart());
+  NCCL_TRY(g_nccl.AllGather(ctx->pos.p, cm.pos_all.p, n * 3, kNcclFloat, cm.nccl, st));
+  NCCL_TRY(g_nccl.AllGather(ctx->rot.p, cm.rot_all.p, n * 4, kNcclFloat, cm.nccl, st));
+  NCCL_TRY(g_nccl.AllGather(ctx->scale.p, cm.scale_all.p, n * 3, kNcclFloat, cm.nccl, st));
+  NCCL_TRY(g_nccl.AllGather(ctx->shs.p, cm.shs_all.p, n * 48, kNcclFloat, cm.nccl, st));
+  NCCL_TRY(g_nccl.GroupEnd());
+  ARAP_CUDA_TRY(cudaMemcpyAsync(cm.rot_base.p, cm.rot_all.p, W * n * 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  ARAP_CUDA_TRY(cudaStreamSynchronize(st));
+  return ARAP_OK;
+}
+
+// One exchange per drag step, after arap_step / arap_apply: asynchronous (side stream), ordered after the step's six-point fit;
+// the next arap_apply waits for it before it overwrites the SoA.
+extern "C" int arap_comm_exchange(arap_ctx* ctx) {
+  CTX_CHECK(ctx);
+  arap_ctx::Comm& cm = ctx->comm;
+  if (!cm.nccl) { set_error("comm_exchange: arap_comm_init first"); return ARAP_ERR_STATE; }
+  const size_t n = (size_t)ctx->N;
+  ARAP_CUDA_TRY(cudaStreamWaitEvent(cm.side, ctx->ev_soa, 0));
+  NCCL_TRY(g_nccl.GroupStart());
+  NCCL_TRY(g_nccl.AllGather(ctx->pos.p, cm.pos_all.p, n * 3, kNcclFloat, cm.nccl, cm.side));
+  NCCL_TRY(g_nccl.AllGather(ctx->rot.p, cm.rot_all.p, n * 4, kNcclFloat, cm.nccl, cm.side));
+  NCCL_TRY(g_nccl.AllGather(ctx->scale.p, cm.scale_all.p, n * 3, kNcclFloat, cm.nccl, cm.side));
+  NCCL_TRY(g_nccl.GroupEnd());
+  ARAP_CUDA_TRY(cudaEventRecord(cm.ev_done, cm.side));
+  ctx->ev_release = cm.ev_done;
+  return ARAP_OK;
+}
+
+// Brings the SH rows of the remote shards up to date with the gathered rotations (call before a consumer on this rank reads
+// arap_gathered_view.shs, e.g. once per rendered frame; not needed per drag step).  Runs on the side stream after the last exchange.
+extern "C" int arap_comm_materialize_sh(arap_ctx* ctx) {
+  CTX_CHECK(ctx);
+  arap_ctx::Comm& cm = ctx->comm;
+  if (!cm.nccl) { set_error("comm_materialize_sh: arap_comm_init first"); return ARAP_ERR_STATE; }
+  const long long n = ctx->N; const long long lo = (long long)cm.rank * n, tot = (long long)cm.world * n;
+  const long long rng[2][2] = {{0, lo}, {lo + n, tot}};
+  for (auto& r : rng) {
+    if (r[1] <= r[0]) continue;
+    TRY(arapk_replay_shs(r[1] - r[0], cm.rot_base.p + 4 * r[0], cm.rot_all.p + 4 * r[0], nullptr, cm.shs_all.p + 48 * r[0], cm.side));
+    ARAP_CUDA_TRY(cudaMemcpyAsync(cm.rot_base.p + 4 * r[0], cm.rot_all.p + 4 * r[0], (size_t)(r[1] - r[0]) * 4 * sizeof(float), cudaMemcpyDeviceToDevice, cm.side));
+  }
+  ARAP_CUDA_TRY(cudaEventRecord(cm.ev_done, cm.side));
+  ctx->ev_release = cm.ev_done;
+  return ARAP_OK;
+}
+
+extern "C" int arap_comm_sync(arap_ctx* ctx) {
+  CTX_CHECK(ctx);
+  if (ctx->comm.side) ARAP_CUDA_TRY(cudaStreamSynchronize(ctx->comm.side));
+  return ARAP_OK;
+}
+
+extern "C" int arap_comm_view(arap_ctx* ctx, arap_gathered_view* o) {
+  CTX_CHECK(ctx); if (!o) return ARAP_ERR_INVALID;
+  arap_ctx::Comm& cm = ctx->comm;
+  if (!cm.nccl) { set_error("comm_view: arap_comm_init first"); return ARAP_ERR_STATE; }
+  o->rank = cm.rank; o->world = cm.world; o->n_per_rank = ctx->N;
+  o->pos = cm.pos_all.p; o->rot = cm.rot_all.p; o->scale = cm.scale_all.p; o->shs = cm.shs_all.p; o->side_stream = cm.side;
+  return ARAP_OK;
+}
+
+static void comm_destroy(arap_ctx* ctx) {
+  arap_ctx::Comm& cm = ctx->comm;
+  if (cm.side) { cudaStreamSynchronize(cm.side); }
+  if (cm.nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(cm.nccl);
+  if (cm.ev_done) cudaEventDestroy(cm.ev_done);
+  if (cm.side) cudaStreamDestroy(cm.side);
+  cm.nccl = nullptr; cm.side = nullptr; cm.ev_done = nullptr;
+}
+extern "C" int arap_comm_destroy(arap_ctx* ctx) {
+  CTX_CHECK(ctx);
+  if (ctx->comm.nccl) {   // the session keeps working on one GPU: its SoA stays where it is (views of the gathered arrays)
+    ARAP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (ctx->ev_release == ctx->comm.ev_done) ctx->ev_release = nullptr;
+    comm_destroy(ctx);
+  }
   return ARAP_OK;
 }
 

@@ -100,7 +100,7 @@ def setup_session(pkg, scenes, workload, n, rank, world, stream):
     cfg = scenes.CONFIGS[workload]
     sc = scenes.make_scene(workload, n=n, seed_offset=rank)
     s = pkg.Session(device=int(os.environ.get("LOCAL_RANK", 0)), stream=stream, grid_num=cfg["grid"], knn_k=cfg["k"],
-                    node_num=cfg["nodes"])
+                    node_num=cfg["nodes"], lbs_mode=3)
     t0 = time.perf_counter()
     s.set_gaussians(sc["pos"], sc["rot"], sc["scale"], sc["opacity"], sc["shs"])
     gi = s.grid_build()
@@ -169,30 +169,29 @@ def run_own(args):
     if args.max_cg is not None:
         s.set_params(max_cg_iters=args.max_cg)
 
-    gather = None
-    if world > 1:   # all-gather of the deformed SoA (232 B / Gaussian): pos 12 + rot 16 + scale 12 + SH 192
+    gather, abi_comm = None, False
+    gmode = os.environ.get("ARAP_GATHER", "abi")
+    if world > 1 and gmode == "abi":
+        # Default: the exchange behind the C ABI (arap_comm_*): in-place grouped NCCL all-gather of pos / rot / scale on the ctx's
+        # high-priority side stream, remote SH rows brought up to date lazily (arap_comm_materialize_sh, timed separately below).
+        # torch.distributed only carries the 128-byte NCCL id, the barriers and the max-over-ranks of the timings.
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(pkg.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        s.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+        abi_comm = True
+    elif world > 1:   # first-round variants through torch.distributed (parallel.py): whole-SoA NCCL gather, peer stores, pose + eager SH replay
         par = importlib.import_module(ge.PKG + ".parallel")
         v = s.device_view()
         parts = {name: torch.as_tensor(par.DevArray(getattr(v, name), (N, w)), device="cuda") for name, w in par.SOA_WIDTHS}
-        # Whole-SoA variants: NCCL all-gather (ARAP_GATHER=nccl) or peer stores through the copy engines (ARAP_GATHER=push).  Measured on 8 B200s:
-        # the copy engines sustain ~270 GB/s per rank for the 9.7 GB a rank sends per step (43.7 ms/step), NCCL's SM
-        # kernels ~900 GB/s (28.7 ms/step); at 2 GPUs both hide behind the sample passes (22.5 / 22.1 ms/step).
-        # Default: pose-only gather + SH replay on the receivers (parallel.SoAGatherPose) — bit-identical to the full gather
-        # (ARAP_GATHER_CHECK=1; verified on 2 GPUs) and faster: 2 GPUs 14.8 -> 14.6 ms per step, 4 GPUs 18.1 -> 15.9.
-        # ARAP_GATHER=nccl: all-gather of the whole SoA (232 B / Gaussian); ARAP_GATHER=push: peer stores by the copy engines.
-        if os.environ.get("ARAP_GATHER", "pose") == "pose":
+        if gmode == "pose":
             gs_static, _ = s.static_flags()
             gather = par.SoAGatherPose(parts, world, rank, pkg.lib(), torch.from_numpy(np.ascontiguousarray(gs_static).astype(np.uint8)).cuda())
-        elif os.environ.get("ARAP_GATHER", "pose") != "push":
+        elif gmode != "push":
             gather = par.SoAGather(parts, world)
         else:
             gather = par.SoAGatherPush(parts, world, rank)
-            ref = par.SoAGather(parts, world)()     # one NCCL all-gather of the initial SoA checks the peer-store path
-            torch.cuda.synchronize(); dist.barrier()
-            got = gather()
-            torch.cuda.synchronize(); dist.barrier()
-            assert all(torch.equal(ref[kk], got[kk]) for kk in ref), "peer-store all-gather differs from NCCL"
-            del ref
 
     side = torch.cuda.Stream(priority=-1) if gather else None
     ev_rel = torch.cuda.Event() if gather else None
@@ -202,6 +201,8 @@ def run_own(args):
         # written the SoA, concurrently with the sample SH pass of the same step; the next step's apply waits for it
         s.aim_translate(DRAG)
         s.step(False)
+        if abi_comm:
+            s.comm_exchange()
         if gather:
             s.soa_ready_wait(side.cuda_stream)
             with torch.cuda.stream(side):
@@ -232,11 +233,11 @@ def run_own(args):
     # of the reference's own rounding chain); the bit-faithful kernels (lbs_mode = 0, the parity checker) are timed first
     # on the same session and reported beside it.
     base = {kk: getattr(s.params, kk) for kk in ("lbs_mode", "warm_start", "newton_eta0", "solver_ctas")}
-    base["lbs_mode"] = 3
     for _ in range(max(args.warmup, 3)):
         one_step()
     barrier()
-    m0, _ = timed_block(10)          # library default: lbs_mode = 0
+    s.set_params(**{**base, "lbs_mode": 0})     # the bit-faithful kernels (their tables are built on first use, outside T_graph)
+    m0, _ = timed_block(10)
     stages_mode0 = [round(float(x), 4) for x in m0]
     # debug: stage timers of parameter variants on the same session (stderr).  --variants "lbs_mode=1;lbs_mode=2,warm_start=0"
     for spec in [v for v in args.variants.split(";") if v]:
@@ -258,6 +259,8 @@ def run_own(args):
         one_step()
     if gather:
         tstream.wait_stream(side)   # the last step's all-gather belongs to the timed region
+    if abi_comm:
+        s.comm_sync()               # ... so does the last arap_comm_exchange (side stream of the ctx)
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -280,6 +283,8 @@ def run_own(args):
         aim[active] += DRAG
         s.aim_set(aim)              # H2D M x 3 floats (+ sync)
         s.step(False)
+        if abi_comm:
+            s.comm_exchange()
         if gather:
             s.soa_ready_wait(side.cuda_stream)
             with torch.cuda.stream(side):
@@ -321,6 +326,26 @@ def run_own(args):
         stroke = {kk: round(stt[kk], 3) for kk in ("scene_aabb", "footprint_lists", "grid_eval")}
         s.set_blocks(setup["blocks"], setup["types"])
 
+    exchange = None
+    if abi_comm:   # remote SH rows on demand: one rotation of every remote row by the accumulated quaternion, device-timed
+        s.comm_sync(); barrier()
+        gv = s.comm_view()
+        side_s = torch.cuda.ExternalStream(gv.side_stream)
+        m0e, m1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0e.record(side_s); s.comm_materialize_sh(); m1e.record(side_s); s.comm_sync()
+        exchange = {"per_step": "in-place grouped ncclAllGather of pos/rot/scale (40 B x %d Gaussians received per rank)" % (N * (world - 1)),
+                    "materialize_remote_sh_ms": round(m0e.elapsed_time(m1e), 3), "remote_rows": N * (world - 1)}
+        if os.environ.get("ARAP_GATHER_CHECK"):   # the gathered copy against a full all-gather of the owners' arrays
+            par = importlib.import_module(ge.PKG + ".parallel")
+            v = s.device_view()
+            own = {name: torch.as_tensor(par.DevArray(getattr(v, name), (N, w)), device="cuda").clone() for name, w in par.SOA_WIDTHS}
+            ref = par.SoAGather(own, world)()
+            got = {name: torch.as_tensor(par.DevArray(getattr(gv, name), (N * world, w)), device="cuda") for name, w in par.SOA_WIDTHS}
+            barrier()
+            bad = [kk for kk in ("pos", "rot", "scale") if not torch.equal(ref[kk], got[kk])]
+            dsh = float((ref["shs"] - got["shs"]).abs().max())
+            print(json.dumps({"gather_check": "abi", "rank": rank, "mismatch": bad, "max_abs_shs_diff": dsh}), file=sys.stderr, flush=True)
+            assert not bad and dsh <= 2e-5, (bad, dsh)
     if gather is not None and os.environ.get("ARAP_GATHER_CHECK"):   # the gathered copy equals a full NCCL gather of the owners' SoA
         barrier()
         got = gather.outs
@@ -363,7 +388,7 @@ def run_own(args):
                    "constraints": "per-node (op type 4), two caps (|z|>0.4); the GUI's default bend mode (centre constraints, op type 1) is rank-deficient with two blocks and is covered by the parity tests with three",
                    "active_nodes": setup["n_active"], "pinned_nodes": setup["n_pinned"], "lbs_mode": lbs_mode,
                    "l2": "inputs (>1.4 GB SoA + tables per step) exceed the 126 MB L2",
-                   "parallelism": "replicated solve, Gaussians/samples sharded by index; every step all ranks exchange the deformed Gaussians on a high-priority side stream (starts when the six-point fit is done: overlaps the sample passes): NCCL all-gather of pos/rot/scale + bit-identical replay of the SH rotation on the receivers (ARAP_GATHER=nccl: all-gather of the whole SoA)" if world > 1 else "single GPU"},
+                   "parallelism": ("replicated solve, Gaussians/samples sharded by index; every step all ranks exchange the deformed Gaussians through the C ABI (arap_comm_exchange): in-place grouped NCCL all-gather of pos/rot/scale on a high-priority side stream, started when the six-point fit is done (overlaps the sample passes); remote SH rows are rotated on demand (arap_comm_materialize_sh, timed in `exchange`)" if abi_comm else "replicated solve, Gaussians/samples sharded by index; exchange variant ARAP_GATHER=" + gmode) if world > 1 else "single GPU"},
         "stages_ms": {"solve": round(float(mean[0]), 4), "sample_advect": round(float(mean[1]), 4), "endpoint_lbs": round(float(mean[2]), 4),
                       "six_point_fit": round(float(mean[3]), 4), "sample_sh_rotate": round(float(mean[4]), 4),
                       "note": "lbs_mode = 3: end-point skinning is fused into six_point_fit (k_apply_union); endpoint_lbs is then the node / mesh-point pass only" if lbs_mode == 3 else ""},
@@ -373,7 +398,7 @@ def run_own(args):
                   "row_phase_split_us": [round(x / 1e3 / max(st["cg_iters"], 1), 2) for x in st["row_sub_ns"]],
                   "cg_iters_gn": st["cg_iters_gn"][:st["gn_iters"]],
                   "row_phase_last_warp_us_and_barrier_us": [round(x / 1e3 / max(st["gn_iters"], 1), 2) for x in st["barrier_skew_ns"]]},
-        "drag_profile": drag_profile,
+        "drag_profile": drag_profile, "exchange": exchange,
         "apply_gaussians_per_s": round(N / (apply_ms * 1e-3), 1) if apply_ms > 0 else None,
         "setup_s": {"grid_build_eval": round(setup["t_grid_s"], 3), "graph_knn": round(setup["t_graph_s"], 3), "note": "host wall clock incl. allocation and table uploads; device stage times below"},
         # T_full = T_step + T_stroke + T_graph (device time, CUDA events on the ctx stream)
@@ -401,7 +426,7 @@ def run_own(args):
         ],
         "e2e": {"value": round(e2e_ms, 4), "unit": UNIT, "h2d_bytes_per_step": M * 12, "d2h_bytes_per_step": M * (12 + 72 + 24) + 64,
                 "what": "arap_aim_set(host aims) + arap_step + arap_download_nodes + arap_solve_stats_get per step"},
-        "gpu_launches": ((9 if lbs_mode == 3 else 10) + (1 if world > 1 and os.environ.get("ARAP_GATHER", "pose") == "pose" else 0)) * args.steps,   # rank 0, per step: aim_translate, group_aims, solve, node_xf, node lbs, [end-point lbs,] fit / apply_union, sample lbs, node_quats, rotate (+ arapk_replay_shs on its one remote range when N > 1)
+        "gpu_launches": ((9 if lbs_mode == 3 else 10) + (1 if world > 1 and gmode == "pose" else 0)) * args.steps,   # rank 0, per step: aim_translate, group_aims, solve, node_xf, node lbs, [end-point lbs,] fit / apply_union, sample lbs, node_quats, rotate (+ arapk_replay_shs on its one remote range when N > 1)
         "clocks": clk,
     }
     if world == 1 and not args.no_cpu_baseline:

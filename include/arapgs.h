@@ -79,6 +79,8 @@ typedef struct arap_params {
   int solver_ctas;     /* 0 (default): the solve uses one CTA per SM.  n > 0: at most n CTAs, leaving the other SMs to kernels that run
                           beside it — the multi-GPU driver reserves SMs for the NCCL all-gather of the previous step's SoA, which
                           otherwise cannot overlap the solve (a 512-thread solver CTA fills an SM's register file). */
+  int fps_mode;        /* node sampling (HC:139-195): 0 (default) = selection loop pruned by the density grid, 1 = one pass over all
+                          candidate points per node (first version).  Same node sequence, bit for bit. */
 } arap_params;
 
 typedef struct arap_solve_stats {
@@ -204,6 +206,13 @@ int arap_graph_build_anchors(arap_ctx* ctx, const int* anchor_idx, int m, int k)
 /* LoadMeshForGraph + "Build Graph on Mesh" + RebuildGraph (GV:4939-4959, 4825-4856): mesh points become the
  * candidate points; nodes = FPS over them with node_num = all. on_mesh=0 keeps nodes on Gaussians but still skins the mesh points. */
 int arap_set_mesh_points(arap_ctx* ctx, const float* pts, int n, int nodes_on_mesh);
+/* The reference's other skinned point sets: family 0 = mesh_points of the textured mesh (setupWeightsforMesh GV:2834-2845),
+ * family 1 = soup_points of <ply>_soup.obj (setupWeightsforSoup GV:2862-2873); both are moved every step by predict_mesh
+ * (UpdatePosition GV:2989-3020) with the bit-faithful kernel.  Call before the graph build.  arap_download_points: family -1 =
+ * the simplified points of arap_set_mesh_points. */
+#define ARAP_POINT_FAMILIES 2
+int arap_set_points(arap_ctx* ctx, int family, const float* pts, long long n);
+int arap_download_points(arap_ctx* ctx, int family, float* pts);
 /* DeformGraph::computeWeights for arbitrary device queries (DH:187-208): idx Q x k (uint32), w Q x k (double), device outputs. */
 int arap_knn_weights(arap_ctx* ctx, const float* queries_dev, long long q, int k, uint32_t* idx_dev, double* w_dev);
 int arap_download_graph(arap_ctx* ctx, int* anchor, float* node_pos, int* nbr /* M x k */);
@@ -250,6 +259,34 @@ int arap_last_step_timing(arap_ctx* ctx, float* ms6);
 int arap_enable_timing(arap_ctx* ctx, int on);
 /* stage timings (6 floats per step, same order) of the most recent steps since timing was enabled, oldest first (ring of 128) */
 int arap_step_timings(arap_ctx* ctx, float* ms, int max_steps, int* n_out);
+
+/* ---- multi-GPU: exchange of the deformed Gaussians between the ranks of one node --------------------
+ * One process (and one arap_ctx) per GPU; every rank owns a contiguous index range of the Gaussians (equal counts) and runs
+ * the replicated node solve.  No reference counterpart (the reference is single-GPU; its per-frame upload GV:1640-1647 is what
+ * the exchange replaces on the non-owning ranks).  Host protocol:
+ *   rank 0: arap_comm_unique_id(id) -> hand the 128 bytes to the other ranks out of band (MPI, a socket, torch.distributed ...)
+ *   all:    arap_set_gaussians(own shard) ... arap_comm_init(ctx, id, rank, world)   [collective; fetch arap_device_view again:
+ *           the SoA now lives inside the gathered arrays]
+ *   step:   arap_step(ctx, ...); arap_comm_exchange(ctx);                            [asynchronous: overlaps the sample passes]
+ *   frame:  arap_comm_materialize_sh(ctx); arap_comm_sync(ctx); read arap_comm_view  [only when this rank consumes remote SH rows]
+ * arap_comm_exchange all-gathers pos / rot / scale (40 B per Gaussian, in place, one grouped NCCL call over NVLink); the SH rows
+ * of remote Gaussians are brought up to date lazily by arap_comm_materialize_sh from the gathered rotations. */
+typedef struct arap_gathered_view {
+  int rank, world;
+  long long n_per_rank;
+  float* pos;    /* world * n x 3, rank-major */
+  float* rot;    /* world * n x 4 */
+  float* scale;  /* world * n x 3 */
+  float* shs;    /* world * n x 48; remote ranges valid after arap_comm_materialize_sh + arap_comm_sync */
+  void* side_stream; /* the cudaStream_t the exchange runs on */
+} arap_gathered_view;
+int arap_comm_unique_id(char id_out[128]);
+int arap_comm_init(arap_ctx* ctx, const char id[128], int rank, int world);
+int arap_comm_exchange(arap_ctx* ctx);
+int arap_comm_materialize_sh(arap_ctx* ctx);
+int arap_comm_sync(arap_ctx* ctx);
+int arap_comm_view(arap_ctx* ctx, arap_gathered_view* out);
+int arap_comm_destroy(arap_ctx* ctx);
 
 /* ---- deform.txt / graph.obj / config / scripts (host IO, byte-compatible) -- */
 typedef struct arap_history arap_history;

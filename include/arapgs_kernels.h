@@ -72,6 +72,10 @@ int arapk_sh_rotate_test(const float* R9, float* shs48_dev, int fast, cudaStream
 int arapk_minmax(const float* pts, long long N, float* out6_dev, cudaStream_t st);
 int arapk_fps(const float* pos, long long N, int node_num, int* out_idx_dev, void* scratch, size_t scratch_bytes,
               int* out_count_host, cudaStream_t st);
+/* the same selection over cell-ordered points, pruned by the density grid (bit-identical sequence) */
+size_t arapk_fps_grid_scratch_bytes(long long N, int G);
+int arapk_fps_grid(const float* pos, long long N, int node_num, const int* cell_prefix, const float* min3_host, float step, int G,
+                   int* out_idx_dev, void* scratch, size_t scratch_bytes, int* out_count_host, cudaStream_t st);
 size_t arapk_knn_workspace_bytes(int M);
 size_t arapk_knn_index_struct_bytes();
 int arapk_knn_build(const float* nodes_dev, int M, void* workspace, size_t workspace_bytes, void* index_out, cudaStream_t st);

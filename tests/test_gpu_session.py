@@ -30,12 +30,13 @@ def _compare_gaussians(out, ref, scene_scale=1.0, tol=REL_TOL):
     assert np.abs(out["shs"] - ref["shs"]).max() <= 5e-6
 
 
-def _compare_drift(s, o, scene_scale, max_ulp, tag, min_exact_share=0.0):
+def _compare_drift(s, o, scene_scale, max_ulp, tag, min_exact_share=0.0, max_abs=None):
     """Long free-running sequences.  The fit reads six float32 end points per Gaussian (the reference stores them as float32,
     GV:3021-3040), so parity on covariances is limited by parity on those: every last-bit difference of an end point
     (delta) moves the fitted axes of a Gaussian of smallest scale s by ~delta / (2 (s + 1e-3)).  Asserted:
       * means within 1e-5 of the scene scale;
-      * every end-point coordinate within `max_ulp` float ulps of the oracle's;
+      * every end-point coordinate within `max_ulp` float ulps of the oracle's (or, when the two solvers themselves differ
+        beyond float resolution — centre constraints, see DESIGN.md — within `max_abs` in absolute terms);
       * covariances within the plain 1e-5 wherever the Gaussian's end points agree bit for bit, and within
         1e-5 + 2 delta_g / (s_min + 1e-3) elsewhere (delta_g = that Gaussian's largest end-point difference).
     Prints the measured maxima."""
@@ -52,7 +53,10 @@ def _compare_drift(s, o, scene_scale, max_ulp, tag, min_exact_share=0.0):
           f"cov rel: median {np.median(rel):.2e} p99.9 {np.quantile(rel, 0.999):.2e} max {rel.max():.2e}, share > 1e-5 {(rel > 1e-5).mean():.2e} "
           f"(bit-identical end points: max {rel[exact].max() if exact.any() else 0.0:.2e}); max|dSH| {np.abs(out['shs'] - o.g['shs']).max():.2e}")
     assert dpos <= REL_TOL * scene_scale
-    assert drift.max() <= max_ulp, drift.max()
+    if max_abs is not None:
+        assert d_end.max() <= max_abs, d_end.max()
+    else:
+        assert drift.max() <= max_ulp, drift.max()
     assert exact.mean() >= min_exact_share
     assert (rel[exact] <= REL_TOL).all()
     bound = REL_TOL + 2.0 * d_end / (o.g["scale"].min(axis=1) + 1e-3)
