@@ -36,7 +36,7 @@ class Params(C.Structure):
                 ("w_rot", C.c_double), ("w_reg", C.c_double), ("w_con", C.c_double),
                 ("max_gn_iters", C.c_int), ("max_cg_iters", C.c_int), ("cg_tol", C.c_double),
                 ("skip_static_endpoints", C.c_int), ("solver_global_memory", C.c_int), ("lbs_mode", C.c_int),
-                ("newton_eta0", C.c_double), ("warm_start", C.c_int), ("solver_ctas", C.c_int), ("fps_mode", C.c_int)]
+                ("newton_eta0", C.c_double), ("warm_start", C.c_int), ("solver_ctas", C.c_int), ("lazy_sample_sh", C.c_int), ("fps_mode", C.c_int)]
 
 
 class SolveStats(C.Structure):
@@ -329,6 +329,9 @@ class Session:
         f, o = np.zeros((S, 48), f32), np.zeros(S, f32)
         check(lib().arap_download_features(self._ctx, int(which), _ptr(f), _ptr(o)))
         return f, o
+
+    def sample_features_materialize(self):
+        check(lib().arap_sample_features_materialize(self._ctx))
 
     def download_samples(self, features=True):
         S = self.grid_info()["samples"]

@@ -18,6 +18,7 @@
 // 256 B fully-coalesced request; the staged LBS kernel reads one-byte slot numbers
 //   slots[(blk*3 + m)*32 + lane]  (uint32 = 4 slots)
 // into a per-tile list of distinct nodes instead of the uint16 ids.
+#include <cuda.h>
 #include <algorithm>
 #include <cstdlib>
 #include "device_math.cuh"
@@ -919,7 +920,7 @@ k_replay_shs(long long N, const float* __restrict__ rot_old, const float* __rest
   const long long g = g0 + tid;
   s_static[tid] = (tid < rows) ? (is_static ? is_static[g] : 0) : 1;
   float4 o4 = make_float4(1.f, 0.f, 0.f, 0.f), n4 = o4;
-  if (tid < rows) { o4 = ldg4(rot_old + 4 * g); n4 = ldg4(rot_new + 4 * g); }
+  if (tid < rows) { if (rot_old) o4 = ldg4(rot_old + 4 * g); n4 = ldg4(rot_new + 4 * g); }
   __syncthreads();
   const float4* gsh = reinterpret_cast<const float4*>(shs + g0 * SH_FLOATS);
   const int cp_r0 = tid / 12, cp_c4 = tid - 12 * cp_r0;
@@ -1138,6 +1139,196 @@ k_rotate_sample_shs(long long S, long long ntiles, int k, const float* __restric
     }
     __syncthreads();
   }
+}
+
+// ------------------------------------------------------------------ sample SH rotation, deferred (lazy_sample_sh = 1)
+// The aim features are only read at a stroke end (UpdateFeatures, GV:1578-1617) or by the stage-II optimiser, never between
+// two drag steps, and SH rotation is a group representation: D(R_T) ... D(R_1) f = D(R_T ... R_1) f.  So a drag step only has
+// to compose the step's blended sample quaternion (same Q_SlerpCUDA chain as k_rotate_sample_shs) onto a per-sample
+// accumulator (16 B read + written instead of 384 B); the row is rotated once, by the accumulated quaternion, when a
+// consumer asks for it (arapk_replay_shs with rot_old = identity).  Off by default: the per-step body is then exactly the
+// reference's (FastUpdateSamplesSH every step, GV:1519).
+template <int K>
+__global__ void __launch_bounds__(256)
+k_accumulate_sample_quats(long long S, int k, const float* __restrict__ w, const uint16_t* __restrict__ idx, const float4* __restrict__ q_xyzw,
+                          const uint8_t* __restrict__ is_static, float4* __restrict__ qacc_wxyz) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S || (is_static && is_static[i])) return;
+  const long long base = (i >> 5) * (long long)(k * 32) + (i & 31);
+  float4 e[K]; float cw[K];
+#pragma unroll
+  for (int j = 0; j < K; j++) if (j < k) { e[j] = __ldg(q_xyzw + idx[base + j * 32]); cw[j] = w[base + j * 32]; }
+  const float4 a4 = qacc_wxyz[i];
+  Quat wq{1.0f, 0.0f, 0.0f, 0.0f};
+  float last = 0.0f;
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    if (j >= k) break;
+    const float t = __fdividef(cw[j], cw[j] + last);
+    Quat eq{e[j].w, e[j].x, e[j].y, e[j].z};
+    float cf = wq.x * eq.x + wq.y * eq.y + wq.z * eq.z + wq.w * eq.w;
+    if (cf < 0.0f) { eq.x = -eq.x; eq.y = -eq.y; eq.z = -eq.z; eq.w = -eq.w; cf = -cf; }
+    float rA, rB;
+    if (cf > 0.99995f) { rA = 1.0f - t; rB = t; }
+    else slerp_ratios_slow(cf, t, rA, rB);
+    Quat l;
+    l.x = fmaf(rA, wq.x, rB * eq.x); l.y = fmaf(rA, wq.y, rB * eq.y);
+    l.z = fmaf(rA, wq.z, rB * eq.z); l.w = fmaf(rA, wq.w, rB * eq.w);
+    const float inv = rsqrtf(quat_n2(l));
+    wq = Quat{l.w * inv, l.x * inv, l.y * inv, l.z * inv};
+    last += cw[j];
+  }
+  const Quat acc = quat_normalized(quat_mul(quat_normalized(wq), Quat{a4.x, a4.y, a4.z, a4.w}));
+  qacc_wxyz[i] = make_float4(acc.w, acc.x, acc.y, acc.z);
+}
+__global__ void k_fill_identity_quats(long long S, float4* __restrict__ q) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < S) q[i] = make_float4(1.f, 0.f, 0.f, 0.f);
+}
+
+// ------------------------------------------------------------------ sample SH rotation, TMA version
+// Same arithmetic as k_rotate_sample_shs; what changes is how a tile moves.  The feature array is described once by a 2-D
+// tensor map ([S rows] x [48 floats], box 128 rows x 16 floats, 64-byte swizzle): a tile arrives as three
+// cp.async.bulk.tensor loads issued by ONE thread and completes on an mbarrier, the tile's weights and node ids as two flat
+// bulk copies on the same barrier, and the rotated tile leaves as three bulk tensor stores — no per-thread copy loops, no
+// per-thread global address arithmetic (the first version spent ~15 % of its instructions and its top stall there).
+// With the 64-byte swizzle a thread's four 16-byte chunks of a 64-byte row segment sit at chunk ^ ((row >> 1) & 3): the
+// eight rows of a quarter-warp hit eight different 16-byte bank groups, so the per-thread LDS.128 / STS.128 on its own row
+// are conflict-free without the 13-chunk padding.
+constexpr int RT_FEAT = 3 * RS_TILE * 64;          // three column blocks of 16 floats, 128 rows x 64 B each
+constexpr int RT_STAGE = 34816;                    // RT_FEAT + 128 * 12 * 4 (weights) + 128 * 12 * 2 (ids), rounded up to 1024
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LAB_DONE_%=;\n"
+      "bra LAB_WAIT_%=;\n"
+      "LAB_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, const void* src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1), "r"(smem_u32(src)) : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __noinline__ void rot_issue_tile(const CUtensorMap* map, long long tile, long long S, int k, const float* __restrict__ w,
+                                           const uint16_t* __restrict__ idx, unsigned char* st, uint64_t* bar) {
+  const long long s0 = tile * RS_TILE;
+  const int rows = (int)min((long long)RS_TILE, S - s0);
+  const int nblk = (rows + 31) >> 5;
+  const unsigned wbytes = (unsigned)(nblk * k * 32 * 4), ibytes = (unsigned)(nblk * k * 32 * 2);
+  mbar_expect_tx(bar, (unsigned)RT_FEAT + wbytes + ibytes);
+#pragma unroll
+  for (int c = 0; c < 3; c++) tma_load_2d(st + c * (RS_TILE * 64), map, 16 * c, (int)s0, bar);
+  bulk_load_1d(st + RT_FEAT, w + (s0 >> 5) * (long long)(k * 32), wbytes, bar);
+  bulk_load_1d(st + RT_FEAT + RS_TILE * 12 * 4, idx + (s0 >> 5) * (long long)(k * 32), ibytes, bar);
+}
+
+template <int K>
+__global__ void __launch_bounds__(RS_TILE, 3)
+k_rotate_sample_shs_tma(const __grid_constant__ CUtensorMap tmap, long long S, long long ntiles, int k, const float* __restrict__ w,
+                        const uint16_t* __restrict__ idx, const float4* __restrict__ q_xyzw, const uint8_t* __restrict__ is_static) {
+  extern __shared__ unsigned char s_raw[];
+  __shared__ uint64_t s_bar[2];
+  unsigned char* base = s_raw + ((1024u - (smem_u32(s_raw) & 1023u)) & 1023u);   // swizzled TMA boxes want 1024-byte alignment
+  const int tid = threadIdx.x;
+  if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  auto issue = [&](long long tile, int stage) {   // one thread; out of line so that its address arithmetic does not cost every thread registers
+    rot_issue_tile(&tmap, tile, S, k, w, idx, base + stage * RT_STAGE, &s_bar[stage]);
+  };
+  long long tile = blockIdx.x;
+  if (tid == 0 && tile < ntiles) issue(tile, 0);
+  for (int it = 0; tile < ntiles; tile += gridDim.x, it++) {
+    const int stage = it & 1;
+    const long long s0 = tile * RS_TILE;
+    const int rows = (int)min((long long)RS_TILE, S - s0);
+    const bool stat = (is_static && tid < rows) ? is_static[s0 + tid] != 0 : false;
+    unsigned char* st = base + stage * RT_STAGE;
+    mbar_wait(&s_bar[stage], (unsigned)((it >> 1) & 1));
+    // quaternion gathers of this tile first, then the next tile's bulk loads (responses return roughly in issue order per SM)
+    float4 e[K]; float cw[K];
+    if (tid < rows) {
+      const float* sw = reinterpret_cast<const float*>(st + RT_FEAT) + (tid >> 5) * (k * 32) + (tid & 31);
+      const uint16_t* si = reinterpret_cast<const uint16_t*>(st + RT_FEAT + RS_TILE * 12 * 4) + (tid >> 5) * (k * 32) + (tid & 31);
+#pragma unroll
+      for (int j = 0; j < K; j++) if (j < k) { e[j] = __ldg(q_xyzw + si[j * 32]); cw[j] = sw[j * 32]; }
+    }
+    const long long next = tile + gridDim.x;
+    if (tid == 0 && next < ntiles) {
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the store that last read the other stage has drained it
+      issue(next, stage ^ 1);
+    }
+    const bool live = tid < rows && !stat;
+    if (live) {
+      Quat wq{1.0f, 0.0f, 0.0f, 0.0f};
+      float last = 0.0f;
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        if (j >= k) break;
+        const float t = __fdividef(cw[j], cw[j] + last);
+        Quat eq{e[j].w, e[j].x, e[j].y, e[j].z};
+        float cf = wq.x * eq.x + wq.y * eq.y + wq.z * eq.z + wq.w * eq.w;
+        if (cf < 0.0f) { eq.x = -eq.x; eq.y = -eq.y; eq.z = -eq.z; eq.w = -eq.w; cf = -cf; }
+        float rA, rB;
+        if (cf > 0.99995f) { rA = 1.0f - t; rB = t; }
+        else slerp_ratios_slow(cf, t, rA, rB);
+        Quat l;
+        l.x = fmaf(rA, wq.x, rB * eq.x); l.y = fmaf(rA, wq.y, rB * eq.y);
+        l.z = fmaf(rA, wq.z, rB * eq.z); l.w = fmaf(rA, wq.w, rB * eq.w);
+        const float inv = rsqrtf(quat_n2(l));
+        wq = Quat{l.w * inv, l.x * inv, l.y * inv, l.z * inv};
+        last += cw[j];
+      }
+      float R[3][3];
+      quat_to_matrix(quat_normalized(wq), R);
+      // this thread's four swizzled chunk positions inside a 64-byte row segment (the three column blocks are 8 KB apart)
+      const unsigned sx = (unsigned)((tid >> 1) & 3);
+      unsigned char* rb0 = st + tid * 64 + ((0u ^ sx) << 4);
+      unsigned char* rb1 = st + tid * 64 + ((1u ^ sx) << 4);
+      unsigned char* rb2 = st + tid * 64 + ((2u ^ sx) << 4);
+      unsigned char* rb3 = st + tid * 64 + ((3u ^ sx) << 4);
+      float v[SH_FLOATS];
+#pragma unroll
+      for (int c = 0; c < 12; c++) {
+        unsigned char* a = ((c & 3) == 0 ? rb0 : (c & 3) == 1 ? rb1 : (c & 3) == 2 ? rb2 : rb3) + (c >> 2) * (RS_TILE * 64);
+        const float4 x = *reinterpret_cast<const float4*>(a);
+        v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
+      }
+      sh_rotate_flipped_fast(R, v);
+#pragma unroll
+      for (int c = 1; c < 12; c++) {
+        unsigned char* a = ((c & 3) == 0 ? rb0 : (c & 3) == 1 ? rb1 : (c & 3) == 2 ? rb2 : rb3) + (c >> 2) * (RS_TILE * 64);
+        *reinterpret_cast<float4*>(a) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      }
+      reinterpret_cast<float*>(rb0)[3] = v[3];   // DC term (floats 0-2) is rotation invariant
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes of the tile -> visible to the bulk store
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) tma_store_2d(&tmap, 16 * c, (int)s0, st + c * (RS_TILE * 64));
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------ static flags
@@ -1392,12 +1583,24 @@ extern "C" int arapk_node_quats(int M, const double* rot, float* q_xyzw, cudaStr
   return ARAP_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = nullptr; static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr; cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
 extern "C" int arapk_rotate_sample_shs(long long S, int k, const float* w, const uint16_t* idx, const float* q_xyzw,
                                        const uint8_t* is_static, float* feature, cudaStream_t st) {
   if (S <= 0) return ARAP_OK;
   int rc = ensure_sh_tables(); if (rc) return rc;
   if (k < 1 || k > 12) { set_error("rotate_sample_shs: k out of range"); return ARAP_ERR_INVALID; }
-  const size_t smem = 2 * (sizeof(float4) * RS_STAGE4 + (size_t)RS_TILE * k * 6);
   const long long ntiles = (S + RS_TILE - 1) / RS_TILE;
   static int sms = 0;
   if (!sms) {
@@ -1406,14 +1609,65 @@ extern "C" int arapk_rotate_sample_shs(long long S, int k, const float* w, const
     ARAP_CUDA_TRY(cudaFuncSetAttribute(k_rotate_sample_shs<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     ARAP_CUDA_TRY(cudaFuncSetAttribute(k_rotate_sample_shs<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     ARAP_CUDA_TRY(cudaFuncSetAttribute(k_rotate_sample_shs<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    const int mt = 2 * RT_STAGE + 1024;
+    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_rotate_sample_shs_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mt));
+    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_rotate_sample_shs_tma<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, mt));
+    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_rotate_sample_shs_tma<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, mt));
   }
   const unsigned nb = (unsigned)std::min<long long>(ntiles, (long long)sms * 3);
   const float4* q4 = (const float4*)q_xyzw;
+  // ARAP_ROT_TMA=1 selects the TMA version.  Measured on the 58.8M-sample workload: 5.89 ms against 5.25 ms for the cp.async version —
+  // the kernel is bound by instruction issue on the SH recurrences (~2500 instructions per sample = 4.1 ms at 4 IPC per SM), the
+  // tensor-map pipeline costs it registers (spills at 168 registers, 3 CTAs per SM), so off-loading the copies does not pay; kept
+  // selectable, default off.
+  static int use_tma = -1;
+  if (use_tma < 0) { const char* ev = getenv("ARAP_ROT_TMA"); use_tma = ev ? atoi(ev) : 0; }
+  EncodeTiledFn enc = use_tma ? tensor_map_encoder() : nullptr;
+  if (enc && ((uintptr_t)feature & 15) == 0 && S < (1LL << 31)) {
+    // one tensor map per (pointer, row count): cached for the session's aim-feature array
+    static CUtensorMap tmap; static const float* m_ptr = nullptr; static long long m_S = 0;
+    if (m_ptr != feature || m_S != S) {
+      const cuuint64_t dims[2] = {48, (cuuint64_t)S};
+      const cuuint64_t strides[1] = {192};
+      const cuuint32_t box[2] = {16, RS_TILE};
+      const cuuint32_t estr[2] = {1, 1};
+      const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)feature, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error("rotate_sample_shs: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"); return ARAP_ERR_CUDA; }
+      m_ptr = feature; m_S = S;
+    }
+    const size_t smem = 2 * RT_STAGE + 1024;
+    if (k <= 8) k_rotate_sample_shs_tma<8><<<nb, RS_TILE, smem, st>>>(tmap, S, ntiles, k, w, idx, q4, is_static);
+    else if (k <= 10) k_rotate_sample_shs_tma<10><<<nb, RS_TILE, smem, st>>>(tmap, S, ntiles, k, w, idx, q4, is_static);
+    else k_rotate_sample_shs_tma<12><<<nb, RS_TILE, smem, st>>>(tmap, S, ntiles, k, w, idx, q4, is_static);
+    ARAP_KERNEL_CHECK();
+    return ARAP_OK;
+  }
+  const size_t smem = 2 * (sizeof(float4) * RS_STAGE4 + (size_t)RS_TILE * k * 6);
   static int order = -1;   // ARAP_ROT_ORDER=0: bulk loads of the next tile issued before the gathers (first version)
   if (order < 0) { const char* ev = getenv("ARAP_ROT_ORDER"); order = ev ? atoi(ev) : 1; }
   if (k <= 8) k_rotate_sample_shs<8><<<nb, RS_TILE, smem, st>>>(S, ntiles, k, w, idx, q4, is_static, feature, order);
   else if (k <= 10) k_rotate_sample_shs<10><<<nb, RS_TILE, smem, st>>>(S, ntiles, k, w, idx, q4, is_static, feature, order);
   else k_rotate_sample_shs<12><<<nb, RS_TILE, smem, st>>>(S, ntiles, k, w, idx, q4, is_static, feature, order);
+  ARAP_KERNEL_CHECK();
+  return ARAP_OK;
+}
+
+extern "C" int arapk_accumulate_sample_quats(long long S, int k, const float* w, const uint16_t* idx, const float* q_xyzw,
+                                             const uint8_t* is_static, float* qacc_wxyz, cudaStream_t st) {
+  if (S <= 0) return ARAP_OK;
+  if (k < 1 || k > 12) { set_error("accumulate_sample_quats: k out of range"); return ARAP_ERR_INVALID; }
+  const unsigned grid = (unsigned)((S + 255) / 256);
+  const float4* q4 = (const float4*)q_xyzw; float4* qa = (float4*)qacc_wxyz;
+  if (k <= 8) k_accumulate_sample_quats<8><<<grid, 256, 0, st>>>(S, k, w, idx, q4, is_static, qa);
+  else if (k <= 10) k_accumulate_sample_quats<10><<<grid, 256, 0, st>>>(S, k, w, idx, q4, is_static, qa);
+  else k_accumulate_sample_quats<12><<<grid, 256, 0, st>>>(S, k, w, idx, q4, is_static, qa);
+  ARAP_KERNEL_CHECK();
+  return ARAP_OK;
+}
+extern "C" int arapk_fill_identity_quats(long long S, float* q_wxyz, cudaStream_t st) {
+  if (S <= 0) return ARAP_OK;
+  k_fill_identity_quats<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(S, (float4*)q_wxyz);
   ARAP_KERNEL_CHECK();
   return ARAP_OK;
 }

@@ -222,17 +222,28 @@ k_fps_pruned(const float* __restrict__ pos, FpsGrid g, const int* __restrict__ p
       if (sb.v < 0.f) continue;
       const int x0 = sx << sgs, y0 = sy << sgs, z0 = sz << sgs;
       if (fps_box_mind(p, g, x0, y0, z0, min(x0 + SG, G) - 1, min(y0 + SG, G) - 1, min(z0 + SG, G) - 1) >= sb.v) continue;
-      for (int u = lane; u < cps; u += 32) {
-        const int x = x0 + (u >> (2 * sgs)), y = y0 + ((u >> sgs) & (SG - 1)), z = z0 + (u & (SG - 1));
-        if (x >= G || y >= G || z >= G) continue;
-        const float md = fps_box_mind(p, g, x, y, z, x, y, z);
-        if (md >= sb.v) continue;
-        const int cell = (x * G + y) * G + z;
-        const FpsBest cb = cm[cell];
-        if (cb.v >= 0.f && md < cb.v) {
-          const int slot = atomicAdd(&s_nlist, 1);
-          if (slot < FPS_LIST) s_list[slot] = cell;
+      // four cells per lane and pass: the (dependent, L2-latency) cell-maximum loads of a pass are in flight together —
+      // the loop runs on one SM and is bound by exposed latency, not by bandwidth
+      for (int u0 = lane; u0 < cps; u0 += 128) {
+        int cell[4]; float md[4]; FpsBest cb[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int u = u0 + 32 * i;
+          const int x = x0 + (u >> (2 * sgs)), y = y0 + ((u >> sgs) & (SG - 1)), z = z0 + (u & (SG - 1));
+          cell[i] = -1; md[i] = 0.f; cb[i] = FpsBest{-1.0f, 0x7fffffff};
+          if (u < cps && x < G && y < G && z < G) {
+            md[i] = fps_box_mind(p, g, x, y, z, x, y, z);
+            if (md[i] < sb.v) cell[i] = (x * G + y) * G + z;
+          }
         }
+#pragma unroll
+        for (int i = 0; i < 4; i++) if (cell[i] >= 0) cb[i] = cm[cell[i]];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+          if (cell[i] >= 0 && cb[i].v >= 0.f && md[i] < cb[i].v) {
+            const int slot = atomicAdd(&s_nlist, 1);
+            if (slot < FPS_LIST) s_list[slot] = cell[i];
+          }
       }
     }
     __syncthreads();
@@ -246,12 +257,24 @@ k_fps_pruned(const float* __restrict__ pos, FpsGrid g, const int* __restrict__ p
         const long long cc = have ? s_list[ci] : 0;
         const int b = have ? (cc ? prefix[cc - 1] : 0) : 0, e = have ? prefix[cc] : 0;
         FpsBest best{-1.0f, 0x7fffffff};
-        for (int j = b + sub; j < e; j += 8) {
-          const double dx = (double)(p[0] - pos[3LL * j]), dy = (double)(p[1] - pos[3LL * j + 1]), dz = (double)(p[2] - pos[3LL * j + 2]);
-          const float dd = (float)sqrt(dx * dx + dy * dy + dz * dz);
-          float cur = dist[j];
-          if (dd < cur) { cur = dd; dist[j] = dd; }
-          best = fps_better_or_empty(best, FpsBest{cur, j});
+        for (int j0 = b + sub; j0 < e; j0 += 32) {     // four points per lane and pass, loads first
+          float px[4], py[4], pz[4], cur[4];
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int j = j0 + 8 * i;
+            if (j < e) { px[i] = pos[3LL * j]; py[i] = pos[3LL * j + 1]; pz[i] = pos[3LL * j + 2]; cur[i] = dist[j]; }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int j = j0 + 8 * i;
+            if (j < e) {
+              const double dx = (double)(p[0] - px[i]), dy = (double)(p[1] - py[i]), dz = (double)(p[2] - pz[i]);
+              const float dd = (float)sqrt(dx * dx + dy * dy + dz * dz);
+              float cv = cur[i];
+              if (dd < cv) { cv = dd; dist[j] = dd; }
+              best = fps_better_or_empty(best, FpsBest{cv, j});
+            }
+          }
         }
 #pragma unroll
         for (int o = 4; o > 0; o >>= 1) best = fps_better_or_empty(best, FpsBest{__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.i, o)});
@@ -267,9 +290,17 @@ k_fps_pruned(const float* __restrict__ pos, FpsGrid g, const int* __restrict__ p
         const int x0 = sx << sgs, y0 = sy << sgs, z0 = sz << sgs;
         if (fps_box_mind(p, g, x0, y0, z0, min(x0 + SG, G) - 1, min(y0 + SG, G) - 1, min(z0 + SG, G) - 1) >= sv) continue;   // untouched in (1)
         FpsBest sup{-1.0f, 0x7fffffff};
-        for (int u = lane; u < cps; u += 32) {
-          const int x = sx * SG + u / (SG * SG), y = sy * SG + (u / SG) % SG, z = sz * SG + u % SG;
-          if (x < G && y < G && z < G) sup = fps_better_or_empty(sup, cm[((long long)x * G + y) * G + z]);
+        for (int u0 = lane; u0 < cps; u0 += 128) {
+          FpsBest cb[4];
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int u = u0 + 32 * i;
+            const int x = x0 + (u >> (2 * sgs)), y = y0 + ((u >> sgs) & (SG - 1)), z = z0 + (u & (SG - 1));
+            cb[i] = FpsBest{-1.0f, 0x7fffffff};
+            if (u < cps && x < G && y < G && z < G) cb[i] = cm[((long long)x * G + y) * G + z];
+          }
+#pragma unroll
+          for (int i = 0; i < 4; i++) sup = fps_better_or_empty(sup, cb[i]);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sup = fps_better_or_empty(sup, FpsBest{__shfl_xor_sync(0xffffffffu, sup.v, o), __shfl_xor_sync(0xffffffffu, sup.i, o)});

@@ -162,6 +162,7 @@ struct arap_ctx {
   DBuf<int> cell_prefix, gs_init_grid_idx, fp_prefix, lists, valid;
   DBuf<float> sample_pos, ada_lpf, aim_feature, aim_opacity, cur_feature, cur_opacity, gs_aabb;
   DBuf<uint8_t> sample_static;
+  DBuf<float> sample_qacc; bool sample_sh_pending = false;   // lazy_sample_sh: accumulated per-sample rotation not yet applied to aim_feature
   DBuf<int> empty_grid;
   DBuf<char> grid_scratch;
   // mesh points ("simplified_points")
@@ -229,7 +230,7 @@ extern "C" int arap_default_params(arap_params* p) {
   if (!p) return ARAP_ERR_INVALID;
   p->grid_num = 64; p->padding = 1; p->knn_k = 10; p->node_num = 150; p->high_quality = 0; p->lpf_parameter = 0.2f;
   p->w_rot = 1.0; p->w_reg = 10.0; p->w_con = 100.0; p->max_gn_iters = 30; p->max_cg_iters = 4000; p->cg_tol = 1e-10;
-  p->skip_static_endpoints = 0; p->solver_global_memory = 0; p->lbs_mode = 0; p->newton_eta0 = 1e-6; p->warm_start = 1; p->solver_ctas = 0; p->fps_mode = 0;
+  p->skip_static_endpoints = 0; p->solver_global_memory = 0; p->lbs_mode = 0; p->newton_eta0 = 1e-6; p->warm_start = 1; p->solver_ctas = 0; p->fps_mode = 0; p->lazy_sample_sh = 0;
   return ARAP_OK;
 }
 
@@ -317,8 +318,10 @@ extern "C" int arap_download_gaussians(arap_ctx* ctx, float* pos, float* rot, fl
   return ARAP_OK;
 }
 
+static int materialize_sample_sh(arap_ctx* ctx);
 extern "C" int arap_get_device_view(arap_ctx* ctx, arap_device_view* o) {
   CTX_CHECK(ctx); if (!o) return ARAP_ERR_INVALID;
+  TRY(materialize_sample_sh(ctx));   // aim_feature is handed out: bring it up to date (stream-ordered)
   memset(o, 0, sizeof(*o));
   o->n_gaussians = ctx->N; o->pos = ctx->pos.p; o->rot = ctx->rot.p; o->scale = ctx->scale.p; o->opacity = ctx->opacity.p; o->shs = ctx->shs.p;
   o->n_nodes = ctx->M; o->node_pos = ctx->node_pos.p; o->node_rot = ctx->rot_d.p; o->node_trans = ctx->trans_d.p;
@@ -425,6 +428,7 @@ extern "C" int arap_grid_build(arap_ctx* ctx) {
   TRY(ctx->ends.alloc((size_t)ctx->N * 18));
   TRY(arapk_end_points(ctx->N, ctx->pos.p, ctx->rot.p, ctx->scale.p, ctx->ends.p, st));
   ctx->aim_feature.release(); ctx->aim_opacity.release(); ctx->cur_feature.release(); ctx->cur_opacity.release(); ctx->empty_grid.release();
+  ctx->sample_qacc.release(); ctx->sample_sh_pending = false;
   ctx->grid_ready = true; ctx->graph_ready = false;
   return ARAP_OK;
 }
@@ -432,6 +436,7 @@ extern "C" int arap_grid_build(arap_ctx* ctx) {
 extern "C" int arap_grid_update_lists(arap_ctx* ctx) {
   CTX_CHECK(ctx);
   if (!ctx->grid_ready) { set_error("grid_update_lists: grid not built"); return ARAP_ERR_STATE; }
+  TRY(materialize_sample_sh(ctx));   // stroke end: the aim features are consumed next (UpdateFeatures -> L1loss3d, GV:4191-4207)
   { StageTimer tmr(ctx, ARAP_ST_SCENE_AABB); TRY(overall_aabb(ctx)); }  // UpdateContainingRelationship recomputes the scene box and step (GV:3636-3644)
   return build_lists(ctx);
 }
@@ -446,6 +451,8 @@ extern "C" int arap_grid_eval(arap_ctx* ctx, int which) {
   TRY(arapk_grid_eval(ctx->valid.p, ctx->V, ctx->fp_prefix.p, ctx->lists.p, ctx->sample_pos.p, ctx->pos.p, ctx->rot.p, ctx->scale.p,
                       ctx->opacity.p, ctx->shs.p, ctx->ada_lpf.p, f.p, o.p, ctx->stream));
   if (which == 0) {   // GPUSetupSamplesFeatures ends with JudgeEmptyGrid (GV:4268)
+    if (ctx->sample_qacc.p) TRY(arapk_fill_identity_quats(ctx->S, ctx->sample_qacc.p, ctx->stream));
+    ctx->sample_sh_pending = false;
     TRY(ctx->empty_grid.alloc((size_t)std::max(ctx->V, 1)));
     TRY(arapk_judge_empty_grid(ctx->valid.p, ctx->V, o.p, ctx->G, ctx->empty_grid.p, ctx->grid_scratch.p, ctx->grid_scratch.n, ctx->stream));
   }
@@ -499,6 +506,7 @@ extern "C" int arap_download_grid(arap_ctx* ctx, int* valid, int* prefix, int* l
 }
 extern "C" int arap_download_features(arap_ctx* ctx, int which, float* feature, float* opacity) {
   CTX_CHECK(ctx); cudaStream_t st = ctx->stream;
+  TRY(materialize_sample_sh(ctx));
   DBuf<float>& f = which == 0 ? ctx->aim_feature : ctx->cur_feature;
   DBuf<float>& o = which == 0 ? ctx->aim_opacity : ctx->cur_opacity;
   if (!f.p) { set_error("download_features: not evaluated"); return ARAP_ERR_STATE; }
@@ -508,6 +516,7 @@ extern "C" int arap_download_features(arap_ctx* ctx, int which, float* feature, 
 }
 extern "C" int arap_download_samples(arap_ctx* ctx, float* sample_pos, float* aim_feature) {
   CTX_CHECK(ctx); cudaStream_t st = ctx->stream;
+  TRY(materialize_sample_sh(ctx));
   TRY(download(sample_pos, ctx->sample_pos.p, (size_t)ctx->S * 3, st));
   if (aim_feature) { if (!ctx->aim_feature.p) { set_error("download_samples: aim features not evaluated"); return ARAP_ERR_STATE; } TRY(download(aim_feature, ctx->aim_feature.p, (size_t)ctx->S * 48, st)); }
   ARAP_CUDA_TRY(cudaStreamSynchronize(st));
@@ -957,6 +966,16 @@ extern "C" int arap_solve_stats_get(arap_ctx* ctx, arap_solve_stats* o) {
   return ARAP_OK;
 }
 
+// lazy_sample_sh: apply the accumulated per-sample rotations to the aim features (no-op when nothing is pending)
+static int materialize_sample_sh(arap_ctx* ctx) {
+  if (!ctx->sample_sh_pending || !ctx->aim_feature.p || !ctx->sample_qacc.p) return ARAP_OK;
+  TRY(arapk_replay_shs(ctx->S, nullptr, ctx->sample_qacc.p, nullptr, ctx->aim_feature.p, ctx->stream));
+  TRY(arapk_fill_identity_quats(ctx->S, ctx->sample_qacc.p, ctx->stream));
+  ctx->sample_sh_pending = false;
+  return ARAP_OK;
+}
+extern "C" int arap_sample_features_materialize(arap_ctx* ctx) { CTX_CHECK(ctx); return materialize_sample_sh(ctx); }
+
 // The per-step update.  The reference's order (GV:1499-1522) is samples, mesh points, end points, nodes, six-point fit,
 // sample SH; every one of these reads only the solve result, the pre-update node positions (captured in node_xf / the
 // double-buffered node_pos) and its own data, so the order is free.  The Gaussian side runs FIRST here: the
@@ -991,7 +1010,14 @@ extern "C" int arap_apply(arap_ctx* ctx) {
   if (tm) cudaEventRecord(ctx->ev[4], st);
   if (ctx->S > 0 && ctx->aim_feature.p) {
     TRY(arapk_node_quats(M, ctx->rot_d.p, ctx->node_q.p, st));
-    TRY(arapk_rotate_sample_shs(ctx->S, k, ctx->sample_rows.wf.p, ctx->sample_rows.idx.p, ctx->node_q.p, ctx->sample_static.p, ctx->aim_feature.p, st));
+    if (ctx->prm.lazy_sample_sh) {   // compose the step's sample rotation; the rows are rotated when a consumer needs them
+      if (!ctx->sample_qacc.p) { TRY(ctx->sample_qacc.alloc((size_t)ctx->S * 4)); TRY(arapk_fill_identity_quats(ctx->S, ctx->sample_qacc.p, st)); }
+      TRY(arapk_accumulate_sample_quats(ctx->S, k, ctx->sample_rows.wf.p, ctx->sample_rows.idx.p, ctx->node_q.p, ctx->sample_static.p, ctx->sample_qacc.p, st));
+      ctx->sample_sh_pending = true;
+    } else {
+      TRY(materialize_sample_sh(ctx));   // a switch from lazy to eager in mid-stroke
+      TRY(arapk_rotate_sample_shs(ctx->S, k, ctx->sample_rows.wf.p, ctx->sample_rows.idx.p, ctx->node_q.p, ctx->sample_static.p, ctx->aim_feature.p, st));
+    }
   }
   if (tm) cudaEventRecord(ctx->ev[5], st);
   // node_pos keeps its address (arap_device_view.node_pos may be cached by the viewer): the double buffer is copied back

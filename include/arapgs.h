@@ -79,6 +79,11 @@ typedef struct arap_params {
   int solver_ctas;     /* 0 (default): the solve uses one CTA per SM.  n > 0: at most n CTAs, leaving the other SMs to kernels that run
                           beside it — the multi-GPU driver reserves SMs for the NCCL all-gather of the previous step's SoA, which
                           otherwise cannot overlap the solve (a 512-thread solver CTA fills an SM's register file). */
+  int lazy_sample_sh;  /* 0 (default): the aim features of the samples are rotated every drag step (FastUpdateSamplesSH, GV:1519), as in the
+                          reference.  1: a step only composes its blended sample rotation onto a per-sample quaternion (32 B instead of
+                          384 B of traffic per sample); the feature rows are rotated once by the accumulated rotation when they are
+                          consumed — arap_grid_update_lists (stroke end), arap_get_device_view, the download calls, or
+                          arap_sample_features_materialize.  Same result up to float rounding (SH rotation composes exactly). */
   int fps_mode;        /* node sampling (HC:139-195): 0 (default) = selection loop pruned by the density grid, 1 = one pass over all
                           candidate points per node (first version).  Same node sequence, bit for bit. */
 } arap_params;
@@ -197,6 +202,8 @@ int arap_grid_info_get(arap_ctx* ctx, arap_grid_info* out);
 int arap_download_grid(arap_ctx* ctx, int* valid, int* prefix, int* lists, float* sample_pos, int* gs_init_grid_idx);
 int arap_download_features(arap_ctx* ctx, int which, float* feature, float* opacity);
 int arap_download_samples(arap_ctx* ctx, float* sample_pos, float* aim_feature);
+/* arap_params.lazy_sample_sh = 1: rotate the aim features by the rotations accumulated since the last call (stream-ordered; no-op otherwise) */
+int arap_sample_features_materialize(arap_ctx* ctx);
 
 /* ---- stage (b): graph, kNN, weights --------------------------------------- */
 /* farthest_control_points_sampling over the Gaussian centres + DeformGraph ctor + setupWeights* (GV:698-754, HC:139-195, DH:54-95). */

@@ -60,6 +60,11 @@ int arapk_replay_shs(long long N, const float* rot_old, const float* rot_new, co
 int arapk_node_quats(int M, const double* rot, float* q_xyzw, cudaStream_t st);
 int arapk_rotate_sample_shs(long long S, int k, const float* w, const uint16_t* idx, const float* q_xyzw,
                             const uint8_t* is_static, float* feature, cudaStream_t st);
+/* deferred sample SH rotation (arap_params.lazy_sample_sh): compose the step's blended sample quaternion onto an accumulator;
+ * the rows are rotated later by arapk_replay_shs with rot_old = NULL (identity) and rot_new = the accumulator */
+int arapk_accumulate_sample_quats(long long S, int k, const float* w, const uint16_t* idx, const float* q_xyzw,
+                                  const uint8_t* is_static, float* qacc_wxyz, cudaStream_t st);
+int arapk_fill_identity_quats(long long S, float* q_wxyz, cudaStream_t st);
 int arapk_static_flags(long long G, int group, int k, const uint16_t* idx, const uint8_t* node_static, uint8_t* out,
                        cudaStream_t st);
 int arapk_sh_rotate_test(const float* R9, float* shs48_dev, int fast, cudaStream_t st);

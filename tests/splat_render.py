@@ -32,6 +32,23 @@ def orbit_cameras(n_views=4, radius=2.6, height=0.6, size=256, fov_deg=40.0):
     return cams
 
 
+def transforms_cameras(path, stride=1):
+    """Cameras of a dataset's transforms_test.json as the reference loads them (src/core/scene/ParseData.cpp:243-246,
+    src/core/assets/InputCamera.cpp:1513-1576): `transform_matrix` is camera-to-world in the Blender convention (x right, y up,
+    -z forward); focal = 0.5 w / tan(camera_angle_x / 2) (= fl_x), w x h pixels.  Returns every `stride`-th frame."""
+    import json
+    d = json.load(open(path))
+    w = int(d.get("w", 800))
+    f = 0.5 * w / math.tan(0.5 * float(d["camera_angle_x"]))
+    cams = []
+    for fr in d["frames"][::stride]:
+        c2w = np.array(fr["transform_matrix"], np.float64)
+        right, up, back, eye = c2w[:3, 0], c2w[:3, 1], c2w[:3, 2], c2w[:3, 3]
+        R = np.stack([right, -up, -back])           # world -> camera (x right, y down, z forward)
+        cams.append(dict(R=R, t=-R @ eye, eye=eye, f=f, size=w))
+    return cams
+
+
 def _sh_color(shs, dirs):
     sh = shs.reshape(-1, 16, 3)
     x, y, z = dirs[:, 0:1], dirs[:, 1:2], dirs[:, 2:3]

@@ -280,3 +280,17 @@ def test_static_flags(pkg, orc):
         pkg.check(lib.arapk_static_flags(C.c_longlong(P // group), group, k, ptr(d_bi), ptr(d_ns), ptr(out), stream()))
         torch.cuda.synchronize()
         assert np.array_equal(out.cpu().numpy(), orc.static_flags(idx, group, ns))
+
+
+def test_selectable_kernel_variants_keep_parity():
+    """Variants chosen by environment variables (read once per process): the TMA version of the sample SH rotation (tensor-map
+    loads / stores, 64-byte swizzle) and the per-query kNN walk of the first round must pass the same oracle comparisons."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    for env, sel in ((dict(ARAP_ROT_TMA="1"), "test_node_quats_and_sample_sh_rotation or test_drag_steps_match_oracle"),
+                     (dict(ARAP_KNN_TILE="0"), "test_knn_indices_and_weights_bit_exact or test_knn_lattice_ties_bit_exact")):
+        r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_kernels.py"), os.path.join(here, "test_gpu_session.py"),
+                            "-m", "gpu", "-x", "-q", "-k", sel], env={**os.environ, **env}, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, (env, r.stdout[-2000:] + r.stderr[-2000:])

@@ -364,3 +364,32 @@ def test_rendered_psnr_after_drag(pkg, scenes):
     print(f"rendered PSNR product vs oracle (worst of 4 views): {worst:.1f} dB; deformed vs undeformed: {moved:.1f} dB")
     assert worst >= 50.0, worst                                # product vs oracle: >= 50 dB on every view
     assert moved < 45.0, moved                                 # ...and the metric sees the deformation itself
+
+
+def test_rendered_psnr_on_the_dataset_test_cameras(pkg, scenes, golden):
+    """north_star: >= 50 dB PSNR on rendered test views.  The 201 cameras of datasets/pinocchio/transforms_test.json (800 x 800,
+    fl 1111.11; ParseData.cpp:243-246), every 25th, at full resolution: the product's against the oracle's deformed Gaussians
+    after a bend of the pinocchio stand-in (the reference's own point_cloud.ply is not in the tree), in lbs_mode 0 and 3."""
+    import splat_render as sr
+    cams = sr.transforms_cameras(golden / "pinocchio_transforms_test.json", stride=25)
+    assert len(sr.transforms_cameras(golden / "pinocchio_transforms_test.json")) == 201 and cams[0]["size"] == 800 and abs(cams[0]["f"] - 1111.111) < 1e-2
+    for mode in (0, 3):
+        sc, s, o, gi, og = _pair(pkg, scenes, name="pinocchio", n=30000, grid_num=64, knn_k=8, node_num=300)
+        s.set_params(lbs_mode=mode)
+        g = s.graph_build_fps(); o.graph_build_fps()
+        npz = g["node_pos"]
+        blocks = [np.nonzero(npz[:, 1] > 0.3)[0].astype(np.uint32), np.nonzero(npz[:, 1] < -0.3)[0].astype(np.uint32)]
+        s.set_blocks(blocks, [1, 0]); o.set_blocks(blocks, [1, 0])
+        before = s.download_gaussians()
+        for step in range(8):
+            s.aim_translate([0.01, 0.0, 0.004]); o.aim_translate([0.01, 0.0, 0.004])
+            s.step(False); o.step(False)
+        out = s.download_gaussians()
+        worst, moved = float("inf"), float("inf")
+        for cam in cams:
+            a, b, c = sr.render(out, cam, chunk=96), sr.render(o.g, cam, chunk=96), sr.render(before, cam, chunk=96)
+            assert a.max() > 0.2
+            worst, moved = min(worst, sr.psnr(a, b)), min(moved, sr.psnr(a, c))
+        print(f"lbs_mode {mode}: PSNR on {len(cams)} dataset test cameras at 800 x 800, product vs oracle: worst {worst:.1f} dB; deformed vs undeformed: {moved:.1f} dB")
+        assert worst >= 50.0 and moved < 45.0
+        s.close()

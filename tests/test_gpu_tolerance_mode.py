@@ -115,3 +115,23 @@ def test_tolerance_mode_large_tiles_and_fallback(pkg, scenes):
     assert np.abs(a["pos"] - b["pos"]).max() <= 1e-6 and rel.max() <= 1e-4 and (rel > 1e-5).mean() <= 5e-2
     assert np.abs(a["shs"] - b["shs"]).max() <= 5e-6
     assert np.abs(outs[1][1] - outs[0][1]).max() <= 6e-7
+
+
+def test_lazy_sample_sh_composes_to_the_eager_result(pkg, scenes):
+    """arap_params.lazy_sample_sh: per-step quaternion accumulation + one rotation at the stroke end against the reference's
+    per-step FastUpdateSamplesSH (oracle) — SH rotation is a group representation, so only float rounding differs."""
+    sc, s, o, gi, og = _pair(pkg, scenes, n=30000, grid_num=32, knn_k=10, node_num=150)
+    s.set_params(lazy_sample_sh=1)
+    s.grid_eval(0); o.grid_eval(0)
+    f0 = s.download_samples()[1].copy()
+    g = s.graph_build_fps(); o.graph_build_fps()
+    blocks, types = scenes.cap_blocks(g["node_pos"], lo=-0.3, hi=0.3)
+    excl = np.nonzero(g["node_pos"][:, 0] > 0.42)[0].astype(np.uint32)
+    s.set_blocks(blocks + [excl], types + [-1]); o.set_blocks(blocks + [excl], types + [-1])
+    for step in range(6):
+        s.aim_translate([0.004, 0.0, 0.02]); o.aim_translate([0.004, 0.0, 0.02])
+        s.step(False); o.step(False)
+    sp, sf = s.download_samples()              # materialises the accumulated rotations
+    assert np.abs(sf - o.aim_feature).max() <= 2e-5 and np.abs(sf - f0).max() > 1e-3
+    assert np.array_equal(s.download_samples()[1], sf)      # idempotent: nothing pending any more
+    _compare_gaussians(s.download_gaussians(), o.g)
