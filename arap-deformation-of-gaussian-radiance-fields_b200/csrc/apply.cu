@@ -1502,6 +1502,9 @@ extern "C" int arapk_lbs_union32(const float* in, float* out, long long P, const
   if (P <= 0) return ARAP_OK;
   if (group < 1) group = 1;
   const long long nblk = (P + 31) / 32;
+  // one warp per 32-row block.  (A persistent grid-stride version with a two-deep software pipeline — next block's weights,
+  // points and offsets in flight while the current one is skinned — measured 1.91 ms against 1.77 ms: the kernel is bound
+  // by l1tex wavefronts, not by exposed latency.)
   k_lbs_union32<<<(unsigned)((nblk + SU_WARPS - 1) / SU_WARPS), SU_WARPS * 32, 0, st>>>(in, out, P, boff, blist, bw, (const NodeXf32*)node_xf32, skip, group);
   ARAP_KERNEL_CHECK();
   return ARAP_OK;

@@ -123,9 +123,10 @@ __device__ __forceinline__ void bitonic_steps(int* a, int n, int tid, int nthrea
 }
 
 // one warp per cell; segments longer than SEG_WARP_CAP go to the block kernel
+constexpr int SEG_MED_CAP = 8192;      // "medium" cells: 32 KB of shared memory per CTA, seven CTAs per SM
 __global__ void __launch_bounds__(256)
 k_segsort_warp(long long ncell, const int* __restrict__ prefix, int* __restrict__ data, int* __restrict__ big_count,
-               int* __restrict__ big_list) {
+               int* __restrict__ big_list) {   // big_count[0] / big_list ascending: medium cells; big_count[1] / big_list descending from its end: large
   __shared__ int s_buf[8][SEG_WARP_CAP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long c = (long long)blockIdx.x * 8 + warp;
@@ -133,7 +134,13 @@ k_segsort_warp(long long ncell, const int* __restrict__ prefix, int* __restrict_
   const int b = c ? prefix[c - 1] : 0, e = prefix[c];
   const int n = e - b;
   if (n <= 1) return;
-  if (n > SEG_WARP_CAP) { if (lane == 0) big_list[atomicAdd(big_count, 1)] = (int)c; return; }
+  if (n > SEG_WARP_CAP) {
+    if (lane == 0) {
+      if (n <= SEG_MED_CAP) big_list[atomicAdd(big_count, 1)] = (int)c;
+      else big_list[ncell - 1 - atomicAdd(big_count + 1, 1)] = (int)c;
+    }
+    return;
+  }
   int* a = s_buf[warp];
   for (int i = lane; i < n; i += 32) a[i] = data[b + i];
   __syncwarp();
@@ -153,12 +160,12 @@ k_segsort_warp(long long ncell, const int* __restrict__ prefix, int* __restrict_
 // else in place in global memory
 constexpr int SEG_BLOCK_CAP = 49152;   // 192 KB of dynamic shared memory
 __global__ void __launch_bounds__(1024)
-k_segsort_block(const int* __restrict__ big_list, const int* __restrict__ prefix, int* __restrict__ data) {
+k_segsort_block(const int* __restrict__ big_list, int list_stride, const int* __restrict__ prefix, int* __restrict__ data) {
   extern __shared__ int s_seg[];
-  const int c = big_list[blockIdx.x];
+  const int c = big_list[(long long)blockIdx.x * list_stride];
   const int b = c ? prefix[c - 1] : 0, e = prefix[c];
   const int n = e - b;
-  if (n > SEG_BLOCK_CAP) { bitonic_steps(data + b, n, threadIdx.x, blockDim.x, true); return; }
+  if (n > SEG_BLOCK_CAP) { bitonic_steps(data + b, n, threadIdx.x, blockDim.x, true); return; }   // only reachable in the "large" launch
   for (int i = threadIdx.x; i < n; i += blockDim.x) s_seg[i] = data[b + i];
   __syncthreads();
   bitonic_steps(s_seg, n, threadIdx.x, blockDim.x, true);
@@ -375,36 +382,62 @@ __global__ void k_judge_collect(int V, const int* __restrict__ valid, const uint
 // One CTA per valid cell, one thread per sample; the cell's list is staged in
 // shared memory in chunks (inverse covariance, centre, alpha, cutoff, 48 SH
 // floats per Gaussian) and consumed in list order.
-constexpr int EV_CHUNK = 32;
-struct EvGauss { float px, py, pz, a, i00, i01, i02, i11, i12, i22, cut, ok; };
+constexpr int EV_CHUNK = 64;   // list entries examined per pass: one per thread
+struct EvGauss { float px, py, pz, a, i00, i01, i02, i11, i12, i22, cut, pad; };
 
+// One CTA per valid cell, one thread per sample.  A cell's list holds every Gaussian whose cut-off box, grown by `padding`
+// cells, meets the cell (GV:4030-4100) — with padding 1 at least 27 cells per Gaussian, most of which it cannot reach.  Each
+// pass therefore first decides PER (cell, Gaussian) pair, one thread per list entry, whether the LPF-widened Gaussian can
+// reach any of the cell's 64 samples at all: the set where the evaluator's own cut-off test  -1/2 d^T (Sigma + LPF)^-1 d >= ln(1/255 / alpha)
+// holds has the axis-aligned half extent sqrt(r^2 (Sigma + LPF)_aa), r^2 = -2 ln(1/255 / alpha), and is tested against the
+// bounding box of the cell's sample positions (measured, so deformed samples are handled too).  Survivors are compacted in
+// list order into shared memory and only THEIR 192-byte SH rows are fetched; the per-sample loop then runs over the
+// survivors exactly as before, so the sums (and their order) are unchanged.
 __global__ void __launch_bounds__(64)
 k_grid_eval(const int* __restrict__ valid, const int* __restrict__ prefix, const int* __restrict__ lists,
             const float* __restrict__ samples, const float* __restrict__ pos, const float* __restrict__ rot,
             const float* __restrict__ scale, const float* __restrict__ opacity, const float* __restrict__ shs,
             const float* __restrict__ ada_lpf, float* __restrict__ out_feature, float* __restrict__ out_opacity) {
   __shared__ EvGauss s_g[EV_CHUNK];
+  __shared__ int s_gi[EV_CHUNK];
   __shared__ float s_sh[EV_CHUNK][48];
+  __shared__ float s_box[2][6];
+  __shared__ int s_wcnt[2];
   const int i = blockIdx.x;
   const int c = valid[i];
   const int beg = c ? prefix[c - 1] : 0, end = prefix[c];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* lp = ada_lpf + (size_t)c * 9;
   const float* xs = samples + ((size_t)i * 64 + tid) * 3;
   const float x0 = xs[0], x1 = xs[1], x2 = xs[2];
+  // bounding box of the cell's samples
+  float bmn[3] = {x0, x1, x2}, bmx[3] = {x0, x1, x2};
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int a = 0; a < 3; a++) { bmn[a] = fminf(bmn[a], __shfl_xor_sync(0xffffffffu, bmn[a], o)); bmx[a] = fmaxf(bmx[a], __shfl_xor_sync(0xffffffffu, bmx[a], o)); }
+  if (lane == 0)
+#pragma unroll
+    for (int a = 0; a < 3; a++) { s_box[warp][a] = bmn[a]; s_box[warp][3 + a] = bmx[a]; }
+  __syncthreads();
+  float bc[3], bh[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    const float mn = fminf(s_box[0][a], s_box[1][a]), mx = fmaxf(s_box[0][3 + a], s_box[1][3 + a]);
+    bc[a] = 0.5f * (mn + mx); bh[a] = 0.5f * (mx - mn);
+  }
   float acc[48];
 #pragma unroll
   for (int u = 0; u < 48; u++) acc[u] = 0.f;
   float opa = 0.f;
   for (int base = beg; base < end; base += EV_CHUNK) {
-    const int nc = min(EV_CHUNK, end - base);
     __syncthreads();
-    if (tid < nc) {
-      const int g = lists[base + tid];
-      EvGauss e; e.ok = 0.f;
+    // ---- one list entry per thread: evaluator constants + reach test
+    bool keep = false; EvGauss e; int g = 0;
+    if (base + tid < end) {
+      g = lists[base + tid];
       const float a = opacity[g];
-      e.px = pos[3 * g]; e.py = pos[3 * g + 1]; e.pz = pos[3 * g + 2]; e.a = a;
-      e.i00 = e.i01 = e.i02 = e.i11 = e.i12 = e.i22 = 0.f; e.cut = 0.f;
+      e.px = pos[3 * g]; e.py = pos[3 * g + 1]; e.pz = pos[3 * g + 2]; e.a = a; e.pad = 0.f;
       if (a > 1.0f / 255.0f) {
         const float4 r4 = ldg4(rot + 4 * g);
         const Quat q = quat_normalized(Quat{r4.x, r4.y, r4.z, r4.w});
@@ -414,10 +447,10 @@ k_grid_eval(const int* __restrict__ valid, const int* __restrict__ prefix, const
         for (int r = 0; r < 3; r++)
 #pragma unroll
           for (int cc = 0; cc < 3; cc++) {
-            float s = 0.f;
+            float sum = 0.f;
 #pragma unroll
-            for (int d = 0; d < 3; d++) s += R[r][d] * (scale[3 * g + d] * scale[3 * g + d]) * R[cc][d];
-            Sg[r][cc] = s + lp[3 * r + cc];
+            for (int d = 0; d < 3; d++) sum += R[r][d] * (scale[3 * g + d] * scale[3 * g + d]) * R[cc][d];
+            Sg[r][cc] = sum + lp[3 * r + cc];
           }
         const float c00 = Sg[1][1] * Sg[2][2] - Sg[1][2] * Sg[2][1];
         const float c01 = Sg[1][2] * Sg[2][0] - Sg[1][0] * Sg[2][2];
@@ -430,25 +463,34 @@ k_grid_eval(const int* __restrict__ valid, const int* __restrict__ prefix, const
           e.i12 = (Sg[0][2] * Sg[1][0] - Sg[0][0] * Sg[1][2]) * id;
           e.i22 = (Sg[0][0] * Sg[1][1] - Sg[0][1] * Sg[1][0]) * id;
           e.cut = logf(1.0f / 255.0f / a);
-          e.ok = 1.f;
+          const float r2 = -2.0f * e.cut * 1.001f;    // margin for the rounded arithmetic of the per-sample test
+          keep = fabsf(e.px - bc[0]) <= bh[0] + sqrtf(r2 * fmaxf(Sg[0][0], 0.f)) * 1.0001f + 1e-7f &&
+                 fabsf(e.py - bc[1]) <= bh[1] + sqrtf(r2 * fmaxf(Sg[1][1], 0.f)) * 1.0001f + 1e-7f &&
+                 fabsf(e.pz - bc[2]) <= bh[2] + sqrtf(r2 * fmaxf(Sg[2][2], 0.f)) * 1.0001f + 1e-7f;
         }
       }
-      s_g[tid] = e;
     }
-    for (int v = tid; v < nc * 12; v += 64) {
+    // ---- compaction in list order
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_wcnt[warp] = __popc(m);
+    __syncthreads();
+    const int slot = (warp ? s_wcnt[0] : 0) + __popc(m & ((1u << lane) - 1u));
+    const int nk = s_wcnt[0] + s_wcnt[1];
+    if (keep) { s_g[slot] = e; s_gi[slot] = g; }
+    __syncthreads();
+    for (int v = tid; v < nk * 12; v += 64) {
       const int r = v / 12, c4 = v - r * 12;
-      const float4 x = __ldg(reinterpret_cast<const float4*>(shs + (size_t)lists[base + r] * 48) + c4);
+      const float4 x = __ldg(reinterpret_cast<const float4*>(shs + (size_t)s_gi[r] * 48) + c4);
       float* d = &s_sh[r][c4 * 4];
       d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w;
     }
     __syncthreads();
-    for (int t = 0; t < nc; t++) {
-      const EvGauss e = s_g[t];
-      if (e.ok == 0.f) continue;
-      const float d0 = x0 - e.px, d1 = x1 - e.py, d2 = x2 - e.pz;
-      const float pw = -0.5f * (e.i00 * d0 * d0 + e.i11 * d1 * d1 + e.i22 * d2 * d2) - (e.i01 * d0 * d1 + e.i02 * d0 * d2 + e.i12 * d1 * d2);
-      if (pw > 0.0f || pw < e.cut) continue;
-      const float w = e.a * expf(pw);
+    for (int t = 0; t < nk; t++) {
+      const EvGauss ev = s_g[t];
+      const float d0 = x0 - ev.px, d1 = x1 - ev.py, d2 = x2 - ev.pz;
+      const float pw = -0.5f * (ev.i00 * d0 * d0 + ev.i11 * d1 * d1 + ev.i22 * d2 * d2) - (ev.i01 * d0 * d1 + ev.i02 * d0 * d2 + ev.i12 * d1 * d2);
+      if (pw > 0.0f || pw < ev.cut) continue;
+      const float w = ev.a * expf(pw);
       opa += w;
 #pragma unroll
       for (int u = 0; u < 48; u++) acc[u] += w * s_sh[t][u];
@@ -479,17 +521,17 @@ static GridScratch carve(void* scratch, int G, long long N) {
   (void)N; return s;
 }
 static int sort_segments(long long ncell, const int* prefix, int* data, int* big, cudaStream_t st) {
-  ARAP_CUDA_TRY(cudaMemsetAsync(big, 0, sizeof(int), st));
-  k_segsort_warp<<<(unsigned)((ncell + 7) / 8), 256, 0, st>>>(ncell, prefix, data, big, big + 1);
+  // big[0], big[1]: counts of medium / large cells; big + 2: the list (ncell entries: medium from the front, large from the back)
+  ARAP_CUDA_TRY(cudaMemsetAsync(big, 0, 2 * sizeof(int), st));
+  k_segsort_warp<<<(unsigned)((ncell + 7) / 8), 256, 0, st>>>(ncell, prefix, data, big, big + 2);
   ARAP_KERNEL_CHECK();
-  int nbig = 0;
-  ARAP_CUDA_TRY(cudaMemcpyAsync(&nbig, big, sizeof(int), cudaMemcpyDeviceToHost, st));
+  int nbig[2] = {0, 0};
+  ARAP_CUDA_TRY(cudaMemcpyAsync(nbig, big, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
   ARAP_CUDA_TRY(cudaStreamSynchronize(st));
-  if (nbig > 0) {
-    static bool attr_set = false;
-    if (!attr_set) { ARAP_CUDA_TRY(cudaFuncSetAttribute(k_segsort_block, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_BLOCK_CAP * (int)sizeof(int))); attr_set = true; }
-    k_segsort_block<<<nbig, 1024, SEG_BLOCK_CAP * sizeof(int), st>>>(big + 1, prefix, data); ARAP_KERNEL_CHECK();
-  }
+  static bool attr_set = false;
+  if (!attr_set) { ARAP_CUDA_TRY(cudaFuncSetAttribute(k_segsort_block, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_BLOCK_CAP * (int)sizeof(int))); attr_set = true; }
+  if (nbig[0] > 0) { k_segsort_block<<<nbig[0], 1024, SEG_MED_CAP * sizeof(int), st>>>(big + 2, 1, prefix, data); ARAP_KERNEL_CHECK(); }
+  if (nbig[1] > 0) { k_segsort_block<<<nbig[1], 1024, SEG_BLOCK_CAP * sizeof(int), st>>>(big + 2 + ncell - 1, -1, prefix, data); ARAP_KERNEL_CHECK(); }
   return ARAP_OK;
 }
 }  // namespace

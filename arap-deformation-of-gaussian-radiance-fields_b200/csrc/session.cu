@@ -369,7 +369,8 @@ static int build_lists(arap_ctx* c) {  // boxes -> count -> fill (GV:3961-4100 /
   long long P = 0;
   TRY(arapk_footprint_count(c->N, c->gs_aabb.p, c->aabb, c->step, c->G, c->prm.padding, c->fp_prefix.p, &P, c->grid_scratch.p, c->grid_scratch.n, st));
   c->P = P;
-  TRY(c->lists.alloc((size_t)std::max<long long>(P, 1)));
+  // 12 % head-room: a stroke-end rebuild after a deformation usually has a few per cent more pairs, and re-allocating 1.5 GB costs ~10 ms
+  if ((size_t)std::max<long long>(P, 1) > c->lists.n) TRY(c->lists.alloc((size_t)(std::max<long long>(P, 1) * 1.12) + 1024));
   TRY(arapk_footprint_fill(c->N, c->gs_aabb.p, c->aabb, c->step, c->G, c->prm.padding, c->fp_prefix.p, c->lists.p, c->grid_scratch.p, c->grid_scratch.n, st));
   return ARAP_OK;
 }
