@@ -36,7 +36,7 @@ class Params(C.Structure):
                 ("w_rot", C.c_double), ("w_reg", C.c_double), ("w_con", C.c_double),
                 ("max_gn_iters", C.c_int), ("max_cg_iters", C.c_int), ("cg_tol", C.c_double),
                 ("skip_static_endpoints", C.c_int), ("solver_global_memory", C.c_int), ("lbs_mode", C.c_int),
-                ("newton_eta0", C.c_double), ("warm_start", C.c_int), ("solver_ctas", C.c_int), ("lazy_sample_sh", C.c_int), ("fps_mode", C.c_int)]
+                ("newton_eta0", C.c_double), ("warm_start", C.c_int), ("solver_ctas", C.c_int), ("lazy_sample_sh", C.c_int), ("fps_mode", C.c_int), ("solver_pipelined", C.c_int)]
 
 
 class SolveStats(C.Structure):

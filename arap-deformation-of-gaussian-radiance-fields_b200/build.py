@@ -24,9 +24,9 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = [*ARCH, "-lineinfo", "-O3", "-std=c++17", "-fmad=false", "-Xcompiler", "-fPIC"]
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off"]
 
-CU = ["apply.cu", "knn.cu", "solve.cu", "solve_smem.cu", "grid.cu", "session.cu"]
+CU = ["apply.cu", "knn.cu", "solve.cu", "solve_smem.cu", "solve_pipe.cu", "grid.cu", "session.cu"]
 CPP = ["host_io.cpp"]
-HEADERS = ["common.cuh", "device_math.cuh", "sh_fast.cuh", "solve_dev.h", "kernels.h", "session.h", "../../include/arapgs.h", "../../include/arapgs_kernels.h"]
+HEADERS = ["common.cuh", "device_math.cuh", "sh_fast.cuh", "solve_dev.h", "solve_smem_dev.cuh", "kernels.h", "session.h", "../../include/arapgs.h", "../../include/arapgs_kernels.h"]
 
 
 def _stale(src: Path, obj: Path) -> bool:

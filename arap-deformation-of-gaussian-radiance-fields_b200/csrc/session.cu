@@ -184,7 +184,7 @@ struct arap_ctx {
   std::vector<std::vector<uint32_t>> blocks; std::vector<int> block_types;
   int n_active_entries = 0;
   // constraints (two variants prepared at set_blocks: per-node and centre)
-  struct ConSet { int n_groups = 0; long long n_entries = 0; DBuf<int> grp_off, grp_member, aim_off, aim_nodes, cin_off, cin_grp, cin_member, cin_slot; DBuf<float> grp_aim; };
+  struct ConSet { int n_groups = 0; long long n_entries = 0; int pipe_ok = 0; int pipe_ctas = -1; std::vector<int> h_grp_off, h_cin_off; DBuf<int> grp_off, grp_member, aim_off, aim_nodes, cin_off, cin_grp, cin_member, cin_slot; DBuf<float> grp_aim; };
   ConSet con[2];
   // solve
   DBuf<double> rot_d, trans_d, stats_d, warm_d; DBuf<char> solve_ws; DBuf<char> node_xf, node_xf32; DBuf<float> node_q;
@@ -230,7 +230,7 @@ extern "C" int arap_default_params(arap_params* p) {
   if (!p) return ARAP_ERR_INVALID;
   p->grid_num = 64; p->padding = 1; p->knn_k = 10; p->node_num = 150; p->high_quality = 0; p->lpf_parameter = 0.2f;
   p->w_rot = 1.0; p->w_reg = 10.0; p->w_con = 100.0; p->max_gn_iters = 30; p->max_cg_iters = 4000; p->cg_tol = 1e-10;
-  p->skip_static_endpoints = 0; p->solver_global_memory = 0; p->lbs_mode = 0; p->newton_eta0 = 1e-6; p->warm_start = 1; p->solver_ctas = 0; p->fps_mode = 0; p->lazy_sample_sh = 0;
+  p->skip_static_endpoints = 0; p->solver_global_memory = 0; p->lbs_mode = 0; p->newton_eta0 = 1e-6; p->warm_start = 1; p->solver_ctas = 0; p->fps_mode = 0; p->lazy_sample_sh = 0; p->solver_pipelined = 1;
   return ARAP_OK;
 }
 
@@ -810,6 +810,7 @@ static int build_conset(arap_ctx* c, arap_ctx::ConSet& cs, bool on_center) {
     cin_off[i + 1] = (int)cg.size();
   }
   cs.n_entries = (long long)cg.size();
+  cs.h_grp_off = grp_off; cs.h_cin_off = cin_off; cs.pipe_ctas = -1;   // eligibility of the one-barrier solver kernel: decided at the first solve
   auto up = [&](DBuf<int>& d, std::vector<int>& v) { if (v.empty()) v.push_back(0); return upload(d, v.data(), v.size(), false, c->stream); };
   TRY(up(cs.grp_off, grp_off)); TRY(up(cs.grp_member, grp_member)); TRY(up(cs.aim_off, aim_off)); TRY(up(cs.aim_nodes, aim_nodes));
   TRY(up(cs.cin_off, cin_off)); TRY(up(cs.cin_grp, cg)); TRY(up(cs.cin_member, cm)); TRY(up(cs.cin_slot, csl));
@@ -945,7 +946,14 @@ extern "C" int arap_solve(arap_ctx* ctx, int on_center) {
   G.grp_off = cs.grp_off.p; G.grp_member = cs.grp_member.p; G.grp_aim = cs.grp_aim.p;
   G.cin_off = cs.cin_off.p; G.cin_grp = cs.cin_grp.p; G.cin_member = cs.cin_member.p; G.cin_slot = cs.cin_slot.p; G.n_cin_entries = cs.n_entries;
   ArapSolveParams P{ctx->prm.w_rot, ctx->prm.w_reg, ctx->prm.w_con, ctx->prm.max_gn_iters, ctx->prm.max_cg_iters, ctx->prm.cg_tol, ctx->prm.solver_global_memory, ctx->prm.newton_eta0,
-                    ctx->prm.warm_start ? ctx->warm_d.p : nullptr, ctx->prm.solver_ctas, ctx->prm.warm_start > 1 ? ctx->prm.warm_start - 1 : 0};
+                    ctx->prm.warm_start ? ctx->warm_d.p : nullptr, ctx->prm.solver_ctas, ctx->prm.warm_start > 1 ? ctx->prm.warm_start - 1 : 0, 0};
+  if (ctx->prm.solver_pipelined && !ctx->prm.solver_global_memory) {
+    if (cs.pipe_ctas != ctx->prm.solver_ctas) {   // depends on the grid size: re-check when solver_ctas changes
+      cs.pipe_ok = arapk_solve_pipe_eligible(G.M, G.k, cs.n_groups, cs.h_grp_off.data(), cs.h_cin_off.data(), ctx->prm.solver_ctas);
+      cs.pipe_ctas = ctx->prm.solver_ctas;
+    }
+    P.pipelined = cs.pipe_ok;
+  }
   TRY(ctx->solve_ws.alloc(arapk_solve_workspace_bytes(G.M, G.k, G.n_groups)));
   TRY(arapk_solve(&G, &P, ctx->solve_ws.p, ctx->solve_ws.n, ctx->rot_d.p, ctx->trans_d.p, ctx->stats_d.p, st));
   ctx->solved = true;

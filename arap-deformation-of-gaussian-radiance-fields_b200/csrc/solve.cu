@@ -473,6 +473,7 @@ extern "C" size_t arapk_solve_workspace_bytes(int M, int k, int n_groups) {
   // (<= groups * 20 * k entries) + partials
   size_t d = (size_t)M * 12 * 7 + (size_t)M * k * 4 + (size_t)M * k * 3 * 2 + (size_t)(n_groups + 1) * 3 +
              (size_t)(n_groups + 1) * 20 * k * 4 * 2 + (size_t)(n_groups + 1) * 20 * k / 2 + 2 * 2048 * NRED + 64 + 32;
+  d += solve_pipe_extra_doubles(M, k, n_groups) + 2;   // one-barrier kernel (solve_pipe.cu): double-buffered partials
   return d * sizeof(double);
 }
 
@@ -507,9 +508,16 @@ extern "C" int arapk_solve(const ArapSolveGraph* G, const ArapSolveParams* P, vo
   S.u_con = w; w += (size_t)(G->n_groups + 1) * 3;
   S.partial = w; w += 2 * 2048 * NRED;
   unsigned* counter = reinterpret_cast<unsigned*>(w);
+  w += 64 + 32;
+  if ((w - (double*)workspace) & 1) w += 1;
+  double* pipe_extra = w;
   S.rot_out = rot_out; S.trans_out = trans_out; S.stats = stats_dev;
   S.warm = P->warm_buf;
   S.warm_systems = P->warm_systems > 0 ? std::min(P->warm_systems, SOLVE_WARM_MAX) : SOLVE_WARM_MAX;
+  if (!P->force_global_kernel && P->pipelined) {   // fastest path: one grid barrier per PCG iteration (solve_pipe.cu)
+    const int rc = launch_solve_pipe(S, reinterpret_cast<unsigned*>(S.partial), pipe_extra, st, P->max_ctas);
+    if (rc >= 0) return rc;
+  }
   if (!P->force_global_kernel) {   // fast path: per-node state resident in shared memory (solve_smem.cu)
     const int rc = launch_solve_smem(S, reinterpret_cast<unsigned*>(S.partial), st, P->max_ctas);   // barrier slots live in the partials area (2 x 148 x 64 B)
     if (rc >= 0) return rc;

@@ -44,5 +44,9 @@ constexpr int SOLVE_WARM_MAX = 4;
 // solve_smem.cu: returns ARAP_OK if launched, a positive error code on CUDA failure, -1 if the per-CTA slice does not
 // fit in shared memory (the caller then runs the global-memory kernel).
 int launch_solve_smem(const SolveDev& S, unsigned* counter, cudaStream_t st, int max_ctas);
+// solve_pipe.cu: one-barrier pipelined PCG; `extra` = solve_pipe_extra_doubles() doubles of workspace, 16-byte aligned.
+// Same return convention.
+int launch_solve_pipe(const SolveDev& S, unsigned* counter, double* extra, cudaStream_t st, int max_ctas);
+size_t solve_pipe_extra_doubles(int M, int k, int n_groups);
 
 }  // namespace arapgs

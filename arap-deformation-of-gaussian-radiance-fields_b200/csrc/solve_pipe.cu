@@ -1,0 +1,677 @@
+// Stage (c), fastest path: the Gauss-Newton solve of solve_smem.cu with ONE grid barrier per PCG iteration.
+//
+// Same energy, same Jacobian, same Gauss-Newton loop, same Jacobi preconditioner and the same stopping rules as
+// solve.cu / solve_smem.cu (Deform.cpp:77-581; see solve.cu for the citations).  Two things change in the linear solve:
+//
+// 1. H = J^T J is applied as an explicit stencil instead of as J^T (J v) with a grid barrier between the two halves.
+//    For node i and component j (unknown 4-vector y_ij = (A_j0, A_j1, A_j2, t_j)) the rows of Deform.cpp:186-330 give
+//      (H v)_ij =  w_reg^2 [ C_i v_ij  -  sum_s c_is vt_{q(s) j}  +  e_t ((indeg_i + static_in_i) vt_ij - sum_{(i',s') -> i} c_i's' . v_i'j) ]
+//               +  E_rot part (node-local: rot_t(rot_lin(A_i, v_i)))
+//               +  sum_{column entries e of i} coef_e u_{g(e) j},      u_gj = sum_{entries e' of group g} coef_e' . v_{q(e') j}
+//    with c_is = (g_q - g_i, 1), C_i = sum_s c_is c_is^T.  Every product that involves a REMOTE 4-vector is formed by that
+//    vector's owner when it publishes the vector ("partials": one double per edge and component delivered to the in-edge
+//    slot of the neighbour, one per constraint entry delivered to the entry's slot in its group), so the consumer side is
+//    a gather of doubles and the whole product needs one exchange.
+// 2. The recurrences are those of pipelined PCG (Ghysels & Vanroose 2014, Alg. 3 with a diagonal preconditioner, so
+//    u = D^-1 r, q = D^-1 s, m = D^-1 w need no storage): the dot products of an iteration are taken BEFORE its stencil
+//    product and reduced by the same barrier that makes the published vector visible.  Iterates agree with classical PCG
+//    to rounding (tests/studies/pipelined_cg.py: identical iteration counts down to 1e-10 on the oracle's Jacobian).
+//
+// Per iteration and CTA: gather (out-neighbour t components, in-edge partials, constraint-group partials) -> stencil ->
+// recurrences -> dots -> publish m and its partials -> barrier.  Published arrays are double-buffered (a CTA is at most
+// one barrier ahead of the slowest reader).  Node ownership, the slice layout, the nonlinear residual / gradient
+// evaluation and the barrier are those of solve_smem.cu (shared through solve_smem_dev.cuh).
+//
+// Constraint groups: a group with one member (per-node constraints, Deform.cpp:300-330 with one control node per group)
+// has k entries and every reader sums its k partials itself; multi-member groups (constraints on block centres: <= 20
+// members, DC:4) are summed once per CTA by a warp.  At most PIPE_NBIG multi-member groups; the slice's column entries must
+// fit the shared-memory table — arapk_solve_pipe_eligible() checks both on the host and the kernel re-checks (flag bit 2).
+#include <cooperative_groups.h>
+#include <algorithm>
+#include <cstdlib>
+#include <type_traits>
+#include <vector>
+#include "common.cuh"
+#include "kernels.h"
+#include "solve_dev.h"
+
+namespace arapgs {
+
+#include "solve_smem_dev.cuh"
+
+constexpr int PIPE_NBIG = 8;   // multi-member constraint groups a solve may have
+
+template <int K, int NL> struct PipeCaps {
+  static constexpr int C = NL <= 112 ? (K <= 10 ? 1024 : 832) : (K <= 10 ? 672 : 512);
+};
+// constraint partials of one group member: [component j][K] doubles in a block of MS doubles (a multiple of 128 bytes, so a
+// block is 2-3 whole lines and a team of lanes fetches it with one coalesced instruction)
+template <int K> struct PipeK { static constexpr int KP = K; static constexpr int MS = (3 * K + 15) / 16 * 16; };
+
+struct PipeBuf { double* pb[2]; double* db[2]; double* pi[2]; };
+
+__device__ __forceinline__ double d4_dot(const D4& a, const D4& b) { return fma(a.d, b.d, fma(a.c, b.c, fma(a.b, b.b, a.a * b.a))); }
+__device__ __forceinline__ D4 d4_axpy(double a, const D4& x, const D4& y) { return D4{fma(a, x.a, y.a), fma(a, x.b, y.b), fma(a, x.c, y.c), fma(a, x.d, y.d)}; }
+__device__ __forceinline__ D4 d4_mul(const D4& x, const D4& y) { return D4{x.a * y.a, x.b * y.b, x.c * y.c, x.d * y.d}; }
+
+// Thread mapping of the linear solve: one thread per ROW (node li, component j) = the 4-vector (A_j0, A_j1, A_j2, t_j);
+// row index rr = 4 li + j, j = 3 idle — a node's three rows share a quad, no lane exchanges are needed anywhere.
+constexpr int PIPE_DR = 5;    // rounds of quad-cooperative in-edge partial loads in flight (4 lanes x 16 bytes each: in-degree <= 13)
+constexpr int PIPE_PPB = 10;  // constraint-entry rounds a warp has in flight in the group-sum pass
+
+// ---- publish row (li, j) of the CTA's new m: keep it in L.ms, its t component for the neighbours' E_reg rows, its
+// edge partials c_is . m_ij into the in-edge slots of the neighbours, its constraint partials into the entries' group slots.
+template <int K>
+__device__ __forceinline__ void publish_row(const Loc& L, int li, int j, const D4& m, double* __restrict__ pbn, double* __restrict__ dbn,
+                                            double* __restrict__ pin) {
+  st4(L.ms + (size_t)li * 12 + 4 * j, m);
+  pbn[(size_t)(li * L.B + L.b) * 12 + 9 + j] = m.d;
+#pragma unroll
+  for (int s = 0; s < K; s++) {
+    const int e = li * K + s;
+    const int slot = L.o2i[e];
+    const float4 b = L.be[e];
+    const double v = fma(m.c, (double)b.z, fma(m.b, (double)b.y, m.a * (double)b.x)) + m.d;
+    if (slot >= 0) dbn[(size_t)slot * 3 + j] = v;
+  }
+  const int eb = L.lcb[li], ee = eb + (L.ce[li] - L.cb[li]);
+  for (int e = eb; e < ee; e++) pin[(size_t)L.eslot[e] + (size_t)j * PipeK<K>::KP] = d4_dot(ld4(L.cc + (size_t)e * 4), m);
+}
+// all rows from L.ms (after the gradient pass, which works per unknown)
+template <int K>
+__device__ __forceinline__ void publish_all(const Loc& L, double* pbn, double* dbn, double* pin) {
+  for (int rr = threadIdx.x; rr < L.nloc * 4; rr += SM_THREADS) {
+    const int li = rr >> 2, j = rr & 3;
+    if (j == 3 || !L.fr[li]) continue;
+    publish_row<K>(L, li, j, ld4(L.ms + (size_t)li * 12 + 4 * j), pbn, dbn, pin);
+  }
+}
+// node-local E_rot rows of the new m (needs all three rows of a node: after a CTA sync)
+__device__ __forceinline__ void uro_pass(const SolveDev& S, const Loc& L) {
+  for (int li = SM_THREADS - 1 - (int)threadIdx.x; li < L.nloc; li += SM_THREADS) {
+    if (!L.fr[li]) continue;
+    const size_t ob = (size_t)li * 12;
+    double u[6];
+    rot_lin(ld4(L.xs + ob), ld4(L.xs + ob + 4), ld4(L.xs + ob + 8), ld4(L.ms + ob), ld4(L.ms + ob + 4), ld4(L.ms + ob + 8), S.w_rot, u);
+#pragma unroll
+    for (int t = 0; t < 6; t++) L.uro[li * 6 + t] = u[t];
+  }
+}
+
+// ---- y = H m, row by row; f(t4, li, j, y) consumes the result (t4 = offset of the row in the slice vectors).
+// m = L.ms for the CTA's own rows; `pb` the published t components, `db` / `pi` the partials published with them.
+template <int K> struct RowLd { double mt[K]; double2 dd[PIPE_DR]; };
+// The in-edge partials of a node are 3 x indeg contiguous doubles ([slot][component]); the four lanes of the node's quad
+// (the idle j = 3 lane included) fetch them 64 contiguous bytes per instruction — a request per line instead of one per slot.
+template <int K>
+__device__ __forceinline__ void row_issue(const Loc& L, const double* __restrict__ pb, const double* __restrict__ db, int rr, RowLd<K>& G) {
+  const int li = rr >> 2, j = rr & 3;
+  const bool qact = li < L.nloc && L.fr[li];
+  const bool act = qact && j < 3;
+#pragma unroll
+  for (int s = 0; s < K; s++) {
+    const int nq = act ? L.nbr[li * K + s] : -1;
+    G.mt[s] = nq >= 0 ? __ldcg(pb + (size_t)nq * 12 + 9 + j) : 0.0;
+  }
+  const int ib3 = qact ? L.inb[li] * 3 : 0, ie3 = qact ? L.ine[li] * 3 : 0;
+  const int E0 = (ib3 & ~1) + 2 * j;
+#pragma unroll
+  for (int r = 0; r < PIPE_DR; r++) {
+    const int E = E0 + 8 * r;
+    G.dd[r] = E < ie3 ? __ldcg(reinterpret_cast<const double2*>(db + E)) : make_double2(0.0, 0.0);
+  }
+}
+// sum of the in-edge partials of (node, component) for all three components, over the quad; every lane of the quad calls this
+template <int K>
+__device__ __forceinline__ double dd_reduce(const Loc& L, const double* __restrict__ db, int li, int j, const RowLd<K>& G) {
+  const int ib3 = L.inb[li] * 3, ie3 = L.ine[li] * 3;
+  const int E0 = (ib3 & ~1) + 2 * j;
+  const int rel0 = E0 - ib3;                 // -1, 0, 1, ...: index of the lane's first element relative to the block
+  int jx = (rel0 + 3) % 3;                   // component of element .x (for rel0 = -1 the element is outside the block)
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+  for (int r = 0; r < PIPE_DR; r++) {
+    const int E = E0 + 8 * r;
+    const bool vx = E >= ib3 && E < ie3, vy = E + 1 < ie3;   // E + 1 >= ib3 always
+    const double x = vx ? G.dd[r].x : 0.0, y = vy ? G.dd[r].y : 0.0;
+    // .x has component jx, .y component jx + 1 (mod 3)
+    a0 += jx == 0 ? x : jx == 2 ? y : 0.0;
+    a1 += jx == 1 ? x : jx == 0 ? y : 0.0;
+    a2 += jx == 2 ? x : jx == 1 ? y : 0.0;
+    jx = jx == 0 ? 2 : jx - 1;               // + 8 elements = + 2 mod 3
+  }
+  for (int E = E0 + 8 * PIPE_DR; E < ie3; E += 8) {   // in-degree > 13: rare
+    const double2 v = __ldcg(reinterpret_cast<const double2*>(db + E));
+    const int jj = (E - ib3) % 3;
+    const double y = E + 1 < ie3 ? v.y : 0.0;
+    a0 += jj == 0 ? v.x : jj == 2 ? y : 0.0;
+    a1 += jj == 1 ? v.x : jj == 0 ? y : 0.0;
+    a2 += jj == 2 ? v.x : jj == 1 ? y : 0.0;
+  }
+  const unsigned qmask = 0xFu << (threadIdx.x & 28);
+  a0 += __shfl_xor_sync(qmask, a0, 1, 4); a1 += __shfl_xor_sync(qmask, a1, 1, 4); a2 += __shfl_xor_sync(qmask, a2, 1, 4);
+  a0 += __shfl_xor_sync(qmask, a0, 2, 4); a1 += __shfl_xor_sync(qmask, a1, 2, 4); a2 += __shfl_xor_sync(qmask, a2, 2, 4);
+  return j == 0 ? a0 : j == 1 ? a1 : a2;
+}
+template <int K>
+__device__ __forceinline__ D4 row_finish(const SolveDev& S, const Loc& L, int li, int j, const RowLd<K>& G, double a2,
+                                         const double (*s_ubig)[3]) {
+  const double w2 = S.w_reg * S.w_reg;
+  const size_t t4 = (size_t)li * 12 + 4 * j;
+  const D4 m = ld4(L.ms + t4);
+  const double* cm = L.Cm + (size_t)li * 16;
+  D4 o{0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int s = 0; s < K; s++) {
+    const float4 b = L.be[li * K + s];
+    o.a = fma((double)b.x, G.mt[s], o.a); o.b = fma((double)b.y, G.mt[s], o.b); o.c = fma((double)b.z, G.mt[s], o.c); o.d += G.mt[s];
+  }
+  const int ib = L.inb[li], ie = L.ine[li];
+  D4 y{w2 * (d4_dot(ld4(cm), m) - o.a), w2 * (d4_dot(ld4(cm + 4), m) - o.b), w2 * (d4_dot(ld4(cm + 8), m) - o.c), w2 * (d4_dot(ld4(cm + 12), m) - o.d)};
+  y.d = fma(w2, (double)(ie - ib + L.sic[li]) * m.d - a2, y.d);
+  {
+    double u[6];
+#pragma unroll
+    for (int q = 0; q < 6; q++) u[q] = L.uro[li * 6 + q];
+    const D4 Aj = ld4(L.xs + t4);
+    y.a += rot_t(Aj, S.w_rot, u, 0); y.b += rot_t(Aj, S.w_rot, u, 1); y.c += rot_t(Aj, S.w_rot, u, 2);
+  }
+  const int eb = L.lcb[li], ee = eb + (L.ce[li] - L.cb[li]);
+  for (int e = eb; e < ee; e++) {
+    const double ug = L.emeta[e] < 0 ? s_ubig[L.erd[e]][j] : L.cu[e * 3 + j];
+    y = d4_axpy(ug, ld4(L.cc + (size_t)e * 4), y);
+  }
+  return y;
+}
+template <int K, class F>
+__device__ __forceinline__ void apply_H(const SolveDev& S, const Loc& L, const double* __restrict__ pb, const double* __restrict__ db,
+                                        const double* __restrict__ pi, int nbig, const int* s_big_g, double (*s_ubig)[3], F&& f,
+                                        double* tsub = nullptr) {
+  constexpr int KP = PipeK<K>::KP, MS = PipeK<K>::MS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nrows = L.nloc * 4;
+  const unsigned long long ts0 = gtime2();
+  // (1) multi-member groups: one warp per (group, component), fixed summation order
+  for (int t = warp; t < nbig * 3; t += SM_THREADS / 32) {
+    const int bi = t / 3, j = t - 3 * bi, g = s_big_g[bi];
+    const int mb = S.grp_off[g], me = S.grp_off[g + 1];
+    const int n = (me - mb) * K;
+    double acc = 0.0;
+    for (int r0 = lane; r0 < n; r0 += 8 * 32) {
+      double v[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const int r = r0 + 32 * q;
+        const int p = r / K, s = r - p * K;
+        v[q] = r < n ? __ldcg(pi + (size_t)(mb + p) * MS + j * KP + s) : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; q++) acc += v[q];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) s_ubig[bi][j] = acc;
+  }
+  // (2) single-member groups: a team of 16 (K <= 10) or 32 lanes per column entry fetches the member's 3 x K partials with one
+  // coalesced instruction (lane l: elements 2l, 2l + 1 of [component][K]); lanes 0..2 of the team then sum component 0..2 in slot order
+  {
+    constexpr int TL = 3 * K / 2 <= 16 ? 16 : 32, TPW = 32 / TL, H = K / 2;
+    const int team = lane / TL, tl = lane % TL;
+    constexpr int STRIDE = (SM_THREADS / 32) * TPW;
+    for (int eb = warp * TPW; eb < L.nent; eb += STRIDE * PIPE_PPB) {
+      double2 v[PIPE_PPB];
+#pragma unroll
+      for (int r = 0; r < PIPE_PPB; r++) {
+        const int e = eb + team + r * STRIDE;
+        const bool ok = e < L.nent && tl < 3 * H && L.emeta[e] >= 0;
+        v[r] = ok ? __ldcg(reinterpret_cast<const double2*>(pi + (size_t)L.erd[e]) + tl) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int r = 0; r < PIPE_PPB; r++) {
+        const int e = eb + team + r * STRIDE;
+        const double x = v[r].x + v[r].y;
+        double acc = 0.0;
+#pragma unroll
+        for (int t = 0; t < H; t++) acc += __shfl_sync(0xffffffffu, x, team * TL + ((tl < 3 ? tl : 0) * H + t));
+        if (tl < 3 && e < L.nent && L.emeta[e] >= 0) L.cu[e * 3 + tl] = acc;
+      }
+    }
+  }
+  RowLd<K> G;
+  int rr = tid;
+  row_issue<K>(L, pb, db, rr, G);
+  const unsigned long long ts1 = gtime2();
+  __syncthreads();   // group sums (L.cu, s_ubig) visible
+  const unsigned long long ts2 = gtime2();
+  unsigned long long ts3 = ts2;
+  // (3) the rows
+  for (;;) {
+    if (rr < nrows) {
+      const int li = rr >> 2, j = rr & 3;
+      if (L.fr[li]) {   // uniform over the quad
+        const double a2 = dd_reduce<K>(L, db, li, j, G);
+        if (j < 3) {
+          const D4 y = row_finish<K>(S, L, li, j, G, a2, s_ubig);
+          if (rr == tid) ts3 = gtime2();
+          f(li * 12 + 4 * j, li, j, y);
+        }
+      }
+    }
+    rr += SM_THREADS;
+    if (rr >= nrows) break;
+    row_issue<K>(L, pb, db, rr, G);
+  }
+  if (tsub && tid == 0) { tsub[0] += (double)(ts1 - ts0); tsub[1] += (double)(ts2 - ts1); tsub[2] += (double)(ts3 - ts2); tsub[3] += (double)(gtime2() - ts3); }
+}
+
+template <int K, int NL>
+__global__ void __launch_bounds__(SM_THREADS, 1) k_solve_pipe(SolveDev S, unsigned* counter, PipeBuf PB) {
+  constexpr int ccap = PipeCaps<K, NL>::C;
+  constexpr int KP = PipeK<K>::KP, MS = PipeK<K>::MS;
+  constexpr int UN = (3 * NL * 12 > NL * K * 3) ? 3 * NL * 12 : NL * K * 3;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Loc L;
+  {
+    double* d = reinterpret_cast<double*>(smem_raw);
+    L.xs = d; d += (size_t)NL * 12; L.rs = d; d += (size_t)NL * 12; L.ps = d; d += (size_t)NL * 12;
+    L.hs = d; d += (size_t)NL * 12; L.ds = d; d += (size_t)NL * 12; L.ms = d; d += (size_t)NL * 12;
+    // w, z, s live only inside a linear solve; the row values of the nonlinear residual (L.us) only between solves
+    L.ws = d; L.zs = d + (size_t)NL * 12; L.ss = d + (size_t)2 * NL * 12; L.us = d; d += UN;
+    L.uro = d; d += (size_t)NL * 6;
+    L.Cm = d; d += (size_t)NL * 16;
+    L.cc = d; d += (size_t)ccap * 4;
+    L.cu = d; d += (size_t)ccap * 3;
+    if ((d - reinterpret_cast<double*>(smem_raw)) & 1) d += 1;
+    L.be = reinterpret_cast<float4*>(d);
+    int* ip = reinterpret_cast<int*>(L.be + (size_t)NL * K);
+    L.nbr = ip; ip += (size_t)NL * K; L.o2i = ip; ip += (size_t)NL * K;
+    L.inb = ip; ip += NL; L.ine = ip; ip += NL; L.cb = ip; ip += NL; L.ce = ip; ip += NL; L.sic = ip; ip += NL; L.fr = ip; ip += NL;
+    L.lcb = ip; ip += NL; L.eslot = ip; ip += ccap; L.erd = ip; ip += ccap; L.emeta = ip; ip += ccap;
+    L.goff = nullptr; L.gq = nullptr; L.gc = nullptr; L.cpart = nullptr; L.cg = nullptr; L.use_g = 0; L.use_c = 0; L.ng = 0; L.ngent = 0;
+  }
+  const int M = S.M, B = gridDim.x, b = blockIdx.x, tid = threadIdx.x;
+  L.b = b; L.B = B; L.nloc = M > b ? (M - b + B - 1) / B : 0;
+  const int nloc = L.nloc, NU = nloc * 12;
+  int phase = 0;
+  double red[SM_NRED];
+  __shared__ int s_big_g[PIPE_NBIG];
+  __shared__ double s_ubig[PIPE_NBIG][3];
+  __shared__ int s_cnt[4];
+  if (tid < 4) s_cnt[tid] = 0;
+  __syncthreads();
+
+  // ---- slice set-up: graph meta, per-edge constants, x = identity
+  for (int li = tid; li < nloc; li += SM_THREADS) {
+    const int i = li * B + b;
+    L.fr[li] = S.node_free[i]; L.inb[li] = S.in_off[i]; L.ine[li] = S.in_off[i + 1];
+    L.cb[li] = S.cin_off[i]; L.ce[li] = S.cin_off[i + 1]; L.sic[li] = S.static_in_cnt[i];
+    for (int t = S.cin_off[i]; t < S.cin_off[i + 1]; t++) {   // w_con wei (v_c - g_q, 1) (Deform.cpp:325-328)
+      const int m = S.cin_member[t];
+      const double wv = S.w_con * S.anc_w[m * K + S.cin_slot[t]];
+      double* c = S.ccoef + (size_t)t * 4;
+      c[0] = wv * (double)(S.node_pos[3 * m] - S.node_pos[3 * i]);
+      c[1] = wv * (double)(S.node_pos[3 * m + 1] - S.node_pos[3 * i + 1]);
+      c[2] = wv * (double)(S.node_pos[3 * m + 2] - S.node_pos[3 * i + 2]);
+      c[3] = wv;
+    }
+  }
+  for (int e = tid; e < nloc * K; e += SM_THREADS) {
+    const int li = e / K, s = e - li * K, i = li * B + b;
+    const int q = S.nbr[i * K + s];
+    L.nbr[e] = S.node_free[q] ? q : (q | (int)0x80000000); L.o2i[e] = S.out_to_in[i * K + s];
+    L.be[e] = make_float4(S.node_pos[3 * q] - S.node_pos[3 * i], S.node_pos[3 * q + 1] - S.node_pos[3 * i + 1],
+                          S.node_pos[3 * q + 2] - S.node_pos[3 * i + 2], 1.0f);   // float differences (Deform.cpp:254-256)
+  }
+  for (int t = tid; t < NU; t += SM_THREADS) {
+    const int li = t / 12, qi = t - 12 * li, c = qi & 3, jj = qi >> 2;
+    const size_t go = (size_t)(li * B + b) * 12 + pub(qi);
+    const double xv = (c == jj) ? 1.0 : 0.0;
+    L.xs[t] = xv; L.hs[t] = 0.0; L.ps[t] = 0.0; L.rs[t] = 0.0; L.ms[t] = 0.0; L.ds[t] = 0.0;
+    S.x[go] = xv; PB.pb[0][go] = 0.0; PB.pb[1][go] = 0.0;   // S.x doubles as the published x + h
+  }
+  {  // constraint partial slots that belong to excluded anchors are never written: zero both buffers once
+    const int n_mem = S.n_groups > 0 ? S.grp_off[S.n_groups] : 0;
+    for (size_t t = (size_t)b * SM_THREADS + tid; t < (size_t)n_mem * MS; t += (size_t)B * SM_THREADS) { PB.pi[0][t] = 0.0; PB.pi[1][t] = 0.0; }
+    for (int g = tid; g < S.n_groups; g += SM_THREADS)   // multi-member groups of the solve (any order: sums are per group)
+      if (S.grp_off[g + 1] - S.grp_off[g] > 1) { const int at = atomicAdd(&s_cnt[0], 1); if (at < PIPE_NBIG) s_big_g[at] = g; }
+  }
+  __syncthreads();
+  if (tid == 32) {
+    int off = 0;
+    for (int li = 0; li < nloc; li++) { L.lcb[li] = off; off += L.ce[li] - L.cb[li]; }
+    s_cnt[1] = off;
+  }
+  // C_i = sum_s c c^T (row r per thread)
+  for (int t = tid; t < nloc * 4; t += SM_THREADS) {
+    const int li = t >> 2, r = t & 3;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    for (int s = 0; s < K; s++) {
+      const float4 bb = L.be[li * K + s];
+      const double br = r == 0 ? (double)bb.x : r == 1 ? (double)bb.y : r == 2 ? (double)bb.z : 1.0;
+      a0 = fma(br, (double)bb.x, a0); a1 = fma(br, (double)bb.y, a1); a2 = fma(br, (double)bb.z, a2); a3 += br;
+    }
+    st4(L.Cm + (size_t)t * 4, D4{a0, a1, a2, a3});
+  }
+  __syncthreads();
+  const int nbig = s_cnt[0];
+  L.nent = s_cnt[1];
+  const bool misfit = nbig > PIPE_NBIG || L.nent > ccap;
+  if (!misfit)
+    for (int li = tid; li < nloc; li += SM_THREADS)   // same thread that wrote these ccoef rows above
+      for (int t = L.cb[li]; t < L.ce[li]; t++) {
+        const int lt = L.lcb[li] + (t - L.cb[li]);
+        const int g = S.cin_grp[t], m = S.cin_member[t];
+        const int mb = S.grp_off[g], me = S.grp_off[g + 1];
+        int p = mb;
+        while (p < me - 1 && S.grp_member[p] != m) p++;
+#pragma unroll
+        for (int c = 0; c < 4; c++) L.cc[(size_t)lt * 4 + c] = S.ccoef[(size_t)t * 4 + c];
+        L.eslot[lt] = p * MS + S.cin_slot[t];
+        if (me - mb > 1) {
+          int bi = 0;
+          while (bi < nbig - 1 && s_big_g[bi] != g) bi++;
+          L.erd[lt] = bi; L.emeta[lt] = li | (int)0x80000000;
+        } else { L.erd[lt] = mb * MS; L.emeta[lt] = li; }
+      }
+  red[0] = misfit ? 1.0 : 0.0; red[1] = red[2] = 0.0;
+  barrier_reduce<1>(S, counter, phase, red);
+  if (red[0] > 0.0) {   // does not fit this kernel (the host-side eligibility check was skipped): identity transforms, flag bit 2
+    for (int t = tid; t < NU; t += SM_THREADS) {
+      const int li = t / 12, qi = t - 12 * li, jj = qi >> 2, c = qi & 3, i = li * B + b;
+      if (c < 3) S.rot_out[(size_t)i * 9 + jj + 3 * c] = (c == jj) ? 1.0 : 0.0; else S.trans_out[(size_t)i * 3 + jj] = 0.0;
+    }
+    if (b == 0 && tid == 0) { for (int t = 0; t < 32; t++) S.stats[t] = 0.0; S.stats[6] = 4.0; S.stats[12] = gridDim.x; if (S.warm) S.warm[0] = 0.0; }
+    return;
+  }
+
+  const int n_warm = S.warm ? min((int)S.warm[0], S.warm_systems) : 0;   // rewritten by block 0 at the very end
+  int gn_iters = 0, halvings = 0, total_cg = 0, flag = 0, pc = 0;
+  double energy = 0.0, normh = 0.0, last_rel = 0.0, abs_target = -1.0, E0 = 0.0;
+  bool have_f = false;
+  __shared__ double s_time[4], s_tsub[4];
+  __shared__ int s_cg_gn[8];
+  if (tid < 4) { s_time[tid] = 0.0; s_tsub[tid] = 0.0; }
+  if (tid < 8) s_cg_gn[tid] = 0;
+
+  for (int gn = 0; gn < S.max_gn; gn++) {
+    gn_iters = gn + 1;
+    if (!have_f) {
+      red[0] = rows_smem<K, 0>(S, L, L.xs, S.x, nullptr, 0.0);
+      barrier_reduce<1>(S, counter, phase, red);
+      E0 = red[0];
+    }
+    energy = E0;
+    // ---- gradient g = -J^T f, Jacobi preconditioner; the first published vector is D^-1 g, or the previous drag step's
+    // solution h' of this system when warm-starting (x0 = alpha h' with the exact line-search alpha = g.h' / h'.H h')
+    const bool warm = gn < n_warm;
+    double* warm_h = S.warm ? S.warm + 8 + (size_t)gn * S.M * 12 : nullptr;
+    double gg_l = 0.0, xx_l = 0.0;
+    for (int t = tid; t < NU; t += SM_THREADS) {
+      const int li = t / 12, qi = t - 12 * li, j = qi >> 2, c = qi & 3;
+      if (!L.fr[li]) continue;
+      const size_t ob = (size_t)li * 12;
+      const D4 A0 = ld4(L.xs + ob), A1 = ld4(L.xs + ob + 4), A2 = ld4(L.xs + ob + 8);
+      double f[6]; rot_res(A0, A1, A2, S.w_rot, f);
+      const D4 Aj = j == 0 ? A0 : j == 1 ? A1 : A2;
+      const double xv = c == 0 ? Aj.a : c == 1 ? Aj.b : c == 2 ? Aj.c : Aj.d;
+      const double g = -gather_smem<K>(S, L, li, j, c, Aj, f, xv);
+      const double di = 1.0 / diag_smem<K>(S, L, li, j, c, Aj);
+      const double m0 = warm ? warm_h[(size_t)(li * B + b) * 12 + qi] : g * di;
+      L.ds[t] = di; L.rs[t] = g; L.hs[t] = 0.0; L.ms[t] = m0;
+      gg_l = fma(g, g, gg_l); xx_l = fma(xv, xv, xx_l);
+    }
+    __syncthreads();   // L.us (row values of f) is dead from here: w, z, s take its place
+    publish_all<K>(L, PB.pb[pc & 1], PB.db[pc & 1], PB.pi[pc & 1]);
+    uro_pass(S, L);
+    red[0] = gg_l; red[1] = xx_l;
+    barrier_reduce<2>(S, counter, phase, red);
+    const double gg = red[0]; const double normv = sqrt(red[1]);
+    if (abs_target < 0.0) abs_target = S.cg_tol * S.cg_tol * gg;
+    const double target = fmax(abs_target, S.eta0 * S.eta0 * gg);   // see solve_smem.cu
+    const int cg_before = total_cg;
+
+    if (gg > 0.0) {
+      if (warm) {
+        double a_l = 0.0, b_l = 0.0;
+        apply_H<K>(S, L, PB.pb[pc & 1], PB.db[pc & 1], PB.pi[pc & 1], nbig, s_big_g, s_ubig,
+                   [&](int t4, int, int, const D4& y) {
+                     const D4 hv = ld4(L.ms + t4);
+                     st4(L.ws + t4, y);
+                     a_l += d4_dot(ld4(L.rs + t4), hv); b_l += d4_dot(hv, y);
+                   });
+        pc++;
+        red[0] = a_l; red[1] = b_l;
+        barrier_reduce<2>(S, counter, phase, red);
+        const double aw = red[1] > 0.0 ? red[0] / red[1] : 0.0;   // zero guess (after a pause): plain cold start
+        for (int rr = tid; rr < nloc * 4; rr += SM_THREADS) {
+          const int li = rr >> 2, j = rr & 3;
+          if (j == 3 || !L.fr[li]) continue;
+          const int t4 = li * 12 + 4 * j;
+          const D4 rv = d4_axpy(-aw, ld4(L.ws + t4), ld4(L.rs + t4));
+          const D4 hv = ld4(L.ms + t4);
+          st4(L.hs + t4, D4{aw * hv.a, aw * hv.b, aw * hv.c, aw * hv.d});
+          st4(L.rs + t4, rv);
+          publish_row<K>(L, li, j, d4_mul(rv, ld4(L.ds + t4)), PB.pb[pc & 1], PB.db[pc & 1], PB.pi[pc & 1]);
+        }
+        __syncthreads();
+        uro_pass(S, L);
+        red[0] = 0.0;
+        barrier_reduce<1>(S, counter, phase, red);
+        total_cg++;
+      }
+      // w0 = H u0, first dots, m0 = D^-1 w0
+      double gam_l = 0.0, del_l = 0.0, rr_l = 0.0;
+      apply_H<K>(S, L, PB.pb[pc & 1], PB.db[pc & 1], PB.pi[pc & 1], nbig, s_big_g, s_ubig,
+                 [&](int t4, int li, int j, const D4& y) {
+                   const D4 di = ld4(L.ds + t4), rv = ld4(L.rs + t4);
+                   const D4 uv = d4_mul(rv, di);
+                   const D4 zero{0.0, 0.0, 0.0, 0.0};
+                   st4(L.ws + t4, y); st4(L.zs + t4, zero); st4(L.ss + t4, zero); st4(L.ps + t4, zero);
+                   gam_l += d4_dot(rv, uv); del_l += d4_dot(y, uv); rr_l += d4_dot(rv, rv);
+                   publish_row<K>(L, li, j, d4_mul(y, di), PB.pb[(pc + 1) & 1], PB.db[(pc + 1) & 1], PB.pi[(pc + 1) & 1]);
+                 });
+      pc++;
+      __syncthreads();
+      uro_pass(S, L);
+      red[0] = gam_l; red[1] = del_l; red[2] = rr_l;
+      barrier_reduce<3>(S, counter, phase, red);
+      total_cg++;
+      double gam_old = 1.0, alpha_old = 1.0;
+      for (int it = 0; it < S.max_cg; it++) {
+        const double gam = red[0], del = red[1], rr = red[2];
+        last_rel = sqrt(rr / gg);
+        if (!(rr == rr)) { flag |= 1; break; }
+        if (rr <= target || rr <= 1e-30 * gg) break;
+        const double beta = it ? gam / gam_old : 0.0;
+        const double den = it ? del - beta * gam / alpha_old : del;
+        if (!(den > 0.0)) { flag |= 1; break; }
+        const double alpha = gam / den;
+        const unsigned long long t0 = gtime2();
+        gam_l = 0.0; del_l = 0.0; rr_l = 0.0;
+        apply_H<K>(S, L, PB.pb[pc & 1], PB.db[pc & 1], PB.pi[pc & 1], nbig, s_big_g, s_ubig,
+                   [&](int t4, int li, int j, const D4& y) {
+                     const D4 di = ld4(L.ds + t4), wo = ld4(L.ws + t4), ro = ld4(L.rs + t4);
+                     const D4 zv = d4_axpy(beta, ld4(L.zs + t4), y);
+                     const D4 sv = d4_axpy(beta, ld4(L.ss + t4), wo);
+                     const D4 pv = d4_axpy(beta, ld4(L.ps + t4), d4_mul(ro, di));
+                     st4(L.zs + t4, zv); st4(L.ss + t4, sv); st4(L.ps + t4, pv);
+                     st4(L.hs + t4, d4_axpy(alpha, pv, ld4(L.hs + t4)));
+                     const D4 rv = d4_axpy(-alpha, sv, ro), wv = d4_axpy(-alpha, zv, wo);
+                     st4(L.rs + t4, rv); st4(L.ws + t4, wv);
+                     const D4 uv = d4_mul(rv, di);
+                     gam_l += d4_dot(rv, uv); del_l += d4_dot(wv, uv); rr_l += d4_dot(rv, rv);
+                     publish_row<K>(L, li, j, d4_mul(wv, di), PB.pb[(pc + 1) & 1], PB.db[(pc + 1) & 1], PB.pi[(pc + 1) & 1]);
+                   }, s_tsub);
+        pc++;
+        const unsigned long long t1 = gtime2();
+        __syncthreads();
+        uro_pass(S, L);
+        red[0] = gam_l; red[1] = del_l; red[2] = rr_l;
+        const unsigned long long t2 = gtime2();
+        barrier_reduce<3>(S, counter, phase, red);
+        const unsigned long long t3 = gtime2();
+        if (tid == 0) { s_time[0] += (double)(t1 - t0); s_time[1] += (double)(t2 - t1); s_time[2] += (double)(t3 - t2); }
+        total_cg++;
+        gam_old = gam; alpha_old = alpha;
+        if (it == S.max_cg - 1) flag |= 2;
+      }
+    }
+    if (flag & 1) {   // numeric breakdown (uniform over the grid): zero step, see solve_smem.cu
+      for (int t = tid; t < NU; t += SM_THREADS) L.hs[t] = 0.0;
+      __syncthreads();
+    }
+    if (S.warm && gn < SOLVE_WARM_MAX)   // this system's solution (before step halving) seeds the next drag step
+      for (int t = tid; t < NU; t += SM_THREADS) warm_h[(size_t)((t / 12) * B + b) * 12 + (t % 12)] = L.hs[t];
+
+    // ---- step halving (Deform.cpp:144-156): publish x + h, evaluate, accept or halve.  L.ps holds x + h (p is dead).
+    bool accepted = false;
+    for (double alpha_ls = 1.0; alpha_ls > 1e-15; alpha_ls *= 0.5) {
+      double hh_l = 0.0;
+      for (int t = tid; t < NU; t += SM_THREADS) {
+        const double hv = L.hs[t];
+        hh_l = fma(hv, hv, hh_l);
+        const double xv = L.xs[t] + hv;
+        L.ps[t] = xv;
+        S.x[(size_t)((t / 12) * B + b) * 12 + pub(t % 12)] = xv;
+      }
+      red[0] = hh_l;
+      barrier_reduce<1>(S, counter, phase, red);
+      const double hh = red[0];
+      red[0] = rows_smem<K, 0>(S, L, L.ps, S.x, nullptr, 0.0);
+      barrier_reduce<1>(S, counter, phase, red);
+      const double E1 = red[0];
+      if (!(E1 <= E0)) {   // also rejects a non-finite energy
+        for (int t = tid; t < NU; t += SM_THREADS) L.hs[t] *= 0.5;
+        halvings++;
+        normh = 0.5 * sqrt(hh);
+        __syncthreads();
+      } else {
+        for (int t = tid; t < NU; t += SM_THREADS) L.xs[t] = L.ps[t];
+        normh = sqrt(hh);
+        E0 = E1; have_f = true; accepted = true;
+        __syncthreads();
+        break;
+      }
+    }
+    if (!accepted) {
+      for (int t = tid; t < NU; t += SM_THREADS) S.x[(size_t)((t / 12) * B + b) * 12 + pub(t % 12)] = L.xs[t];
+      red[0] = 0.0;
+      barrier_reduce<1>(S, counter, phase, red);
+      have_f = false;
+    }
+    if (gn < 8 && tid == 0) s_cg_gn[gn] = total_cg - cg_before;
+    if (normh < (normv + 1e-6) * 1e-6) break;
+  }
+
+  // putFreeInputs (Deform.hpp:140-151)
+  for (int t = tid; t < NU; t += SM_THREADS) {
+    const int li = t / 12, qi = t - 12 * li, jj = qi >> 2, c = qi & 3, i = li * B + b;
+    const double v = L.xs[t];
+    if (c < 3) S.rot_out[(size_t)i * 9 + jj + 3 * c] = v; else S.trans_out[(size_t)i * 3 + jj] = v;
+  }
+  if (b == 0 && tid == 0) {
+    if (S.warm) S.warm[0] = (flag & 1) ? 0.0 : (double)min(gn_iters, SOLVE_WARM_MAX);
+    S.stats[0] = gn_iters; S.stats[1] = energy; S.stats[2] = halvings; S.stats[3] = normh;
+    S.stats[4] = total_cg; S.stats[5] = last_rel; S.stats[6] = flag;
+    // phase timers of block 0 (summed over PCG iterations): stencil + recurrences, partial publication, barrier
+    S.stats[8] = s_time[0]; S.stats[9] = s_time[1]; S.stats[10] = s_time[2]; S.stats[11] = 0.0; S.stats[12] = gridDim.x;
+    for (int t = 0; t < 8; t++) S.stats[16 + t] = s_cg_gn[t];
+    for (int t = 0; t < 6; t++) S.stats[24 + t] = 0.0;
+    // stencil phase split (thread 0 of block 0): gathers issued + group sums, CTA sync, first row's stencil, recurrences + publication
+    S.stats[13] = s_tsub[0]; S.stats[14] = s_tsub[1]; S.stats[15] = s_tsub[2]; S.stats[7] = s_tsub[3];
+  }
+}
+
+static size_t solve_pipe_bytes(int NL, int K, int ccap) {
+  const size_t un = std::max((size_t)3 * NL * 12, (size_t)NL * K * 3);
+  size_t d = (size_t)NL * 12 * 6 + un + (size_t)NL * 6 + (size_t)NL * 16 + (size_t)ccap * 7;
+  if (d & 1) d += 1;
+  return d * 8 + (size_t)NL * K * 16 + (size_t)NL * K * 8 + (size_t)NL * 7 * 4 + (size_t)ccap * 12 + 32;
+}
+
+int solve_pipe_grid(int M, int max_ctas) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  int grid = std::max(1, std::min(sms, (M + 23) / 24));   // small graphs: fewer CTAs make the barriers cheaper
+  if (max_ctas > 0) grid = std::min(grid, max_ctas);
+  if (const char* ev = getenv("ARAP_SOLVE_GRID")) grid = std::max(1, std::min(sms, atoi(ev)));   // measurement aid
+  return grid;
+}
+int solve_pipe_ccap(int NL, int K) {
+  if (K != 8 && K != 10 && K != 12) return -1;
+  if (NL <= 112) return K <= 10 ? PipeCaps<10, 112>::C : PipeCaps<12, 112>::C;
+  if (NL <= 136) return K <= 10 ? PipeCaps<10, 136>::C : PipeCaps<12, 136>::C;
+  return -1;
+}
+
+// returns ARAP_OK if launched, -1 if the slice does not fit (the caller runs the two-barrier kernel)
+int launch_solve_pipe(const SolveDev& S, unsigned* counter, double* extra, cudaStream_t st, int max_ctas) {
+  if (S.k != 8 && S.k != 10 && S.k != 12) return -1;
+  const int grid = solve_pipe_grid(S.M, max_ctas);
+  if (grid < 1) return -1;
+  int dev = 0, max_smem = 0;
+  ARAP_CUDA_TRY(cudaGetDevice(&dev));
+  ARAP_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const int NL = (S.M + grid - 1) / grid;
+  void* kern = nullptr; size_t smem = 0;
+  auto pick = [&](auto kc) {
+    constexpr int KK = decltype(kc)::value;
+    if (NL <= 112) { kern = (void*)k_solve_pipe<KK, 112>; smem = solve_pipe_bytes(112, KK, PipeCaps<KK, 112>::C); }
+    else if (NL <= 136) { kern = (void*)k_solve_pipe<KK, 136>; smem = solve_pipe_bytes(136, KK, PipeCaps<KK, 136>::C); }
+  };
+  if (S.k == 8) pick(std::integral_constant<int, 8>{});
+  else if (S.k == 10) pick(std::integral_constant<int, 10>{});
+  else pick(std::integral_constant<int, 12>{});
+  if (!kern) return -1;
+  cudaFuncAttributes fa;
+  ARAP_CUDA_TRY(cudaFuncGetAttributes(&fa, (const void*)kern));
+  if (smem + fa.sharedSizeBytes > (size_t)max_smem) return -1;
+  ARAP_CUDA_TRY(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  ARAP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kern, SM_THREADS, smem));
+  if (per_sm < 1) return -1;
+  ARAP_CUDA_TRY(cudaMemsetAsync(counter, 0, (size_t)2 * (grid + 1) * LL_WORDS * sizeof(unsigned long long), st));
+  // extra workspace: second in-edge partial buffer, two constraint-partial buffers
+  PipeBuf PB;
+  const size_t nin = (size_t)S.M * S.k * 3;
+  PB.pb[0] = S.p0; PB.pb[1] = S.p1;
+  PB.db[0] = extra; PB.db[1] = extra + nin;
+  double* pi = extra + 2 * nin;
+  pi += (16 - ((reinterpret_cast<uintptr_t>(pi) >> 3) & 15)) & 15;   // 128-byte aligned member blocks
+  const size_t npi = (size_t)(S.n_groups + 1) * 20 * 48;
+  PB.pi[0] = pi; PB.pi[1] = pi + npi;
+  SolveDev Sc = S; unsigned* cnt = counter;
+  void* args[] = {(void*)&Sc, (void*)&cnt, (void*)&PB};
+  ARAP_CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(SM_THREADS), args, smem, st));
+  return ARAP_OK;
+}
+
+size_t solve_pipe_extra_doubles(int M, int k, int n_groups) {
+  return (size_t)M * k * 3 * 2 + 16 + (size_t)(n_groups + 1) * 20 * 48 * 2;
+}
+
+}  // namespace arapgs
+
+using namespace arapgs;
+
+// Host-side eligibility of the one-barrier kernel for a constraint set (host copies of the group and column-entry offsets):
+// the slice of every CTA must fit the shared-memory entry table and there may be at most PIPE_NBIG multi-member groups,
+// each with at most 20 members (the workspace bound).
+extern "C" int arapk_solve_pipe_eligible(int M, int k, int n_groups, const int* grp_off_host, const int* cin_off_host, int max_ctas) {
+  const int grid = solve_pipe_grid(M, max_ctas);
+  if (grid < 1) return 0;
+  const int NL = (M + grid - 1) / grid;
+  const int ccap = solve_pipe_ccap(NL, k);
+  if (ccap < 0) return 0;
+  int nbig = 0;
+  for (int g = 0; g < n_groups; g++) {
+    const int n = grp_off_host[g + 1] - grp_off_host[g];
+    if (n > 20) return 0;
+    if (n > 1) nbig++;
+  }
+  if (nbig > PIPE_NBIG) return 0;
+  std::vector<long long> per((size_t)grid, 0);
+  for (int i = 0; i < M; i++) per[(size_t)(i % grid)] += cin_off_host[i + 1] - cin_off_host[i];
+  for (long long v : per) if (v > ccap) return 0;
+  return 1;
+}

@@ -394,6 +394,9 @@ def run_own(args):
                       "note": "lbs_mode = 3: end-point skinning is fused into six_point_fit (k_apply_union); endpoint_lbs is then the node / mesh-point pass only" if lbs_mode == 3 else ""},
         "stages_ms_lbs_mode0": dict(zip(("solve", "sample_advect", "endpoint_lbs", "six_point_fit", "sample_sh_rotate", "total"), stages_mode0)),
         "solve": {"gn_iters": st["gn_iters"], "cg_iters": st["cg_iters"], "flags": st["flags"], "grid_blocks": st["grid_blocks"],
+                  "kernel": ("k_solve_pipe: pipelined PCG on the explicit J^T J stencil, one grid barrier per iteration; phases = [stencil + recurrences + publication, CTA sync + E_rot rows, barrier, -], "
+                             "split = [group sums + gathers issued, CTA sync, first row's stencil, recurrences + publication]") if s.params.solver_pipelined and st["phase_ns"][3] == 0
+                            else "k_solve_smem: matrix-free PCG, two grid barriers per iteration; phases = [row phase, barrier, gather phase, barrier], split = row phase [form p, E_reg, E_rot, constraints]",
                   "phase_us_per_cg_iter": [round(x / 1e3 / max(st["cg_iters"], 1), 2) for x in st["phase_ns"]],
                   "row_phase_split_us": [round(x / 1e3 / max(st["cg_iters"], 1), 2) for x in st["row_sub_ns"]],
                   "cg_iters_gn": st["cg_iters_gn"][:st["gn_iters"]],

@@ -86,19 +86,25 @@ typedef struct arap_params {
                           arap_sample_features_materialize.  Same result up to float rounding (SH rotation composes exactly). */
   int fps_mode;        /* node sampling (HC:139-195): 0 (default) = selection loop pruned by the density grid, 1 = one pass over all
                           candidate points per node (first version).  Same node sequence, bit for bit. */
+  int solver_pipelined; /* 1 (default): the linear systems of the Gauss-Newton solve run as pipelined PCG on the explicit J^T J stencil with
+                          ONE grid barrier per iteration (csrc/solve_pipe.cu) whenever the constraint set fits that kernel (checked at
+                          arap_set_blocks); 0 = the two-barrier matrix-free PCG (csrc/solve_smem.cu).  Same preconditioner, same stopping
+                          rules, iterates equal to rounding. */
 } arap_params;
 
 typedef struct arap_solve_stats {
   int gn_iters;        /* Gauss-Newton iterations taken */
-  int cg_iters;        /* total PCG iterations */
+  int cg_iters;        /* total PCG iterations (one-barrier kernel: products with J^T J, i.e. iterations + 1-2 set-up products per system) */
   int halvings;        /* step-halving count */
-  int flags;           /* bit0: numeric breakdown, bit1: PCG hit the iteration cap */
+  int flags;           /* bit0: numeric breakdown, bit1: PCG hit the iteration cap, bit2: constraint set does not fit the selected solver kernel (identity transforms returned) */
   double energy;       /* f.f at the last linearisation point (Deform::optimize return) */
   double normh;        /* |h| of the last accepted step */
   double last_rel_residual;
-  double phase_ns[4];  /* block 0's time in: row phase, barrier 1, gather/update phase, barrier 2 (summed over PCG iterations) */
+  double phase_ns[4];  /* block 0's time (summed over PCG iterations) in: row phase, barrier 1, gather/update phase, barrier 2 (two-barrier kernel);
+                          stencil + recurrences + publication, CTA sync + E_rot rows, barrier, 0 (one-barrier kernel, solver_pipelined) */
   int grid_blocks;     /* cooperative grid size used */
-  double row_sub_ns[4]; /* row phase split: form p, E_reg rows, E_rot rows, constraint rows (shared-memory kernel only) */
+  double row_sub_ns[4]; /* row phase split: form p, E_reg rows, E_rot rows, constraint rows (two-barrier shared-memory kernel); one-barrier kernel:
+                           group sums + gathers issued, CTA sync, first row's stencil, recurrences + publication */
   int cg_iters_gn[8];  /* PCG iterations of the first 8 Gauss-Newton iterations */
   double barrier_skew_ns[6]; /* diagnostics sampled at PCG iteration 50 of each Gauss-Newton iteration (summed), block 0: time from the
                                 start of the row phase until its LAST warp has finished E_reg rows, E_rot rows, constraint gathers,

@@ -122,7 +122,12 @@ typedef struct ArapSolveParams {
                                // null = every PCG solve starts from 0.  See arapgs.h (arap_params.warm_start).
   int max_ctas;                // 0 = one CTA per SM; n > 0 = at most n CTAs (shared-memory kernel)
   int warm_systems;            // 0 = all (SOLVE_WARM_MAX), n > 0 = only the first n Gauss-Newton systems of a step
+  int pipelined;               // 1 = one-barrier pipelined PCG kernel (csrc/solve_pipe.cu) when the slice fits it; the caller must have
+                               // checked arapk_solve_pipe_eligible() for this constraint set (the kernel re-checks: stats flag bit 2)
 } ArapSolveParams;
+
+/* host-side check for ArapSolveParams.pipelined: host copies of grp_off (n_groups + 1) and cin_off (M + 1) */
+int arapk_solve_pipe_eligible(int M, int k, int n_groups, const int* grp_off_host, const int* cin_off_host, int max_ctas);
 
 size_t arapk_solve_warm_doubles(int M);
 

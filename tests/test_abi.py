@@ -36,7 +36,7 @@ def test_struct_layouts_match_header(pkg):
     assert (p.grid_num, p.padding, p.knn_k, p.node_num) == (64, 1, 10, 150)
     assert (p.w_rot, p.w_reg, p.w_con, p.max_gn_iters) == (1.0, 10.0, 100.0, 30)
     assert abs(p.lpf_parameter - 0.2) < 1e-7
-    assert ctypes.sizeof(pkg.Params) == 104 and p.lazy_sample_sh == 0 and p.fps_mode == 0 and p.warm_start == 1 and p.lbs_mode == 0 and p.solver_ctas == 0 and ctypes.sizeof(pkg.SolveStats) == 192
+    assert ctypes.sizeof(pkg.Params) == 112 and p.solver_pipelined == 1 and p.lazy_sample_sh == 0 and p.fps_mode == 0 and p.warm_start == 1 and p.lbs_mode == 0 and p.solver_ctas == 0 and ctypes.sizeof(pkg.SolveStats) == 192
 
 
 def test_no_cpu_fallback(pkg):

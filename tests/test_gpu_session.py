@@ -205,6 +205,44 @@ def test_solver_on_fewer_ctas_agrees(pkg, scenes):
             assert np.abs(r0 - r1).max() <= 2e-9 and np.abs(t0 - t1).max() <= 2e-9
 
 
+def test_pipelined_solver_matches_the_two_barrier_kernel(pkg, scenes):
+    """arap_params.solver_pipelined (csrc/solve_pipe.cu): pipelined PCG on the explicit J^T J stencil, one grid barrier per
+    iteration, against the matrix-free two-barrier PCG (solve_smem.cu) — per-node constraints and constraints on block centres
+    (multi-member groups), cold and warm-started steps, an excluded block.  Same Gauss-Newton iteration counts, transforms
+    equal to the solver tolerance; iteration counts of the linear solves within a few per cent."""
+    sc = scenes.make_scene("sphere1m", n=60000)
+    for on_center, ctas in ((False, 0), (True, 0), (False, 24)):
+        res = []
+        for pipe in (1, 0):
+            s = pkg.Session(device=0, grid_num=32, knn_k=10, node_num=3000)
+            s.set_params(solver_pipelined=pipe, solver_ctas=ctas)
+            s.set_gaussians(sc["pos"], sc["rot"], sc["scale"], sc["opacity"], sc["shs"])
+            s.grid_build()
+            g = s.graph_build_fps()
+            npz = g["node_pos"]
+            blocks = [np.nonzero(npz[:, 2] > 0.3)[0].astype(np.uint32), np.nonzero(npz[:, 2] < -0.3)[0].astype(np.uint32),
+                      np.nonzero((npz[:, 0] > 0.4) & (np.abs(npz[:, 2]) < 0.2))[0].astype(np.uint32),
+                      np.nonzero((npz[:, 0] < -0.45) & (np.abs(npz[:, 2]) < 0.1))[0].astype(np.uint32)]
+            types = [1, 0, 0, -1]
+            s.set_blocks(blocks, types)
+            out = []
+            for step in range(4):
+                if step < 3: s.aim_translate([0.002, 0.0, 0.01])
+                else: s.aim_twist([0.1, 0.2, 1.0, 0.0], 25)
+                s.solve(on_center)
+                st = s.solve_stats()
+                assert st["flags"] == 0, st
+                out.append((st["gn_iters"], st["cg_iters"], s.download_nodes()[1:]))
+                s.apply()
+            res.append(out)
+            s.close()
+        for (gn1, cg1, (r1, t1)), (gn0, cg0, (r0, t0)) in zip(*res):
+            assert gn1 == gn0, (on_center, gn1, gn0)
+            assert abs(cg1 - cg0) <= 0.1 * cg0 + 12, (on_center, cg1, cg0)     # + the extra products of the warm start / set-up
+            assert np.abs(r0 - r1).max() <= 2e-9 and np.abs(t0 - t1).max() <= 2e-9, (on_center, np.abs(r0 - r1).max(), np.abs(t0 - t1).max())
+        print(f"on_center={on_center} ctas={ctas}: PCG iterations pipelined {[o[1] for o in res[0]]} two-barrier {[o[1] for o in res[1]]}")
+
+
 def test_twist_scale_and_excluded_blocks(pkg, scenes):
     sc, s, o, gi, og = _pair(pkg, scenes, n=20000, grid_num=32, knn_k=10, node_num=120)
     g = s.graph_build_fps(); o.graph_build_fps()
