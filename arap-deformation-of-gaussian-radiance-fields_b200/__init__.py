@@ -475,6 +475,16 @@ class Session:
     def comm_exchange(self):
         check(lib().arap_comm_exchange(self._ctx))
 
+    def comm_grid_build(self, x_lo=-1, x_hi=-1):
+        """One scene sharded over the ranks: grid over everybody's Gaussians, this rank's x-slab of cells (arap_comm_grid_build)."""
+        check(lib().arap_comm_grid_build(self._ctx, int(x_lo), int(x_hi)))
+        return self.grid_info()
+
+    def comm_slab(self):
+        lo, hi = C.c_int(), C.c_int()
+        check(lib().arap_comm_slab_get(self._ctx, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
     def comm_materialize_sh(self):
         check(lib().arap_comm_materialize_sh(self._ctx))
 

@@ -260,15 +260,17 @@ __device__ __forceinline__ void cell_range(const float* a, float3 mn, float step
   }
 }
 
+// [xlo, xhi): the x-slab of cells this launch bins into (the whole grid: 0, G) — multi-GPU grid sharding, SURVEY 8(e)
 template <bool FILL>
 __global__ void k_footprint(long long N, const float* __restrict__ aabb, float3 mn, float step, int G, int padding,
-                            int* __restrict__ cnt_or_fill, const int* __restrict__ prefix, int* __restrict__ lists) {
+                            int* __restrict__ cnt_or_fill, const int* __restrict__ prefix, int* __restrict__ lists, int xlo, int xhi) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= N) return;
   float a[6];
 #pragma unroll
   for (int c = 0; c < 6; c++) a[c] = aabb[6 * g + c];
   int lo[3], hi[3]; cell_range(a, mn, step, G, padding, lo, hi);
+  lo[0] = max(lo[0], xlo); hi[0] = min(hi[0], xhi - 1);
   for (int x = lo[0]; x <= hi[0]; x++) for (int y = lo[1]; y <= hi[1]; y++) for (int z = lo[2]; z <= hi[2]; z++) {
     const int c = x * G * G + y * G + z;
     if (FILL) {
@@ -276,6 +278,20 @@ __global__ void k_footprint(long long N, const float* __restrict__ aabb, float3 
       lists[start + atomicAdd(&cnt_or_fill[c], 1)] = (int)g;
     } else atomicAdd(&cnt_or_fill[c], 1);
   }
+}
+
+// Gaussians per x-layer of cells (balanced slab cuts for the multi-GPU grid): same cell expression as k_cell_hist
+__global__ void k_xlayer_hist(long long N, const float* __restrict__ pos, float mnx, float step, int G, int* __restrict__ hist) {
+  __shared__ int s_h[256];
+  for (int t = threadIdx.x; t < 256; t += blockDim.x) s_h[t] = 0;
+  __syncthreads();
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < N; g += (long long)gridDim.x * blockDim.x) {
+    int x = (int)floorf((pos[3 * g] - mnx) / step);
+    x = min(max(x, 0), G - 1);
+    atomicAdd(&s_h[x], 1);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < G; t += blockDim.x) if (s_h[t]) atomicAdd(&hist[t], s_h[t]);
 }
 
 // ------------------------------------------------------------------ valid cells + samples
@@ -573,12 +589,17 @@ extern "C" int arapk_gs_aabbs(long long N, const float* pos, const float* rot, c
 
 extern "C" int arapk_footprint_count(long long N, const float* aabb, const float* min3, float step, int G, int padding,
                                      int* prefix_out, long long* total_host, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+  return arapk_footprint_count_slab(N, aabb, min3, step, G, padding, 0, G, prefix_out, total_host, scratch, scratch_bytes, st);
+}
+extern "C" int arapk_footprint_count_slab(long long N, const float* aabb, const float* min3, float step, int G, int padding, int xlo, int xhi,
+                                          int* prefix_out, long long* total_host, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+  if (xlo < 0 || xhi > G || xlo > xhi) { set_error("footprint_count: bad slab"); return ARAP_ERR_INVALID; }
   if (scratch_bytes < arapk_grid_scratch_bytes(0, G)) { set_error("footprint_count: scratch too small"); return ARAP_ERR_INVALID; }
   const long long gc = (long long)G * G * G;
   GridScratch s = carve(scratch, G, N);
   ARAP_CUDA_TRY(cudaMemsetAsync(s.cnt, 0, sizeof(int) * gc, st));
   const float3 mn = make_float3(min3[0], min3[1], min3[2]);
-  if (N > 0) { k_footprint<false><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, aabb, mn, step, G, padding, s.cnt, nullptr, nullptr); ARAP_KERNEL_CHECK(); }
+  if (N > 0) { k_footprint<false><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, aabb, mn, step, G, padding, s.cnt, nullptr, nullptr, xlo, xhi); ARAP_KERNEL_CHECK(); }
   int rc = scan_inclusive(s.cnt, prefix_out, gc, s.sums, st); if (rc) return rc;
   if (total_host) {
     int last = 0;
@@ -591,13 +612,25 @@ extern "C" int arapk_footprint_count(long long N, const float* aabb, const float
 
 extern "C" int arapk_footprint_fill(long long N, const float* aabb, const float* min3, float step, int G, int padding,
                                     const int* prefix, int* lists_out, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+  return arapk_footprint_fill_slab(N, aabb, min3, step, G, padding, 0, G, prefix, lists_out, scratch, scratch_bytes, st);
+}
+extern "C" int arapk_footprint_fill_slab(long long N, const float* aabb, const float* min3, float step, int G, int padding, int xlo, int xhi,
+                                         const int* prefix, int* lists_out, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+  if (xlo < 0 || xhi > G || xlo > xhi) { set_error("footprint_fill: bad slab"); return ARAP_ERR_INVALID; }
   if (scratch_bytes < arapk_grid_scratch_bytes(0, G)) { set_error("footprint_fill: scratch too small"); return ARAP_ERR_INVALID; }
   const long long gc = (long long)G * G * G;
   GridScratch s = carve(scratch, G, N);
   ARAP_CUDA_TRY(cudaMemsetAsync(s.fill, 0, sizeof(int) * gc, st));
   const float3 mn = make_float3(min3[0], min3[1], min3[2]);
-  if (N > 0) { k_footprint<true><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, aabb, mn, step, G, padding, s.fill, prefix, lists_out); ARAP_KERNEL_CHECK(); }
+  if (N > 0) { k_footprint<true><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, aabb, mn, step, G, padding, s.fill, prefix, lists_out, xlo, xhi); ARAP_KERNEL_CHECK(); }
   return sort_segments(gc, prefix, lists_out, s.big, st);
+}
+
+extern "C" int arapk_xlayer_hist(const float* pos, long long N, const float* min3, float step, int G, int* hist_dev, cudaStream_t st) {
+  if (G < 1 || G > 256) { set_error("xlayer_hist: grid_num out of range"); return ARAP_ERR_INVALID; }
+  ARAP_CUDA_TRY(cudaMemsetAsync(hist_dev, 0, sizeof(int) * G, st));
+  if (N > 0) { k_xlayer_hist<<<(unsigned)std::min<long long>((N + 255) / 256, 148 * 8), 256, 0, st>>>(N, pos, min3[0], step, G, hist_dev); ARAP_KERNEL_CHECK(); }
+  return ARAP_OK;
 }
 
 extern "C" int arapk_valid_cells(const int* prefix, int G, int* valid_out, int* count_host, void* scratch, size_t scratch_bytes,

@@ -196,8 +196,11 @@ struct arap_ctx {
   struct Comm {
     void* nccl = nullptr;            // ncclComm_t
     int rank = 0, world = 1;
-    DBuf<float> pos_all, rot_all, scale_all, shs_all, rot_base;
+    DBuf<float> pos_all, rot_all, scale_all, shs_all, rot_base, opacity_all;
     cudaStream_t side = nullptr; cudaEvent_t ev_done = nullptr;
+    // one scene sharded over the ranks (arap_comm_grid_build): the grid stages read ALL Gaussians (the gathered arrays) and
+    // bin / evaluate only the x-slab [slab_lo, slab_hi) of cells
+    bool slab = false; int slab_lo = 0, slab_hi = 0;
   } comm;
   // timing
   // timing: a ring of per-step event sets so a whole timed region can be read back afterwards
@@ -335,9 +338,20 @@ extern "C" int arap_get_device_view(arap_ctx* ctx, arap_device_view* o) {
 // ------------------------------------------------------------------ grid
 // getOverallAABB (GV:3601-3631): min/max on device, the box arithmetic in host float
 // (Eigen float vectors x double literals evaluate in float).
+// The Gaussians the grid stages read: the session's own, or — one scene sharded over the ranks — everybody's (gathered arrays)
+struct GridSrc { const float *pos, *rot, *scale, *opacity, *shs; long long N; int xlo, xhi; };
+static GridSrc grid_src(arap_ctx* c) {
+  if (c->comm.slab) {
+    const arap_ctx::Comm& cm = c->comm;
+    return GridSrc{cm.pos_all.p, cm.rot_all.p, cm.scale_all.p, cm.opacity_all.p, cm.shs_all.p, (long long)cm.world * c->N, cm.slab_lo, cm.slab_hi};
+  }
+  return GridSrc{c->pos.p, c->rot.p, c->scale.p, c->opacity.p, c->shs.p, c->N, 0, c->G};
+}
+
 static int overall_aabb(arap_ctx* c) {
   DBuf<float> mm; TRY(mm.alloc(8));
-  TRY(arapk_minmax(c->pos.p, c->N, mm.p, c->stream));
+  const GridSrc gs = grid_src(c);
+  TRY(arapk_minmax(gs.pos, gs.N, mm.p, c->stream));
   float h[6];
   ARAP_CUDA_TRY(cudaMemcpyAsync(h, mm.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   ARAP_CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -362,22 +376,25 @@ static int overall_aabb(arap_ctx* c) {
 static int build_lists(arap_ctx* c) {  // boxes -> count -> fill (GV:3961-4100 / 3634-3743)
   cudaStream_t st = c->stream;
   StageTimer tmr(c, ARAP_ST_FOOTPRINT_LISTS);
-  TRY(c->gs_aabb.alloc((size_t)c->N * 6));
-  TRY(arapk_gs_aabbs(c->N, c->pos.p, c->rot.p, c->scale.p, c->opacity.p, c->gs_aabb.p, nullptr, nullptr, st));
+  const GridSrc gs = grid_src(c);
+  TRY(c->gs_aabb.alloc((size_t)gs.N * 6));
+  TRY(arapk_gs_aabbs(gs.N, gs.pos, gs.rot, gs.scale, gs.opacity, c->gs_aabb.p, nullptr, nullptr, st));
   const size_t gc = (size_t)c->G * c->G * c->G;
   TRY(c->fp_prefix.alloc(gc));
   long long P = 0;
-  TRY(arapk_footprint_count(c->N, c->gs_aabb.p, c->aabb, c->step, c->G, c->prm.padding, c->fp_prefix.p, &P, c->grid_scratch.p, c->grid_scratch.n, st));
+  TRY(arapk_footprint_count_slab(gs.N, c->gs_aabb.p, c->aabb, c->step, c->G, c->prm.padding, gs.xlo, gs.xhi, c->fp_prefix.p, &P, c->grid_scratch.p, c->grid_scratch.n, st));
   c->P = P;
   // 12 % head-room: a stroke-end rebuild after a deformation usually has a few per cent more pairs, and re-allocating 1.5 GB costs ~10 ms
   if ((size_t)std::max<long long>(P, 1) > c->lists.n) TRY(c->lists.alloc((size_t)(std::max<long long>(P, 1) * 1.12) + 1024));
-  TRY(arapk_footprint_fill(c->N, c->gs_aabb.p, c->aabb, c->step, c->G, c->prm.padding, c->fp_prefix.p, c->lists.p, c->grid_scratch.p, c->grid_scratch.n, st));
+  TRY(arapk_footprint_fill_slab(gs.N, c->gs_aabb.p, c->aabb, c->step, c->G, c->prm.padding, gs.xlo, gs.xhi, c->fp_prefix.p, c->lists.p, c->grid_scratch.p, c->grid_scratch.n, st));
   return ARAP_OK;
 }
 
+static int grid_finish(arap_ctx* ctx);
 extern "C" int arap_grid_build(arap_ctx* ctx) {
   CTX_CHECK(ctx);
   if (ctx->N <= 0) { set_error("grid_build: no Gaussians"); return ARAP_ERR_STATE; }
+  if (ctx->comm.slab) { set_error("grid_build: this session holds a shard of a multi-GPU scene (arap_comm_grid_build)"); return ARAP_ERR_STATE; }
   cudaStream_t st = ctx->stream;
   ctx->G = ctx->prm.grid_num;
   if (ctx->G < 1 || ctx->G > 256) { set_error("grid_build: grid_num out of range"); return ARAP_ERR_INVALID; }
@@ -411,6 +428,13 @@ extern "C" int arap_grid_build(arap_ctx* ctx) {
     TRY(arapk_cell_assign(ctx->pos.p, ctx->N, ctx->aabb, ctx->step, ctx->G, ctx->gs_init_grid_idx.p, ctx->cell_prefix.p, nullptr,
                           ctx->grid_scratch.p, ctx->grid_scratch.n, st));
   }
+  return grid_finish(ctx);
+}
+
+// lists -> valid cells -> samples -> LPF ratios -> end points: the part of the grid build that follows the (optional) re-order
+static int grid_finish(arap_ctx* ctx) {
+  cudaStream_t st = ctx->stream;
+  const size_t gc = (size_t)ctx->G * ctx->G * ctx->G;
   TRY(build_lists(ctx));
   StageTimer tmr_samples(ctx, ARAP_ST_SAMPLES);
   // valid cells = non-empty padded lists (GV:4040-4053); 4^3 samples each (GV:4111-4133)
@@ -438,6 +462,10 @@ extern "C" int arap_grid_update_lists(arap_ctx* ctx) {
   CTX_CHECK(ctx);
   if (!ctx->grid_ready) { set_error("grid_update_lists: grid not built"); return ARAP_ERR_STATE; }
   TRY(materialize_sample_sh(ctx));   // stroke end: the aim features are consumed next (UpdateFeatures -> L1loss3d, GV:4191-4207)
+  if (ctx->comm.slab) {   // the lists and the field evaluation read everybody's Gaussians: last exchange done, remote SH rows current
+    TRY(arap_comm_materialize_sh(ctx));
+    ARAP_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->comm.ev_done, 0));
+  }
   { StageTimer tmr(ctx, ARAP_ST_SCENE_AABB); TRY(overall_aabb(ctx)); }  // UpdateContainingRelationship recomputes the scene box and step (GV:3636-3644)
   return build_lists(ctx);
 }
@@ -449,8 +477,9 @@ extern "C" int arap_grid_eval(arap_ctx* ctx, int which) {
   DBuf<float>& o = which == 0 ? ctx->aim_opacity : ctx->cur_opacity;
   TRY(f.alloc((size_t)std::max<long long>(ctx->S, 1) * 48)); TRY(o.alloc((size_t)std::max<long long>(ctx->S, 1)));
   StageTimer tmr(ctx, ARAP_ST_GRID_EVAL);
-  TRY(arapk_grid_eval(ctx->valid.p, ctx->V, ctx->fp_prefix.p, ctx->lists.p, ctx->sample_pos.p, ctx->pos.p, ctx->rot.p, ctx->scale.p,
-                      ctx->opacity.p, ctx->shs.p, ctx->ada_lpf.p, f.p, o.p, ctx->stream));
+  const GridSrc gs = grid_src(ctx);
+  TRY(arapk_grid_eval(ctx->valid.p, ctx->V, ctx->fp_prefix.p, ctx->lists.p, ctx->sample_pos.p, gs.pos, gs.rot, gs.scale,
+                      gs.opacity, gs.shs, ctx->ada_lpf.p, f.p, o.p, ctx->stream));
   if (which == 0) {   // GPUSetupSamplesFeatures ends with JudgeEmptyGrid (GV:4268)
     if (ctx->sample_qacc.p) TRY(arapk_fill_identity_quats(ctx->S, ctx->sample_qacc.p, ctx->stream));
     ctx->sample_sh_pending = false;
@@ -1157,7 +1186,7 @@ extern "C" int arap_comm_init(arap_ctx* ctx, const char id[128], int rank, int w
   cm.rank = rank; cm.world = world;
   const size_t n = (size_t)ctx->N, W = (size_t)world;
   TRY(cm.pos_all.alloc(W * n * 3)); TRY(cm.rot_all.alloc(W * n * 4)); TRY(cm.scale_all.alloc(W * n * 3)); TRY(cm.shs_all.alloc(W * n * 48));
-  TRY(cm.rot_base.alloc(W * n * 4));
+  TRY(cm.rot_base.alloc(W * n * 4)); TRY(cm.opacity_all.alloc(W * n));
   int lo = 0, hi = 0;
   ARAP_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   ARAP_CUDA_TRY(cudaStreamCreateWithPriority(&cm.side, cudaStreamNonBlocking, hi));
@@ -1178,6 +1207,7 @@ extern "C" int arap_comm_init(arap_ctx* ctx, const char id[128], int rank, int w
   NCCL_TRY(g_nccl.AllGather(ctx->rot.p, cm.rot_all.p, n * 4, kNcclFloat, cm.nccl, st));
   NCCL_TRY(g_nccl.AllGather(ctx->scale.p, cm.scale_all.p, n * 3, kNcclFloat, cm.nccl, st));
   NCCL_TRY(g_nccl.AllGather(ctx->shs.p, cm.shs_all.p, n * 48, kNcclFloat, cm.nccl, st));
+  NCCL_TRY(g_nccl.AllGather(ctx->opacity.p, cm.opacity_all.p, n, kNcclFloat, cm.nccl, st));   // opacities never change under deformation
   NCCL_TRY(g_nccl.GroupEnd());
   ARAP_CUDA_TRY(cudaMemcpyAsync(cm.rot_base.p, cm.rot_all.p, W * n * 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   ARAP_CUDA_TRY(cudaStreamSynchronize(st));
@@ -1217,6 +1247,64 @@ extern "C" int arap_comm_materialize_sh(arap_ctx* ctx) {
   }
   ARAP_CUDA_TRY(cudaEventRecord(cm.ev_done, cm.side));
   ctx->ev_release = cm.ev_done;
+  return ARAP_OK;
+}
+
+// One scene sharded over the ranks (BASELINE configs[4]): rank r holds the Gaussians [r N, (r + 1) N) of a
+// scene that is already in cell order (what a single-GPU arap_grid_build leaves behind: contiguous index ranges are x-slabs
+// up to boundary effects).  The grid stages then work on ONE grid over all ranks' Gaussians — every rank sees them in the
+// gathered arrays — and each rank bins and evaluates only its x-slab of cells (x-major cell index: a contiguous range of the
+// prefix sums), including the Gaussians of other ranks whose padded footprint reaches into the slab (the halo).  No
+// collective: the scene box, the slab cuts (balanced by Gaussians per x-layer) and the lists are computed from the gathered
+// arrays, identically on every rank.  x_lo < 0: automatic cuts; else the slab [x_lo, x_hi) is taken as given.
+// Replaces arap_grid_build for such a session (no re-order: the global order is the caller's).
+extern "C" int arap_comm_grid_build(arap_ctx* ctx, int x_lo, int x_hi) {
+  CTX_CHECK(ctx);
+  arap_ctx::Comm& cm = ctx->comm;
+  if (!cm.nccl) { set_error("comm_grid_build: arap_comm_init first"); return ARAP_ERR_STATE; }
+  cudaStream_t st = ctx->stream;
+  ctx->G = ctx->prm.grid_num;
+  if (ctx->G < 1 || ctx->G > 256) { set_error("comm_grid_build: grid_num out of range"); return ARAP_ERR_INVALID; }
+  if (x_lo >= 0 && (x_hi > ctx->G || x_lo >= x_hi)) { set_error("comm_grid_build: bad slab"); return ARAP_ERR_INVALID; }
+  if (x_lo < 0 && ctx->G < cm.world) { set_error("comm_grid_build: fewer x-layers than ranks"); return ARAP_ERR_INVALID; }
+  const size_t gc = (size_t)ctx->G * ctx->G * ctx->G;
+  const long long n_all = (long long)cm.world * ctx->N;
+  if (n_all > 2147483647LL) { set_error("comm_grid_build: more than 2^31 - 1 Gaussians"); return ARAP_ERR_INVALID; }
+  cm.slab = true; cm.slab_lo = 0; cm.slab_hi = ctx->G;
+  { StageTimer tmr(ctx, ARAP_ST_SCENE_AABB); TRY(overall_aabb(ctx)); }
+  TRY(ctx->grid_scratch.alloc(arapk_grid_scratch_bytes(n_all, ctx->G)));
+  TRY(ctx->cell_prefix.alloc(gc)); TRY(ctx->gs_init_grid_idx.alloc((size_t)ctx->N));
+  {
+    StageTimer tmr(ctx, ARAP_ST_CELL_ASSIGN);
+    TRY(arapk_cell_assign(ctx->pos.p, ctx->N, ctx->aabb, ctx->step, ctx->G, ctx->gs_init_grid_idx.p, ctx->cell_prefix.p, nullptr,
+                          ctx->grid_scratch.p, ctx->grid_scratch.n, st));
+    if (x_lo < 0) {   // balanced cuts: rank r starts at the first x-layer where the running Gaussian count reaches r / world of the total
+      DBuf<int> hist; TRY(hist.alloc((size_t)ctx->G));
+      TRY(arapk_xlayer_hist(cm.pos_all.p, n_all, ctx->aabb, ctx->step, ctx->G, hist.p, st));
+      std::vector<int> h((size_t)ctx->G);
+      TRY(download(h.data(), hist.p, h.size(), st));
+      ARAP_CUDA_TRY(cudaStreamSynchronize(st));
+      std::vector<int> cut((size_t)cm.world + 1, ctx->G);
+      cut[0] = 0;
+      long long run = 0; int r = 1;
+      for (int x = 0; x < ctx->G && r < cm.world; x++) {
+        run += h[(size_t)x];
+        while (r < cm.world && run * cm.world >= (long long)r * n_all) { cut[(size_t)r] = x + 1; r++; }
+      }
+      for (int q = 1; q <= cm.world; q++) cut[(size_t)q] = std::min(std::max(cut[(size_t)q], cut[(size_t)q - 1] + 1), ctx->G - (cm.world - q));   // at least one layer each
+      cut[(size_t)cm.world] = ctx->G;
+      x_lo = cut[(size_t)cm.rank]; x_hi = cut[(size_t)cm.rank + 1];
+    }
+  }
+  cm.slab_lo = x_lo; cm.slab_hi = x_hi;
+  ARAP_CUDA_TRY(cudaMemcpyAsync(ctx->scale_backup.p, ctx->scale.p, (size_t)ctx->N * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return grid_finish(ctx);
+}
+extern "C" int arap_comm_slab_get(arap_ctx* ctx, int* x_lo, int* x_hi) {
+  CTX_CHECK(ctx);
+  if (!ctx->comm.slab) { set_error("comm_slab_get: not a sharded-scene session"); return ARAP_ERR_STATE; }
+  if (x_lo) *x_lo = ctx->comm.slab_lo;
+  if (x_hi) *x_hi = ctx->comm.slab_hi;
   return ARAP_OK;
 }
 

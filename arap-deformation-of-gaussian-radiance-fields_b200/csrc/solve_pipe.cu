@@ -75,7 +75,13 @@ __device__ __forceinline__ void publish_row(const Loc& L, int li, int j, const D
     if (slot >= 0) dbn[(size_t)slot * 3 + j] = v;
   }
   const int eb = L.lcb[li], ee = eb + (L.ce[li] - L.cb[li]);
-  for (int e = eb; e < ee; e++) pin[(size_t)L.eslot[e] + (size_t)j * PipeK<K>::KP] = d4_dot(ld4(L.cc + (size_t)e * 4), m);
+  for (int e0 = eb; e0 < ee; e0 += 4) {
+    D4 c[4]; int sl[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) { const int e = e0 + r < ee ? e0 + r : eb; c[r] = ld4(L.cc + (size_t)e * 4); sl[r] = L.eslot[e]; }
+#pragma unroll
+    for (int r = 0; r < 4; r++) if (e0 + r < ee) pin[(size_t)sl[r] + (size_t)j * PipeK<K>::KP] = d4_dot(c[r], m);
+  }
 }
 // all rows from L.ms (after the gradient pass, which works per unknown)
 template <int K>
@@ -177,9 +183,18 @@ __device__ __forceinline__ D4 row_finish(const SolveDev& S, const Loc& L, int li
     y.a += rot_t(Aj, S.w_rot, u, 0); y.b += rot_t(Aj, S.w_rot, u, 1); y.c += rot_t(Aj, S.w_rot, u, 2);
   }
   const int eb = L.lcb[li], ee = eb + (L.ce[li] - L.cb[li]);
-  for (int e = eb; e < ee; e++) {
-    const double ug = L.emeta[e] < 0 ? s_ubig[L.erd[e]][j] : L.cu[e * 3 + j];
-    y = d4_axpy(ug, ld4(L.cc + (size_t)e * 4), y);
+  for (int e0 = eb; e0 < ee; e0 += 4) {   // four entries at a time: their shared-memory loads overlap
+    double ug[4]; D4 c[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const bool ok = e0 + r < ee;
+      const int e = ok ? e0 + r : eb;
+      const double u = L.emeta[e] < 0 ? s_ubig[L.erd[e]][j] : L.cu[e * 3 + j];
+      ug[r] = ok ? u : 0.0;
+      c[r] = ld4(L.cc + (size_t)e * 4);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) y = d4_axpy(ug[r], c[r], y);
   }
   return y;
 }
@@ -510,7 +525,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_solve_pipe(SolveDev S, unsign
         const unsigned long long t2 = gtime2();
         barrier_reduce<3>(S, counter, phase, red);
         const unsigned long long t3 = gtime2();
-        if (tid == 0) { s_time[0] += (double)(t1 - t0); s_time[1] += (double)(t2 - t1); s_time[2] += (double)(t3 - t2); }
+        if (tid == 0) { s_time[0] += (double)(t1 - t0); s_time[1] += (double)(t2 - t1); s_time[2] += (double)(t3 - t2); s_time[3] += (double)(t2 - t0); }
         total_cg++;
         gam_old = gam; alpha_old = alpha;
         if (it == S.max_cg - 1) flag |= 2;
@@ -569,6 +584,16 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_solve_pipe(SolveDev S, unsign
     const double v = L.xs[t];
     if (c < 3) S.rot_out[(size_t)i * 9 + jj + 3 * c] = v; else S.trans_out[(size_t)i * 3 + jj] = v;
   }
+  // diagnostics: spread of the CTAs' own work per iteration (everything but the barrier); the per-CTA totals go through S.z
+  if (tid == 0) { S.z[2 * b] = s_time[3]; S.z[2 * b + 1] = (double)L.nent; }
+  red[0] = 0.0;
+  barrier_reduce<1>(S, counter, phase, red);
+  if (b == 0 && tid == 0) {
+    double mx = 0.0, mn = 1e300, sum = 0.0; int amx = 0;
+    for (int bb = 0; bb < B; bb++) { const double v = __ldcg(S.z + 2 * bb); sum += v; if (v > mx) { mx = v; amx = bb; } mn = fmin(mn, v); }
+    // barrier_skew_ns[0..3]: per-CTA work (everything but the barrier) summed over the PCG iterations: mean, max, min over CTAs, block 0's
+    S.stats[24] = sum / B; S.stats[25] = mx; S.stats[26] = mn; S.stats[27] = s_time[3]; S.stats[28] = amx; S.stats[29] = __ldcg(S.z + 2 * amx + 1);
+  }
   if (b == 0 && tid == 0) {
     if (S.warm) S.warm[0] = (flag & 1) ? 0.0 : (double)min(gn_iters, SOLVE_WARM_MAX);
     S.stats[0] = gn_iters; S.stats[1] = energy; S.stats[2] = halvings; S.stats[3] = normh;
@@ -576,7 +601,6 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_solve_pipe(SolveDev S, unsign
     // phase timers of block 0 (summed over PCG iterations): stencil + recurrences, partial publication, barrier
     S.stats[8] = s_time[0]; S.stats[9] = s_time[1]; S.stats[10] = s_time[2]; S.stats[11] = 0.0; S.stats[12] = gridDim.x;
     for (int t = 0; t < 8; t++) S.stats[16 + t] = s_cg_gn[t];
-    for (int t = 0; t < 6; t++) S.stats[24 + t] = 0.0;
     // stencil phase split (thread 0 of block 0): gathers issued + group sums, CTA sync, first row's stencil, recurrences + publication
     S.stats[13] = s_tsub[0]; S.stats[14] = s_tsub[1]; S.stats[15] = s_tsub[2]; S.stats[7] = s_tsub[3];
   }

@@ -400,7 +400,9 @@ def run_own(args):
                   "phase_us_per_cg_iter": [round(x / 1e3 / max(st["cg_iters"], 1), 2) for x in st["phase_ns"]],
                   "row_phase_split_us": [round(x / 1e3 / max(st["cg_iters"], 1), 2) for x in st["row_sub_ns"]],
                   "cg_iters_gn": st["cg_iters_gn"][:st["gn_iters"]],
-                  "row_phase_last_warp_us_and_barrier_us": [round(x / 1e3 / max(st["gn_iters"], 1), 2) for x in st["barrier_skew_ns"]]},
+                  **({"cta_work_us_per_cg_iter_mean_max_min_block0": [round(x / 1e3 / max(st["cg_iters"], 1), 2) for x in st["barrier_skew_ns"][:4]]}
+                     if s.params.solver_pipelined and st["phase_ns"][3] == 0 else
+                     {"row_phase_last_warp_us_and_barrier_us": [round(x / 1e3 / max(st["gn_iters"], 1), 2) for x in st["barrier_skew_ns"]]})},
         "drag_profile": drag_profile, "exchange": exchange,
         "apply_gaussians_per_s": round(N / (apply_ms * 1e-3), 1) if apply_ms > 0 else None,
         "setup_s": {"grid_build_eval": round(setup["t_grid_s"], 3), "graph_knn": round(setup["t_graph_s"], 3), "note": "host wall clock incl. allocation and table uploads; device stage times below"},

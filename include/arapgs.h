@@ -108,7 +108,9 @@ typedef struct arap_solve_stats {
   int cg_iters_gn[8];  /* PCG iterations of the first 8 Gauss-Newton iterations */
   double barrier_skew_ns[6]; /* diagnostics sampled at PCG iteration 50 of each Gauss-Newton iteration (summed), block 0: time from the
                                 start of the row phase until its LAST warp has finished E_reg rows, E_rot rows, constraint gathers,
-                                the CTA sync, the whole phase; [5] = last CTA's arrival at the barrier -> block 0's exit */
+                                the CTA sync, the whole phase; [5] = last CTA's arrival at the barrier -> block 0's exit.
+                                One-barrier kernel: [0..3] = a CTA's own work (everything but the barrier) summed over the PCG iterations:
+                                mean, max, min over the CTAs, block 0's */
 } arap_solve_stats;
 
 typedef struct arap_grid_info {
@@ -300,6 +302,17 @@ int arap_comm_materialize_sh(arap_ctx* ctx);
 int arap_comm_sync(arap_ctx* ctx);
 int arap_comm_view(arap_ctx* ctx, arap_gathered_view* out);
 int arap_comm_destroy(arap_ctx* ctx);
+/* ONE scene sharded over the ranks (BASELINE configs[4]).  Rank r holds the Gaussians [r n, (r + 1) n) of a
+ * scene that is already in cell order (the order a single-GPU arap_grid_build leaves behind; contiguous index ranges are then
+ * x-slabs up to boundary effects).  arap_comm_grid_build replaces arap_grid_build for such a session (after arap_comm_init):
+ * one grid over all ranks' Gaussians (scene box GV:3601-3631 over the gathered positions, identical on every rank), of which
+ * this rank bins (GV:3961-4100) and evaluates (GV:4159-4186) only its x-slab of cells [x_lo, x_hi) — including the Gaussians
+ * of other ranks whose padded footprint reaches into the slab (the halo; they are read from the gathered arrays, no extra
+ * exchange).  x_lo < 0: automatic cuts balanced by the number of Gaussians per x-layer (same result on every rank).
+ * The samples, their skinning tables, the per-step sample passes and the stroke-end rebuild (arap_grid_update_lists: call
+ * arap_comm_exchange after the last step first) then cover that slab only; the union over the ranks is the single-GPU grid. */
+int arap_comm_grid_build(arap_ctx* ctx, int x_lo, int x_hi);
+int arap_comm_slab_get(arap_ctx* ctx, int* x_lo, int* x_hi);
 
 /* ---- deform.txt / graph.obj / config / scripts (host IO, byte-compatible) -- */
 typedef struct arap_history arap_history;

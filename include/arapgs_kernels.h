@@ -156,6 +156,12 @@ int arapk_footprint_count(long long N, const float* aabb, const float* min3_host
                           cudaStream_t st);
 int arapk_footprint_fill(long long N, const float* aabb, const float* min3_host, float step, int G, int padding,
                          const int* prefix, int* lists_out, void* scratch, size_t scratch_bytes, cudaStream_t st);
+/* multi-GPU grid sharding: the same passes restricted to the x-slab [xlo, xhi) of cells; per-x-layer Gaussian counts */
+int arapk_footprint_count_slab(long long N, const float* aabb, const float* min3_host, float step, int G, int padding, int xlo, int xhi,
+                               int* prefix_out, long long* total_host, void* scratch, size_t scratch_bytes, cudaStream_t st);
+int arapk_footprint_fill_slab(long long N, const float* aabb, const float* min3_host, float step, int G, int padding, int xlo, int xhi,
+                              const int* prefix, int* lists_out, void* scratch, size_t scratch_bytes, cudaStream_t st);
+int arapk_xlayer_hist(const float* pos, long long N, const float* min3_host, float step, int G, int* hist_dev /* G */, cudaStream_t st);
 int arapk_valid_cells(const int* prefix, int G, int* valid_out, int* count_host, void* scratch, size_t scratch_bytes,
                       cudaStream_t st);
 int arapk_emit_samples(const int* valid, int V, const float* min3_host, float step, int G, float* out, cudaStream_t st);

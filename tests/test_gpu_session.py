@@ -243,6 +243,73 @@ def test_pipelined_solver_matches_the_two_barrier_kernel(pkg, scenes):
         print(f"on_center={on_center} ctas={ctas}: PCG iterations pipelined {[o[1] for o in res[0]]} two-barrier {[o[1] for o in res[1]]}")
 
 
+def test_sharded_scene_grid_slabs_union_to_the_single_gpu_grid(pkg, scenes):
+    """arap_comm_grid_build (one scene sharded over the ranks): every slab of the grid — built from the
+    gathered arrays, binning restricted to an x-range of cells — must be exactly that part of the single-GPU grid: valid
+    cells, per-cell lists, sample positions and the evaluated field, bit for bit; also after a drag and a stroke-end rebuild.
+    One GPU: world-1 communicators (the gathered arrays are then the session's own), three slabs built one after the other;
+    the multi-rank index offsets are exercised by tools/sharded_scene_check.py on 2 GPUs."""
+    sc = scenes.make_scene("sphere1m", n=40000)
+    kw = dict(grid_num=32, knn_k=10, node_num=200)
+    full = pkg.Session(device=0, **kw)
+    full.set_gaussians(sc["pos"], sc["rot"], sc["scale"], sc["opacity"], sc["shs"])
+    gi = full.grid_build()
+    full.grid_eval(0)
+    ordered = full.download_gaussians()                    # cell order: what a sharded host would distribute
+    g = full.graph_build_fps()
+    blocks, types = scenes.cap_blocks(g["node_pos"], lo=-0.3, hi=0.3)
+
+    def state(s):
+        d = s.download_grid(); f, o = s.download_features(0)
+        return d, f, o
+
+    def drag(s):
+        s.set_blocks(blocks, types)
+        for _ in range(2):
+            s.aim_translate([0.0, 0.01, 0.02]); s.step(False)
+
+    ref, rf, ro = state(full)
+    drag(full)
+    full.grid_update_lists(); full.grid_eval(1)
+    ref2 = full.download_grid(); rf2, ro2 = full.download_features(1)
+    G = gi["grid_num"]
+    cuts = [0, 11, 19, G]
+    got_valid, got_cells = [], 0
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        s = pkg.Session(device=0, **kw)
+        s.set_gaussians(ordered["pos"], ordered["rot"], ordered["scale"], ordered["opacity"], ordered["shs"])
+        s.comm_init(pkg.comm_unique_id(), 0, 1)
+        si = s.comm_grid_build(lo, hi)
+        assert s.comm_slab() == (lo, hi)
+        s.grid_eval(0)
+        d, f, o = state(s)
+        assert np.array_equal(d["gs_init_grid_idx"], ref["gs_init_grid_idx"])
+        x = d["valid"] // (G * G)
+        assert si["valid_cells"] > 0 and x.min() >= lo and x.max() < hi
+        sel = np.nonzero((ref["valid"] // (G * G) >= lo) & (ref["valid"] // (G * G) < hi))[0]
+        assert np.array_equal(d["valid"], ref["valid"][sel])
+        rows = (sel[:, None] * 64 + np.arange(64)[None, :]).reshape(-1)
+        assert np.array_equal(d["sample_pos"], ref["sample_pos"][rows])
+        assert np.array_equal(f, rf[rows]) and np.array_equal(o, ro[rows])
+        # per-cell lists of the slab's cells
+        rp = np.concatenate([[0], ref["prefix"]]); dp = np.concatenate([[0], d["prefix"]])
+        for c in d["valid"][:: max(1, len(d["valid"]) // 200)]:
+            assert np.array_equal(d["lists"][dp[c]:dp[c + 1]], ref["lists"][rp[c]:rp[c + 1]])
+        assert dp[-1] == sum(rp[c + 1] - rp[c] for c in d["valid"])
+        # drag + stroke end (world 1: the exchange is a self-copy)
+        s.graph_build_anchors(g["anchor"])
+        drag(s)
+        s.comm_exchange()
+        s.grid_update_lists(); s.grid_eval(1)
+        d2 = s.download_grid(); f2, o2 = s.download_features(1)
+        assert np.array_equal(d2["sample_pos"], ref2["sample_pos"][rows])
+        assert np.array_equal(f2, rf2[rows]) and np.array_equal(o2, ro2[rows])
+        got_valid.append(d["valid"]); got_cells += si["valid_cells"]
+        s.close()
+    assert got_cells == gi["valid_cells"] and np.array_equal(np.concatenate(got_valid), ref["valid"])
+    full.close()
+
+
 def test_twist_scale_and_excluded_blocks(pkg, scenes):
     sc, s, o, gi, og = _pair(pkg, scenes, n=20000, grid_num=32, knn_k=10, node_num=120)
     g = s.graph_build_fps(); o.graph_build_fps()
