@@ -294,6 +294,15 @@ __global__ void k_xlayer_hist(long long N, const float* __restrict__ pos, float 
   for (int t = threadIdx.x; t < G; t += blockDim.x) if (s_h[t]) atomicAdd(&hist[t], s_h[t]);
 }
 
+// total of the per-cell pair counts in 64 bits: the prefix sums and list offsets are int32
+__global__ void k_count_total(long long ncell, const int* __restrict__ cnt, unsigned long long* __restrict__ total) {
+  unsigned long long a = 0;
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += (long long)gridDim.x * blockDim.x) a += (unsigned)cnt[c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0 && a) atomicAdd(total, a);
+}
+
 // ------------------------------------------------------------------ valid cells + samples
 __global__ void k_valid_flags(long long ncell, const int* __restrict__ prefix, int* __restrict__ flags) {
   const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -600,14 +609,17 @@ extern "C" int arapk_footprint_count_slab(long long N, const float* aabb, const 
   ARAP_CUDA_TRY(cudaMemsetAsync(s.cnt, 0, sizeof(int) * gc, st));
   const float3 mn = make_float3(min3[0], min3[1], min3[2]);
   if (N > 0) { k_footprint<false><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, aabb, mn, step, G, padding, s.cnt, nullptr, nullptr, xlo, xhi); ARAP_KERNEL_CHECK(); }
-  int rc = scan_inclusive(s.cnt, prefix_out, gc, s.sums, st); if (rc) return rc;
-  if (total_host) {
-    int last = 0;
-    ARAP_CUDA_TRY(cudaMemcpyAsync(&last, prefix_out + gc - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (total_host) {   // 64-bit total first: more than 2^31 - 1 pairs do not fit the int32 offsets (shard the grid: arap_comm_grid_build)
+    unsigned long long* tot = reinterpret_cast<unsigned long long*>(s.big);   // 8-byte aligned scratch, rewritten by the fill pass
+    ARAP_CUDA_TRY(cudaMemsetAsync(tot, 0, sizeof(unsigned long long), st));
+    k_count_total<<<148 * 4, 256, 0, st>>>(gc, s.cnt, tot); ARAP_KERNEL_CHECK();
+    unsigned long long h = 0;
+    ARAP_CUDA_TRY(cudaMemcpyAsync(&h, tot, sizeof(h), cudaMemcpyDeviceToHost, st));
     ARAP_CUDA_TRY(cudaStreamSynchronize(st));
-    *total_host = last;
+    if (h > 2147483647ULL) { set_error("footprint_count: " + std::to_string(h) + " (cell, Gaussian) pairs exceed the int32 list offsets of one GPU: shard the grid over more ranks (arap_comm_grid_build)"); return ARAP_ERR_INVALID; }
+    *total_host = (long long)h;
   }
-  return ARAP_OK;
+  return scan_inclusive(s.cnt, prefix_out, gc, s.sums, st);
 }
 
 extern "C" int arapk_footprint_fill(long long N, const float* aabb, const float* min3, float step, int G, int padding,

@@ -20,7 +20,8 @@ CONFIGS = {
     "sphere1m": dict(index=2, n=1_000_000, s_med=0.004, grid=64, nodes=4000, k=10),
     "shells6m": dict(index=3, n=6_000_000, s_med=0.002, grid=128, nodes=16000, k=10,
                      samples_at_n=58_776_512),   # 64 x valid cells of the full scene (grid_build on the GPU arm)
-    "shells50m": dict(index=4, n=50_000_000, s_med=0.001, grid=128, nodes=16000, k=10),
+    # ONE scene sharded over the ranks (BASELINE configs[4]): make_scene_shard, arap_comm_grid_build
+    "shells50m": dict(index=4, n=50_000_000, s_med=0.001, grid=128, nodes=16000, k=10, sharded_scene=True),
 }
 
 
@@ -78,6 +79,56 @@ def make_scene(name: str, n: int | None = None, seed_offset: int = 0):
     rot, scale, opacity, shs = _attributes(rng, n, cfg["s_med"])
     return dict(pos=np.ascontiguousarray(pos), rot=rot, scale=scale, opacity=opacity, shs=shs, name=name,
                 grid=cfg["grid"], nodes=cfg["nodes"], k=cfg["k"], n=n)
+
+
+def _attributes32(rng, n, s_med):
+    """Same law as _attributes, float32 draws (the 50M-Gaussian scene: 2.4 G normal variates)."""
+    scale = np.exp(np.float32(np.log(s_med)) + np.float32(0.4) * rng.standard_normal((n, 3), dtype=np.float32))
+    opacity = (1.0 / (1.0 + np.exp(-(np.float32(2.0) + rng.standard_normal(n, dtype=np.float32))))).astype(np.float32)
+    q = rng.standard_normal((n, 4), dtype=np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    shs = np.empty((n, 48), np.float32)
+    shs[:, :3] = rng.random((n, 3), dtype=np.float32) * np.float32(2.0) - np.float32(1.0)
+    shs[:, 3:] = np.float32(0.05) * rng.standard_normal((n, 45), dtype=np.float32)
+    return q, scale.astype(np.float32), opacity, shs
+
+
+SHARD_BLOCKS = 64      # attribute streams of a sharded scene: one per 1/64 of the globally ordered Gaussians
+SHARD_CHUNK = 2_000_000
+
+
+def make_scene_shard(name: str, n_total: int, rank: int, world: int):
+    """Rank `rank`'s contiguous part [rank n, (rank + 1) n) of ONE scene of n_total Gaussians in global cell order (x-major cells
+    of a fixed 128^3 grid over [-0.8, 0.8]^3: what a single-GPU grid build would leave behind, up to its data-dependent box).
+    The scene does not depend on `world`: positions come from per-chunk streams (every rank draws all of them and sorts the
+    cell keys), the i.i.d. attributes from one stream per 1/64 of the ordered Gaussians (a rank draws only its own)."""
+    cfg = CONFIGS[name]
+    n_total = int(n_total)
+    assert SHARD_BLOCKS % world == 0 and n_total % SHARD_BLOCKS == 0, "n_total must divide into 64 blocks, world into 64"
+    n = n_total // world
+    pos = np.empty((n_total, 3), np.float32)
+    for c, lo in enumerate(range(0, n_total, SHARD_CHUNK)):
+        m = min(SHARD_CHUNK, n_total - lo)
+        rng = np.random.Generator(np.random.PCG64(BASE_SEED + cfg["index"] + 1000 * (100 + c)))
+        pos[lo:lo + m] = _positions(name, rng, m).astype(np.float32)
+    G = 128
+    cell = np.clip(np.floor((pos + np.float32(0.8)) * np.float32(G / 1.6)), 0, G - 1).astype(np.int32)
+    key = (cell[:, 0] * G + cell[:, 1]) * G + cell[:, 2]
+    del cell
+    order = np.argsort(key, kind="stable")
+    del key
+    own = order[rank * n:(rank + 1) * n]
+    del order
+    out = dict(pos=np.ascontiguousarray(pos[own]), name=name, grid=cfg["grid"], nodes=cfg["nodes"], k=cfg["k"], n=n, n_total=n_total)
+    del pos
+    blk = n_total // SHARD_BLOCKS
+    parts = []
+    for b in range(rank * n // blk, (rank + 1) * n // blk):
+        rng = np.random.Generator(np.random.PCG64(BASE_SEED + cfg["index"] + 1000 * (5000 + b)))
+        parts.append(_attributes32(rng, blk, cfg["s_med"]))
+    for i, kk in enumerate(("rot", "scale", "opacity", "shs")):
+        out[kk] = np.ascontiguousarray(np.concatenate([p[i] for p in parts]))
+    return out
 
 
 def cap_blocks(node_pos: np.ndarray, axis: int = 2, lo: float = -0.4, hi: float = 0.4):

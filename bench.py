@@ -38,6 +38,7 @@ UNIT = "ms"
 WORKLOADS = {
     "shells6m": "synthetic 6M-Gaussian scene, 128^3 grid, 16k nodes, k=10, solve+samples+apply per drag step (BASELINE configs[3]; its high_quality flag only acts inside the reference's external CudaRasterizer fork and changes nothing here)",
     "sphere1m": "synthetic 1M-Gaussian cloud, 64^3 grid, 4k graph nodes, k=10, drag replay",
+    "shells50m": "synthetic 50M-Gaussian scene (ONE scene, strong scaling), 128^3 grid, 16k nodes, k=10, apply and grid sampling sharded over the GPUs with an NCCL all-gather of the deformed Gaussians (BASELINE configs[4])",
 }
 DRAG = np.array([0.0, 0.0, 0.002], np.float32)
 
@@ -127,6 +128,45 @@ def setup_session(pkg, scenes, workload, n, rank, world, stream):
                                                                  **{k2: st_graph[k2] for k2 in ("fps", "node_graph", "knn_ends", "knn_samples", "tile_tables")}})
 
 
+def setup_session_sharded(pkg, scenes, workload, n_total, rank, world, stream, dist, torch):
+    """BASELINE configs[4]: ONE scene of n_total Gaussians, rank r holds the contiguous part r of its global cell order; the grid
+    is built over everybody's Gaussians and each rank bins / evaluates its x-slab of cells (arap_comm_grid_build)."""
+    cfg = scenes.CONFIGS[workload]
+    sc = scenes.make_scene_shard(workload, n_total, rank, world)
+    s = pkg.Session(device=int(os.environ.get("LOCAL_RANK", 0)), stream=stream, grid_num=cfg["grid"], knn_k=cfg["k"],
+                    node_num=cfg["nodes"], lbs_mode=3)
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(pkg.comm_unique_id()), dtype=torch.uint8))
+    if world > 1:
+        dist.broadcast(idt, 0)
+    t0 = time.perf_counter()
+    s.set_gaussians(sc["pos"], sc["rot"], sc["scale"], sc["opacity"], sc["shs"])
+    s.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+    gi = s.comm_grid_build()
+    s.grid_eval(0)
+    s.sync(); t_grid = time.perf_counter() - t0
+    st_grid = s.setup_timing()
+    t0 = time.perf_counter()
+    # replicated solve: every rank uses the same node set (FPS over a common seeded cloud of the same law), for every world size
+    common = scenes.make_scene("shells6m", n=max(cfg["nodes"] * 25, 100000), seed_offset=7777)
+    tmp = pkg.Session(device=int(os.environ.get("LOCAL_RANK", 0)), grid_num=16, knn_k=cfg["k"], node_num=cfg["nodes"])
+    tmp.set_gaussians(common["pos"], common["rot"], common["scale"], common["opacity"], common["shs"])
+    tmp.grid_build()
+    nodes = tmp.graph_build_fps()["node_pos"]
+    tmp.close()
+    s.set_mesh_points(nodes, True)
+    g = s.graph_build_fps()
+    s.sync(); t_graph = time.perf_counter() - t0
+    st_graph = s.setup_timing()
+    blocks, types = scenes.cap_blocks(g["node_pos"])
+    s.set_blocks(blocks, types)
+    lo, hi = s.comm_slab()
+    return s, sc, gi, dict(t_grid_s=t_grid, t_graph_s=t_graph, n_active=len(blocks[0]), n_pinned=len(blocks[1]), active=blocks[0], slab=[lo, hi],
+                           blocks=blocks, types=types, stage_ms={**{k2: st_grid[k2] for k2 in ("scene_aabb", "cell_assign", "reorder", "footprint_lists", "samples", "grid_eval")},
+                                                                 **{k2: st_graph[k2] for k2 in ("fps", "node_graph", "knn_ends", "knn_samples", "tile_tables")}})
+
+
 def run_own(args):
     import torch
     import torch.distributed as dist
@@ -159,7 +199,11 @@ def run_own(args):
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
     assert stream != 0
-    s, sc, gi, setup = setup_session(pkg, scenes, args.workload, n, rank, world, stream)
+    sharded = bool(cfg.get("sharded_scene"))
+    if sharded:
+        s, sc, gi, setup = setup_session_sharded(pkg, scenes, args.workload, n, rank, world, stream, dist, torch)
+    else:
+        s, sc, gi, setup = setup_session(pkg, scenes, args.workload, n, rank, world, stream)
     M, k, N, S = s.M, cfg["k"], s.N, gi["samples"]
     if world > 1 and nccl_ctas > 0:
         sms = torch.cuda.get_device_properties(local).multi_processor_count
@@ -169,9 +213,11 @@ def run_own(args):
     if args.max_cg is not None:
         s.set_params(max_cg_iters=args.max_cg)
 
-    gather, abi_comm = None, False
+    gather, abi_comm = None, sharded
     gmode = os.environ.get("ARAP_GATHER", "abi")
-    if world > 1 and gmode == "abi":
+    if sharded:
+        pass                         # the communicator was set up before the grid build (setup_session_sharded)
+    elif world > 1 and gmode == "abi":
         # Default: the exchange behind the C ABI (arap_comm_*): in-place grouped NCCL all-gather of pos / rot / scale on the ctx's
         # high-priority side stream, remote SH rows brought up to date lazily (arap_comm_materialize_sh, timed separately below).
         # torch.distributed only carries the 128-byte NCCL id, the barriers and the max-over-ranks of the timings.
@@ -236,9 +282,11 @@ def run_own(args):
     for _ in range(max(args.warmup, 3)):
         one_step()
     barrier()
-    s.set_params(**{**base, "lbs_mode": 0})     # the bit-faithful kernels (their tables are built on first use, outside T_graph)
-    m0, _ = timed_block(10)
-    stages_mode0 = [round(float(x), 4) for x in m0]
+    stages_mode0 = []
+    if not args.no_mode0:
+        s.set_params(**{**base, "lbs_mode": 0})     # the bit-faithful kernels (their tables are built on first use, outside T_graph)
+        m0, _ = timed_block(10)
+        stages_mode0 = [round(float(x), 4) for x in m0]
     # debug: stage timers of parameter variants on the same session (stderr).  --variants "lbs_mode=1;lbs_mode=2,warm_start=0"
     for spec in [v for v in args.variants.split(";") if v]:
         s.set_params(**{**base, **parse(spec)})
@@ -380,7 +428,7 @@ def run_own(args):
     t_stroke = sum(stroke.values()) if stroke else sm["scene_aabb"] + sm["footprint_lists"] + sm["grid_eval"]
     line = {
         "metric": METRIC, "value": round(ms_step, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": round(ms_step, 4), "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": round(ms_step, 4), "higher_is_better": False, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
         "dtype": "f32 storage; f64 Gauss-Newton solve; skinning " + ("f32 displacement form (arap_params.lbs_mode = 3, within ~1 float ulp of the reference's float += double chain)" if lbs_mode == 3 else "f64 products + float accumulator (bit-faithful, lbs_mode = %d)" % lbs_mode),
         "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload], "gaussians_per_gpu": N, "gaussians_total": N * world, "nodes": M, "k": k,
@@ -388,6 +436,7 @@ def run_own(args):
                    "constraints": "per-node (op type 4), two caps (|z|>0.4); the GUI's default bend mode (centre constraints, op type 1) is rank-deficient with two blocks and is covered by the parity tests with three",
                    "active_nodes": setup["n_active"], "pinned_nodes": setup["n_pinned"], "lbs_mode": lbs_mode,
                    "l2": "inputs (>1.4 GB SoA + tables per step) exceed the 126 MB L2",
+                   **({"sharded_scene": {"x_slab_of_rank0": setup["slab"], "what": "ONE scene; rank r holds part r of its global cell order, the grid is built over all ranks' Gaussians (gathered arrays) and every rank bins / evaluates / advects only its x-slab of cells (arap_comm_grid_build); total work is fixed as N grows"}} if sharded else {}),
                    "parallelism": ("replicated solve, Gaussians/samples sharded by index; every step all ranks exchange the deformed Gaussians through the C ABI (arap_comm_exchange): in-place grouped NCCL all-gather of pos/rot/scale on a high-priority side stream, started when the six-point fit is done (overlaps the sample passes); remote SH rows are rotated on demand (arap_comm_materialize_sh, timed in `exchange`)" if abi_comm else "replicated solve, Gaussians/samples sharded by index; exchange variant ARAP_GATHER=" + gmode) if world > 1 else "single GPU"},
         "stages_ms": {"solve": round(float(mean[0]), 4), "sample_advect": round(float(mean[1]), 4), "endpoint_lbs": round(float(mean[2]), 4),
                       "six_point_fit": round(float(mean[3]), 4), "sample_sh_rotate": round(float(mean[4]), 4),
@@ -564,6 +613,7 @@ def main():
     ap.add_argument("--workload", default="shells6m", choices=list(WORKLOADS))
     ap.add_argument("--gaussians", type=int, default=0, help="override the Gaussian count per GPU (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mode0", action="store_true", help="skip the timing of the bit-faithful skinning kernels (their extra tables: memory at 50M Gaussians per GPU)")
     ap.add_argument("--no-drag-profile", action="store_true", help="skip the non-steady drag sequence and the stroke-end timing")
     ap.add_argument("--newton-eta0", type=float, default=None, help="override arap_params.newton_eta0 (debug)")
     ap.add_argument("--max-cg", type=int, default=None, help="override arap_params.max_cg_iters (debug)")
