@@ -228,7 +228,7 @@ __device__ __forceinline__ void apply_H(const SolveDev& S, const Loc& L, const d
     if (lane == 0) s_ubig[bi][j] = acc;
   }
   // (2) single-member groups: a team of 16 (K <= 10) or 32 lanes per column entry fetches the member's 3 x K partials with one
-  // coalesced instruction (lane l: elements 2l, 2l + 1 of [component][K]); lanes 0..2 of the team then sum component 0..2 in slot order
+  // coalesced instruction (lane l: elements 2l, 2l + 1 of [component][K]); a fixed shuffle tree over the K / 2 lanes of a component sums it
   {
     constexpr int TL = 3 * K / 2 <= 16 ? 16 : 32, TPW = 32 / TL, H = K / 2;
     const int team = lane / TL, tl = lane % TL;
@@ -244,11 +244,13 @@ __device__ __forceinline__ void apply_H(const SolveDev& S, const Loc& L, const d
 #pragma unroll
       for (int r = 0; r < PIPE_PPB; r++) {
         const int e = eb + team + r * STRIDE;
+        // lanes [j H, (j + 1) H) of the team hold component j: fixed tree over the H lanes, the sum lands on lane j H
         const double x = v[r].x + v[r].y;
-        double acc = 0.0;
-#pragma unroll
-        for (int t = 0; t < H; t++) acc += __shfl_sync(0xffffffffu, x, team * TL + ((tl < 3 ? tl : 0) * H + t));
-        if (tl < 3 && e < L.nent && L.emeta[e] >= 0) L.cu[e * 3 + tl] = acc;
+        double a = x + __shfl_down_sync(0xffffffffu, x, 1);
+        double acc = a + __shfl_down_sync(0xffffffffu, a, 2);
+        if (H == 5) acc += __shfl_down_sync(0xffffffffu, x, 4);
+        if (H == 6) acc += __shfl_down_sync(0xffffffffu, a, 4);
+        if (tl < 3 * H && tl % H == 0 && e < L.nent && L.emeta[e] >= 0) L.cu[e * 3 + tl / H] = acc;
       }
     }
   }
