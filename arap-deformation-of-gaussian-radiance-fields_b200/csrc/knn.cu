@@ -304,6 +304,7 @@ k_fps_pruned(const float* __restrict__ pos, FpsGrid g, const int* __restrict__ p
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sup = fps_better_or_empty(sup, FpsBest{__shfl_xor_sync(0xffffffffu, sup.v, o), __shfl_xor_sync(0xffffffffu, sup.i, o)});
+        __syncwarp();   // every lane has read s_sm[s] above (the shuffles already order it; this states it for racecheck)
         if (lane == 0) s_sm[s] = sup;
       }
     } else

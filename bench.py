@@ -320,6 +320,20 @@ def run_own(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
 
+    # ---- for information: the same steps with the per-step sample SH rotation deferred to the stroke end (arap_params.lazy_sample_sh:
+    # a step composes its blended rotation onto a per-sample quaternion, the feature rows are rotated once when they are consumed).
+    # Not the reported configuration: the reference rotates the rows every step (GV:1519).
+    lazy_info = None
+    if world == 1 and not args.no_mode0:
+        s.set_params(lazy_sample_sh=1)
+        ml, _ = timed_block(10)
+        le0, le1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        le0.record(); s.sample_features_materialize(); le1.record(); torch.cuda.synchronize()
+        lazy_info = {"ms_per_step": round(float(ml[5]), 4), "sample_quaternion_accumulate_ms": round(float(ml[4]), 4),
+                     "materialize_once_ms": round(le0.elapsed_time(le1), 3), "what": "arap_params.lazy_sample_sh = 1; off by default (the reference rotates the sample features every step)"}
+        s.set_params(lazy_sample_sh=0)
+        s.enable_timing(True)
+
     # ---- e2e: host-driven drag loop through the C ABI: host aims in, node positions + solve stats out, every step
     s.enable_timing(False)
     aim = s.aim_get()
@@ -452,7 +466,7 @@ def run_own(args):
                   **({"cta_work_us_per_cg_iter_mean_max_min_block0": [round(x / 1e3 / max(st["cg_iters"], 1), 2) for x in st["barrier_skew_ns"][:4]]}
                      if s.params.solver_pipelined and st["phase_ns"][3] == 0 else
                      {"row_phase_last_warp_us_and_barrier_us": [round(x / 1e3 / max(st["gn_iters"], 1), 2) for x in st["barrier_skew_ns"]]})},
-        "drag_profile": drag_profile, "exchange": exchange,
+        "drag_profile": drag_profile, "exchange": exchange, "lazy_sample_sh_variant": lazy_info,
         "apply_gaussians_per_s": round(N / (apply_ms * 1e-3), 1) if apply_ms > 0 else None,
         "setup_s": {"grid_build_eval": round(setup["t_grid_s"], 3), "graph_knn": round(setup["t_graph_s"], 3), "note": "host wall clock incl. allocation and table uploads; device stage times below"},
         # T_full = T_step + T_stroke + T_graph (device time, CUDA events on the ctx stream)
