@@ -405,7 +405,8 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_solve_pipe(SolveDev S, unsign
   int gn_iters = 0, halvings = 0, total_cg = 0, flag = 0, pc = 0;
   double energy = 0.0, normh = 0.0, last_rel = 0.0, abs_target = -1.0, E0 = 0.0;
   bool have_f = false;
-  __shared__ double s_time[4], s_tsub[4];
+  __shared__ double s_time[4], s_tsub[4], s_skew[4];
+  if (tid < 4) s_skew[tid] = 0.0;
   __shared__ int s_cg_gn[8];
   if (tid < 4) { s_time[tid] = 0.0; s_tsub[tid] = 0.0; }
   if (tid < 8) s_cg_gn[tid] = 0;
@@ -528,6 +529,12 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_solve_pipe(SolveDev S, unsign
         barrier_reduce<3>(S, counter, phase, red);
         const unsigned long long t3 = gtime2();
         if (tid == 0) { s_time[0] += (double)(t1 - t0); s_time[1] += (double)(t2 - t1); s_time[2] += (double)(t3 - t2); s_time[3] += (double)(t2 - t0); }
+        if (b == 0 && tid == 0 && (it & 7) == 3) {   // diagnostics (every 8th iteration): arrival spread of the CTAs at this barrier, last arrival -> block 0's exit
+          const unsigned long long* set = reinterpret_cast<const unsigned long long*>(counter) + (size_t)((phase - 1) & 1) * gridDim.x * LL_WORDS;
+          unsigned long long mx = 0, mn = ~0ull;
+          for (int bb = 0; bb < (int)gridDim.x; bb++) { const unsigned long long tt = ll_load(set + (size_t)bb * LL_WORDS + 7); mx = tt > mx ? tt : mx; mn = tt < mn ? tt : mn; }
+          s_skew[0] += (double)(mx - mn); s_skew[1] += (double)(t3 - mx); s_skew[2] += 1.0; s_skew[3] += (double)(mx - t2);
+        }
         total_cg++;
         gam_old = gam; alpha_old = alpha;
         if (it == S.max_cg - 1) flag |= 2;
@@ -594,7 +601,9 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_solve_pipe(SolveDev S, unsign
     double mx = 0.0, mn = 1e300, sum = 0.0; int amx = 0;
     for (int bb = 0; bb < B; bb++) { const double v = __ldcg(S.z + 2 * bb); sum += v; if (v > mx) { mx = v; amx = bb; } mn = fmin(mn, v); }
     // barrier_skew_ns[0..3]: per-CTA work (everything but the barrier) summed over the PCG iterations: mean, max, min over CTAs, block 0's
-    S.stats[24] = sum / B; S.stats[25] = mx; S.stats[26] = mn; S.stats[27] = s_time[3]; S.stats[28] = amx; S.stats[29] = __ldcg(S.z + 2 * amx + 1);
+    S.stats[24] = sum / B; S.stats[25] = mx; S.stats[26] = mn; S.stats[27] = s_time[3];
+    // [4]: arrival spread of the CTAs at the barrier, [5]: last arrival -> block 0's exit (ns per sampled iteration)
+    S.stats[28] = s_skew[2] > 0.0 ? s_skew[0] / s_skew[2] : 0.0; S.stats[29] = s_skew[2] > 0.0 ? s_skew[1] / s_skew[2] : 0.0; S.stats[30] = s_skew[2] > 0.0 ? s_skew[3] / s_skew[2] : 0.0;
   }
   if (b == 0 && tid == 0) {
     if (S.warm) S.warm[0] = (flag & 1) ? 0.0 : (double)min(gn_iters, SOLVE_WARM_MAX);

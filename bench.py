@@ -463,7 +463,8 @@ def run_own(args):
                   "phase_us_per_cg_iter": [round(x / 1e3 / max(st["cg_iters"], 1), 2) for x in st["phase_ns"]],
                   "row_phase_split_us": [round(x / 1e3 / max(st["cg_iters"], 1), 2) for x in st["row_sub_ns"]],
                   "cg_iters_gn": st["cg_iters_gn"][:st["gn_iters"]],
-                  **({"cta_work_us_per_cg_iter_mean_max_min_block0": [round(x / 1e3 / max(st["cg_iters"], 1), 2) for x in st["barrier_skew_ns"][:4]]}
+                  **({"cta_work_us_per_cg_iter_mean_max_min_block0": [round(x / 1e3 / max(st["cg_iters"], 1), 2) for x in st["barrier_skew_ns"][:4]],
+                      "barrier_us_arrival_spread_and_last_arrival_to_exit": [round(x / 1e3, 2) for x in st["barrier_skew_ns"][4:6]]}
                      if s.params.solver_pipelined and st["phase_ns"][3] == 0 else
                      {"row_phase_last_warp_us_and_barrier_us": [round(x / 1e3 / max(st["gn_iters"], 1), 2) for x in st["barrier_skew_ns"]]})},
         "drag_profile": drag_profile, "exchange": exchange, "lazy_sample_sh_variant": lazy_info,
