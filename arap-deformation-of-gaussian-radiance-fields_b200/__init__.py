@@ -475,6 +475,10 @@ class Session:
     def comm_exchange(self):
         check(lib().arap_comm_exchange(self._ctx))
 
+    def comm_set_mode(self, mode):
+        """0 = NCCL all-gather per exchange, 1 = exchange fused into the apply kernel (peer stores over NVLink)."""
+        check(lib().arap_comm_set_mode(self._ctx, int(mode)))
+
     def comm_grid_build(self, x_lo=-1, x_hi=-1):
         """One scene sharded over the ranks: grid over everybody's Gaussians, this rank's x-slab of cells (arap_comm_grid_build)."""
         check(lib().arap_comm_grid_build(self._ctx, int(x_lo), int(x_hi)))

@@ -733,12 +733,17 @@ __global__ void k_words_of_rows(long long n, const int* __restrict__ rows, int* 
   if (i < n) words[i] = (rows[i] + 3) >> 2;
 }
 
+// PUSH: the fused multi-GPU epilogue: when the tile's pose is final the CTA copies it — 40 bytes per Gaussian, as
+// coalesced 16-byte stores — straight into every peer's gathered arrays over NVLink (peer pointers from cudaIpc, see
+// arap_comm_set_mode), so the exchange of the deformed Gaussians rides inside the apply pass instead of following it as a
+// collective.  Static Gaussians are copied too (their values have not changed: same bits on both sides).
+template <bool PUSH>
 __global__ void __launch_bounds__(FIT_TILE, 4)
 k_apply_union(long long N, const NodeXf32* __restrict__ nodes, const uint16_t* __restrict__ gtile_cnt,
               const uint16_t* __restrict__ gtile_nodes, const int* __restrict__ uoff, const int* __restrict__ woff,
               const uint32_t* __restrict__ usw, const uint16_t* __restrict__ unode, const float* __restrict__ uw, float* ends,
               const float* __restrict__ scale_backup, const uint8_t* __restrict__ is_static, float* __restrict__ pos,
-              float* __restrict__ rot, float* __restrict__ scale, float* __restrict__ shs) {
+              float* __restrict__ rot, float* __restrict__ scale, float* __restrict__ shs, ArapPeerPush pp) {
   extern __shared__ float4 s_sh4[];                                        // FIT_TILE x FIT_PITCH4 float4
   float* s_end = reinterpret_cast<float*>(s_sh4 + FIT_TILE * FIT_PITCH4);  // FIT_TILE x END_PITCH
   float4* s_rec = reinterpret_cast<float4*>(s_end + FIT_TILE * END_PITCH); // GT_CAP x 3 float4
@@ -901,6 +906,24 @@ k_apply_union(long long N, const NodeXf32* __restrict__ nodes, const uint16_t* _
       const int r = cp_r0 + 10 * t;
       if (r < rows && !s_static[r]) st_stream4(osh + (size_t)(tid + 120 * t) * 4, s_sh4[r * FIT_PITCH4 + cp_c4]);
     }
+  }
+  if (PUSH) {   // every thread's pos / rot / scale stores precede the __syncthreads above: the tile's pose is complete in L2
+    auto push = [&](const float* own, float* const* peer, int w) {
+      const long long o = g0 * w;
+      const int nf = rows * w;
+      const int n4 = (reinterpret_cast<uintptr_t>(own) & 15) == 0 ? nf >> 2 : 0;   // g0 * w * 4 bytes is a multiple of 16
+      for (int c = tid; c < n4; c += FIT_TILE) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(own + o) + c);
+#pragma unroll
+        for (int q = 0; q < ARAP_MAX_PEERS; q++) if (q < pp.n) reinterpret_cast<float4*>(peer[q] + o)[c] = v;
+      }
+      for (int c = n4 * 4 + tid; c < nf; c += FIT_TILE) {
+        const float v = __ldcg(own + o + c);
+#pragma unroll
+        for (int q = 0; q < ARAP_MAX_PEERS; q++) if (q < pp.n) peer[q][o + c] = v;
+      }
+    };
+    push(pos, pp.pos, 3); push(rot, pp.rot, 4); push(scale, pp.scale, 3);
   }
 }
 
@@ -1550,16 +1573,30 @@ extern "C" int arapk_apply_union(long long N, const void* node_xf32, const uint1
                                  const int* uoff, const int* woff, const uint32_t* usw, const uint16_t* unode, const float* uw,
                                  float* ends, const float* scale_backup, const uint8_t* is_static, float* pos, float* rot,
                                  float* scale, float* shs, cudaStream_t st) {
+  return arapk_apply_union_push(N, node_xf32, gtile_cnt, gtile_nodes, uoff, woff, usw, unode, uw, ends, scale_backup, is_static, pos, rot, scale, shs, nullptr, st);
+}
+extern "C" int arapk_apply_union_push(long long N, const void* node_xf32, const uint16_t* gtile_cnt, const uint16_t* gtile_nodes,
+                                      const int* uoff, const int* woff, const uint32_t* usw, const uint16_t* unode, const float* uw,
+                                      float* ends, const float* scale_backup, const uint8_t* is_static, float* pos, float* rot,
+                                      float* scale, float* shs, const ArapPeerPush* peers, cudaStream_t st) {
   if (N <= 0) return ARAP_OK;
+  if (peers && (peers->n < 0 || peers->n > ARAP_MAX_PEERS)) { set_error("apply_union: bad peer count"); return ARAP_ERR_INVALID; }
   int rc = ensure_sh_tables(); if (rc) return rc;
   const size_t smem = sizeof(float4) * FIT_TILE * FIT_PITCH4 + sizeof(float) * FIT_TILE * END_PITCH + sizeof(float4) * GT_CAP * 3;
   static bool attr_set = false;
   if (!attr_set) {
-    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_apply_union, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_apply_union<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_apply_union<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  k_apply_union<<<(unsigned)arapk_gtile_count(N), FIT_TILE, smem, st>>>(N, (const NodeXf32*)node_xf32, gtile_cnt, gtile_nodes, uoff, woff, usw,
-                                                                      unode, uw, ends, scale_backup, is_static, pos, rot, scale, shs);
+  ArapPeerPush pp{};
+  if (peers && peers->n > 0) {
+    pp = *peers;
+    k_apply_union<true><<<(unsigned)arapk_gtile_count(N), FIT_TILE, smem, st>>>(N, (const NodeXf32*)node_xf32, gtile_cnt, gtile_nodes, uoff, woff, usw,
+                                                                              unode, uw, ends, scale_backup, is_static, pos, rot, scale, shs, pp);
+  } else
+    k_apply_union<false><<<(unsigned)arapk_gtile_count(N), FIT_TILE, smem, st>>>(N, (const NodeXf32*)node_xf32, gtile_cnt, gtile_nodes, uoff, woff, usw,
+                                                                               unode, uw, ends, scale_backup, is_static, pos, rot, scale, shs, pp);
   ARAP_KERNEL_CHECK();
   return ARAP_OK;
 }

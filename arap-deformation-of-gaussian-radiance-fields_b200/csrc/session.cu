@@ -201,6 +201,14 @@ struct arap_ctx {
     // one scene sharded over the ranks (arap_comm_grid_build): the grid stages read ALL Gaussians (the gathered arrays) and
     // bin / evaluate only the x-slab [slab_lo, slab_hi) of cells
     bool slab = false; int slab_lo = 0, slab_hi = 0;
+    // mode 1 (arap_comm_set_mode): the exchange is fused into the apply kernel — peer stores over NVLink into the other ranks'
+    // gathered arrays (cudaIpc mappings), ordered by per-rank epoch flags instead of a collective
+    int mode = 0;
+    ArapPeerPush push{};                                  // peers' gathered arrays, offset to this rank's range
+    void* ipc_base[3][ARAP_MAX_PEERS] = {{nullptr}};      // what cudaIpcOpenMemHandle returned (for the close)
+    DBuf<unsigned long long> flags;                       // [2 * world]: ready[r], done[r] written by rank r
+    unsigned long long* peer_flags[ARAP_MAX_PEERS] = {nullptr};
+    unsigned long long epoch = 0; bool last_pushed = false;
   } comm;
   // timing
   // timing: a ring of per-step event sets so a whole timed region can be read back afterwards
@@ -959,6 +967,33 @@ extern "C" int arap_aim_reload(arap_ctx* ctx) {
   return ARAP_OK;
 }
 
+// ---- epoch flags of the fused exchange (mode 1).  flags[r] = "rank r is about to push epoch e" (ready), flags[world + r] =
+// "rank r's pushes of epoch e have landed" (done); rank r writes its two words into every rank's array (its own included).
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+struct FlagPeers { unsigned long long* p[ARAP_MAX_PEERS + 1]; int n; };
+// signal word `slot` = epoch on every rank, then (wait_lo < wait_hi) wait until the local words [wait_lo, wait_hi) reached it
+__global__ void k_comm_flags(FlagPeers dst, int slot, unsigned long long epoch, const unsigned long long* local, int wait_lo, int wait_hi) {
+  const int t = threadIdx.x;
+  if (slot >= 0 && t < dst.n) { __threadfence_system(); st_release_sys(dst.p[t] + slot, epoch); }
+  for (int w = wait_lo + t; w < wait_hi; w += blockDim.x)
+    while (ld_acquire_sys(local + w) < epoch) __nanosleep(64);
+}
+
+static FlagPeers flag_targets(arap_ctx* ctx) {
+  FlagPeers f; f.n = 0;
+  for (int q = 0; q < ctx->comm.push.n; q++) f.p[f.n++] = ctx->comm.peer_flags[q];
+  f.p[f.n++] = ctx->comm.flags.p;
+  return f;
+}
+
+
 // ------------------------------------------------------------------ solve + apply
 extern "C" int arap_solve(arap_ctx* ctx, int on_center) {
   GRAPH_CHECK(ctx);
@@ -1038,10 +1073,26 @@ extern "C" int arap_apply(arap_ctx* ctx) {
   if (ctx->ev_release) { ARAP_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_release, 0)); ctx->ev_release = nullptr; }
   if (fused) {   // tolerance mode: end-point skinning + fit + SH rotation in one pass (end points of static Gaussians stay put)
     const RowTable& t = ctx->end_rows;
-    TRY(arapk_apply_union(ctx->N, ctx->node_xf32.p, t.gtile_cnt.p, t.gtile_nodes.p, t.uoff.p, t.woff.p, t.usw.p, t.unode.p, t.uw.p,
-                          ctx->ends.p, ctx->scale_backup.p, ctx->gs_static.p, ctx->pos.p, ctx->rot.p, ctx->scale.p, ctx->shs.p, st));
-  } else
+    arap_ctx::Comm& cm = ctx->comm;
+    const bool push = cm.mode == 1 && cm.nccl;
+    cm.last_pushed = push;
+    if (push) {   // ready handshake: every rank is past its consumers of the previous pose (see arap_comm_set_mode)
+      cm.epoch++;
+      k_comm_flags<<<1, 32, 0, st>>>(flag_targets(ctx), cm.rank, cm.epoch, cm.flags.p, 0, cm.world);
+      ARAP_KERNEL_CHECK();
+    }
+    TRY(arapk_apply_union_push(ctx->N, ctx->node_xf32.p, t.gtile_cnt.p, t.gtile_nodes.p, t.uoff.p, t.woff.p, t.usw.p, t.unode.p, t.uw.p,
+                               ctx->ends.p, ctx->scale_backup.p, ctx->gs_static.p, ctx->pos.p, ctx->rot.p, ctx->scale.p, ctx->shs.p,
+                               push ? &cm.push : nullptr, st));
+    if (push) {
+      FlagPeers f = flag_targets(ctx);
+      k_comm_flags<<<1, 32, 0, st>>>(f, cm.world + cm.rank, cm.epoch, cm.flags.p, 0, 0);
+      ARAP_KERNEL_CHECK();
+    }
+  } else {
+    ctx->comm.last_pushed = false;
     TRY(arapk_fit_gaussians(ctx->N, ctx->ends.p, ctx->scale_backup.p, ctx->gs_static.p, ctx->pos.p, ctx->rot.p, ctx->scale.p, ctx->shs.p, st));
+  }
   ARAP_CUDA_TRY(cudaEventRecord(ctx->ev_soa, st));
   if (tm) cudaEventRecord(ctx->ev[3], st);
   if (ctx->S > 0) TRY(lbs_family(ctx, ctx->sample_pos.p, ctx->sample_pos.p, ctx->sample_rows, ctx->sample_static.p, 1));
@@ -1214,6 +1265,61 @@ extern "C" int arap_comm_init(arap_ctx* ctx, const char id[128], int rank, int w
   return ARAP_OK;
 }
 
+// Mode 1: the exchange of a step is fused into its apply kernel (k_apply_union<PUSH>: peer stores of the tile's pos / rot / scale
+// into every other rank's gathered arrays, SURVEY 8(e) "fuse the gather into the apply kernel's epilogue via NVLink peer
+// stores").  Collective: every rank calls it after arap_comm_init.  The gathered arrays and a flag array are exported with
+// cudaIpc (one process per GPU on one node); a rank orders its pushes against the peers' consumers with two epoch flags per
+// rank instead of a collective: "ready" (written to all ranks on the ctx stream right before the apply kernel, after the
+// stream has waited for this rank's own consumers; the kernel starts when every rank is ready, i.e. nobody still reads the
+// previous pose) and "done" (written after the kernel; arap_comm_exchange waits for every rank's).  Needs lbs_mode = 3 (the
+// fused apply kernel); other modes keep using the all-gather.
+extern "C" int arap_comm_set_mode(arap_ctx* ctx, int mode) {
+  CTX_CHECK(ctx);
+  arap_ctx::Comm& cm = ctx->comm;
+  if (!cm.nccl) { set_error("comm_set_mode: arap_comm_init first"); return ARAP_ERR_STATE; }
+  if (mode != 0 && mode != 1) { set_error("comm_set_mode: mode must be 0 (all-gather) or 1 (fused peer stores)"); return ARAP_ERR_INVALID; }
+  if (mode == 0 || cm.mode == 1) { cm.mode = mode; return ARAP_OK; }
+  if (cm.world - 1 > ARAP_MAX_PEERS) { set_error("comm_set_mode: more than 8 ranks"); return ARAP_ERR_UNSUPPORTED; }
+  cudaStream_t st = ctx->stream;
+  const int W = cm.world;
+  TRY(cm.flags.alloc((size_t)2 * W));
+  ARAP_CUDA_TRY(cudaMemsetAsync(cm.flags.p, 0, (size_t)2 * W * sizeof(unsigned long long), st));
+  // all-gather the four IPC handles (64 bytes each) of every rank
+  struct Handles { cudaIpcMemHandle_t h[4]; };
+  static_assert(sizeof(Handles) == 256, "cudaIpcMemHandle_t is 64 bytes");
+  Handles mine;
+  void* bases[4] = {cm.pos_all.p, cm.rot_all.p, cm.scale_all.p, cm.flags.p};
+  for (int a = 0; a < 4; a++) ARAP_CUDA_TRY(cudaIpcGetMemHandle(&mine.h[a], bases[a]));
+  DBuf<float> hbuf; TRY(hbuf.alloc((size_t)W * 64));
+  ARAP_CUDA_TRY(cudaMemcpyAsync(hbuf.p + (size_t)cm.rank * 64, &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+  NCCL_TRY(g_nccl.AllGather(hbuf.p + (size_t)cm.rank * 64, hbuf.p, 64, kNcclFloat, cm.nccl, st));
+  std::vector<Handles> all((size_t)W);
+  ARAP_CUDA_TRY(cudaMemcpyAsync(all.data(), hbuf.p, (size_t)W * sizeof(Handles), cudaMemcpyDeviceToHost, st));
+  ARAP_CUDA_TRY(cudaStreamSynchronize(st));
+  const size_t n = (size_t)ctx->N;
+  int q = 0;
+  for (int r = 0; r < W; r++) {
+    if (r == cm.rank) continue;
+    void* m[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int a = 0; a < 4; a++) {
+      cudaError_t e = cudaIpcOpenMemHandle(&m[a], all[(size_t)r].h[a], cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) { set_error(std::string("comm_set_mode: cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); return ARAP_ERR_UNSUPPORTED; }
+    }
+    for (int a = 0; a < 3; a++) cm.ipc_base[a][q] = m[a];
+    cm.push.pos[q] = (float*)m[0] + (size_t)cm.rank * n * 3;
+    cm.push.rot[q] = (float*)m[1] + (size_t)cm.rank * n * 4;
+    cm.push.scale[q] = (float*)m[2] + (size_t)cm.rank * n * 3;
+    cm.peer_flags[q] = (unsigned long long*)m[3];
+    q++;
+  }
+  cm.push.n = q;
+  cm.epoch = 0;
+  // nobody pushes before everybody's flags are zeroed and mapped
+  NCCL_TRY(g_nccl.AllGather(hbuf.p + (size_t)cm.rank * 64, hbuf.p, 64, kNcclFloat, cm.nccl, st));
+  ARAP_CUDA_TRY(cudaStreamSynchronize(st));
+  cm.mode = 1;
+  return ARAP_OK;
+}
 // One exchange per drag step, after arap_step / arap_apply: asynchronous (side stream), ordered after the step's six-point fit;
 // the next arap_apply waits for it before it overwrites the SoA.
 extern "C" int arap_comm_exchange(arap_ctx* ctx) {
@@ -1222,6 +1328,13 @@ extern "C" int arap_comm_exchange(arap_ctx* ctx) {
   if (!cm.nccl) { set_error("comm_exchange: arap_comm_init first"); return ARAP_ERR_STATE; }
   const size_t n = (size_t)ctx->N;
   ARAP_CUDA_TRY(cudaStreamWaitEvent(cm.side, ctx->ev_soa, 0));
+  if (cm.mode == 1 && cm.last_pushed) {   // the poses were pushed by the apply kernels: wait until every rank's "done" flag reached this epoch
+    FlagPeers none; none.n = 0;
+    k_comm_flags<<<1, 32, 0, cm.side>>>(none, -1, cm.epoch, cm.flags.p, cm.world, 2 * cm.world);
+    ARAP_KERNEL_CHECK();
+    ARAP_CUDA_TRY(cudaEventRecord(cm.ev_done, cm.side));
+    return ARAP_OK;   // the next apply does not wait for this (it waits for the ranks' ready flags instead)
+  }
   NCCL_TRY(g_nccl.GroupStart());
   NCCL_TRY(g_nccl.AllGather(ctx->pos.p, cm.pos_all.p, n * 3, kNcclFloat, cm.nccl, cm.side));
   NCCL_TRY(g_nccl.AllGather(ctx->rot.p, cm.rot_all.p, n * 4, kNcclFloat, cm.nccl, cm.side));
@@ -1326,6 +1439,11 @@ extern "C" int arap_comm_view(arap_ctx* ctx, arap_gathered_view* o) {
 static void comm_destroy(arap_ctx* ctx) {
   arap_ctx::Comm& cm = ctx->comm;
   if (cm.side) { cudaStreamSynchronize(cm.side); }
+  for (int q = 0; q < cm.push.n; q++) {
+    for (int a = 0; a < 3; a++) if (cm.ipc_base[a][q]) { cudaIpcCloseMemHandle(cm.ipc_base[a][q]); cm.ipc_base[a][q] = nullptr; }
+    if (cm.peer_flags[q]) { cudaIpcCloseMemHandle(cm.peer_flags[q]); cm.peer_flags[q] = nullptr; }
+  }
+  cm.push.n = 0; cm.mode = 0;
   if (cm.nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(cm.nccl);
   if (cm.ev_done) cudaEventDestroy(cm.ev_done);
   if (cm.side) cudaStreamDestroy(cm.side);

@@ -143,6 +143,8 @@ def setup_session_sharded(pkg, scenes, workload, n_total, rank, world, stream, d
     t0 = time.perf_counter()
     s.set_gaussians(sc["pos"], sc["rot"], sc["scale"], sc["opacity"], sc["shs"])
     s.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+    if os.environ.get("ARAP_COMM_PUSH", "1") == "1" and world > 1:
+        s.comm_set_mode(1)            # the exchange fused into the apply kernel (peer stores over NVLink)
     gi = s.comm_grid_build()
     s.grid_eval(0)
     s.sync(); t_grid = time.perf_counter() - t0
@@ -226,6 +228,8 @@ def run_own(args):
             idt.copy_(torch.frombuffer(bytearray(pkg.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
         s.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+        if os.environ.get("ARAP_COMM_PUSH", "1") == "1":
+            s.comm_set_mode(1)        # the exchange fused into the apply kernel (peer stores over NVLink); ARAP_COMM_PUSH=0: NCCL all-gather
         abi_comm = True
     elif world > 1:   # first-round variants through torch.distributed (parallel.py): whole-SoA NCCL gather, peer stores, pose + eager SH replay
         par = importlib.import_module(ge.PKG + ".parallel")
@@ -395,7 +399,7 @@ def run_own(args):
         side_s = torch.cuda.ExternalStream(gv.side_stream)
         m0e, m1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         m0e.record(side_s); s.comm_materialize_sh(); m1e.record(side_s); s.comm_sync()
-        exchange = {"per_step": "in-place grouped ncclAllGather of pos/rot/scale (40 B x %d Gaussians received per rank)" % (N * (world - 1)),
+        exchange = {"per_step": ("peer stores from the apply kernel's epilogue" if os.environ.get("ARAP_COMM_PUSH", "1") == "1" and world > 1 else "in-place grouped ncclAllGather of pos/rot/scale") + " (40 B x %d Gaussians received per rank)" % (N * (world - 1)),
                     "materialize_remote_sh_ms": round(m0e.elapsed_time(m1e), 3), "remote_rows": N * (world - 1)}
         if os.environ.get("ARAP_GATHER_CHECK"):   # the gathered copy against a full all-gather of the owners' arrays
             par = importlib.import_module(ge.PKG + ".parallel")
@@ -451,7 +455,7 @@ def run_own(args):
                    "active_nodes": setup["n_active"], "pinned_nodes": setup["n_pinned"], "lbs_mode": lbs_mode,
                    "l2": "inputs (>1.4 GB SoA + tables per step) exceed the 126 MB L2",
                    **({"sharded_scene": {"x_slab_of_rank0": setup["slab"], "what": "ONE scene; rank r holds part r of its global cell order, the grid is built over all ranks' Gaussians (gathered arrays) and every rank bins / evaluates / advects only its x-slab of cells (arap_comm_grid_build); total work is fixed as N grows"}} if sharded else {}),
-                   "parallelism": ("replicated solve, Gaussians/samples sharded by index; every step all ranks exchange the deformed Gaussians through the C ABI (arap_comm_exchange): in-place grouped NCCL all-gather of pos/rot/scale on a high-priority side stream, started when the six-point fit is done (overlaps the sample passes); remote SH rows are rotated on demand (arap_comm_materialize_sh, timed in `exchange`)" if abi_comm else "replicated solve, Gaussians/samples sharded by index; exchange variant ARAP_GATHER=" + gmode) if world > 1 else "single GPU"},
+                   "parallelism": (("replicated solve, Gaussians/samples sharded by index; every step all ranks exchange the deformed Gaussians through the C ABI, FUSED into the apply kernel (arap_comm_set_mode(1): each tile's final pos/rot/scale is stored straight into the peers' gathered arrays over NVLink, cudaIpc mappings, epoch flags instead of a collective); remote SH rows are rotated on demand (arap_comm_materialize_sh, timed in `exchange`)" if os.environ.get("ARAP_COMM_PUSH", "1") == "1" else "replicated solve, Gaussians/samples sharded by index; every step all ranks exchange the deformed Gaussians through the C ABI (arap_comm_exchange): in-place grouped NCCL all-gather of pos/rot/scale on a high-priority side stream, started when the six-point fit is done (overlaps the sample passes); remote SH rows are rotated on demand (arap_comm_materialize_sh, timed in `exchange`)") if abi_comm else "replicated solve, Gaussians/samples sharded by index; exchange variant ARAP_GATHER=" + gmode) if world > 1 else "single GPU"},
         "stages_ms": {"solve": round(float(mean[0]), 4), "sample_advect": round(float(mean[1]), 4), "endpoint_lbs": round(float(mean[2]), 4),
                       "six_point_fit": round(float(mean[3]), 4), "sample_sh_rotate": round(float(mean[4]), 4),
                       "note": "lbs_mode = 3: end-point skinning is fused into six_point_fit (k_apply_union); endpoint_lbs is then the node / mesh-point pass only" if lbs_mode == 3 else ""},

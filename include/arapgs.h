@@ -312,6 +312,12 @@ int arap_comm_destroy(arap_ctx* ctx);
  * The samples, their skinning tables, the per-step sample passes and the stroke-end rebuild (arap_grid_update_lists: call
  * arap_comm_exchange after the last step first) then cover that slab only; the union over the ranks is the single-GPU grid. */
 int arap_comm_grid_build(arap_ctx* ctx, int x_lo, int x_hi);
+/* mode 0 (default): arap_comm_exchange is an in-place NCCL all-gather.  mode 1: the exchange is FUSED into the apply kernel —
+ * every tile's final pos / rot / scale is stored straight into the other ranks' gathered arrays over NVLink (peer mappings via
+ * cudaIpc: one process per GPU, one node, <= 8 ranks), ordered by per-rank epoch flags instead of a collective; arap_comm_exchange
+ * then only waits for the ranks' "done" flags.  Collective (call on every rank after arap_comm_init); needs lbs_mode = 3.
+ * Like the all-gather it requires every rank to run the same sequence of arap_step / arap_apply calls. */
+int arap_comm_set_mode(arap_ctx* ctx, int mode);
 int arap_comm_slab_get(arap_ctx* ctx, int* x_lo, int* x_hi);
 
 /* ---- deform.txt / graph.obj / config / scripts (host IO, byte-compatible) -- */

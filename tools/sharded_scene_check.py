@@ -88,6 +88,44 @@ def main():
           f"rest state bit-identical; stroke end: lists identical, field max abs diff {err:.2e}; union {int(tot[0])} = {gi['valid_cells']} cells, "
           f"pairs {int(tot[1])} vs {gi['pairs']} single-GPU", flush=True)
     s.close(); full.close()
+
+    # ---- transport check: the exchange fused into the apply kernel (arap_comm_set_mode(1): peer stores over NVLink, epoch flags)
+    # against the NCCL all-gather, both on the fused tolerance-mode apply (lbs_mode 3): gathered arrays, stroke-end lists and
+    # field must be identical bit for bit — only the transport differs.
+    par = importlib.import_module(ge.PKG + ".parallel")
+
+    def run(mode):
+        t = pkg.Session(device=local, lbs_mode=3, **kw)
+        t.set_gaussians(own["pos"], own["rot"], own["scale"], own["opacity"], own["shs"])
+        ib = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            ib.copy_(torch.frombuffer(bytearray(pkg.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(ib, 0)
+        t.comm_init(bytes(ib.cpu().numpy().tobytes()), rank, world)
+        t.comm_set_mode(mode)
+        t.comm_grid_build(); t.grid_eval(0)
+        t.set_mesh_points(g["node_pos"], True); t.graph_build_fps(); t.set_blocks(blocks, types)
+        for step in range(5):
+            t.aim_translate([0.0, 0.01, 0.02]); t.step(False); t.comm_exchange()
+            if step == 2:                       # a consumer of remote rows in mid-stroke: the next pushes must wait for it
+                t.comm_materialize_sh()
+        t.comm_sync()
+        gv = t.comm_view()
+        got = {name: torch.as_tensor(par.DevArray(getattr(gv, name), (m * world, w)), device="cuda").clone().cpu().numpy() for name, w in (("pos", 3), ("rot", 4), ("scale", 3))}
+        t.grid_update_lists(); t.grid_eval(1)
+        dg = t.download_grid(); ff, oo = t.download_features(1)
+        t.sync(); dist.barrier()
+        t.close()
+        return got, dg, ff, oo
+    a_got, a_dg, a_f, a_o = run(0)
+    b_got, b_dg, b_f, b_o = run(1)
+    for kk in a_got:
+        assert np.array_equal(a_got[kk], b_got[kk]), ("gathered", kk)
+        assert not np.array_equal(a_got[kk][(1 - rank) * m:(2 - rank) * m] if world == 2 else a_got[kk], ordered[kk][(1 - rank) * m:(2 - rank) * m] if world == 2 else ordered[kk]), "remote range did not move"
+    for kk in ("valid", "prefix", "lists", "sample_pos"):
+        assert np.array_equal(a_dg[kk], b_dg[kk]), ("stroke-end grid", kk)
+    assert np.array_equal(a_f, b_f) and np.array_equal(a_o, b_o), "stroke-end field"
+    print(f"rank {rank}/{world}: fused peer-store exchange == NCCL all-gather (gathered pos / rot / scale after 5 steps, stroke-end lists and field: bit-identical)", flush=True)
     dist.destroy_process_group()
 
 
