@@ -25,8 +25,8 @@ NVCC_FLAGS = [*ARCH, "-lineinfo", "-O3", "-std=c++17", "-fmad=false", "-Xcompile
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off"]
 
 CU = ["apply.cu", "knn.cu", "solve.cu", "solve_smem.cu", "solve_pipe.cu", "grid.cu", "session.cu"]
-CPP = ["host_io.cpp"]
-HEADERS = ["common.cuh", "device_math.cuh", "sh_fast.cuh", "solve_dev.h", "solve_smem_dev.cuh", "kernels.h", "session.h", "../../include/arapgs.h", "../../include/arapgs_kernels.h"]
+CPP = ["host_io.cpp", "mcast.cpp"]
+HEADERS = ["common.cuh", "device_math.cuh", "sh_fast.cuh", "solve_dev.h", "solve_smem_dev.cuh", "kernels.h", "session.h", "mcast.h", "../../include/arapgs.h", "../../include/arapgs_kernels.h"]
 
 
 def _stale(src: Path, obj: Path) -> bool:

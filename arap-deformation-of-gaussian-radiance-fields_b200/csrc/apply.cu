@@ -737,7 +737,15 @@ __global__ void k_words_of_rows(long long n, const int* __restrict__ rows, int* 
 // coalesced 16-byte stores — straight into every peer's gathered arrays over NVLink (peer pointers from cudaIpc, see
 // arap_comm_set_mode), so the exchange of the deformed Gaussians rides inside the apply pass instead of following it as a
 // collective.  Static Gaussians are copied too (their values have not changed: same bits on both sides).
-template <bool PUSH>
+// PUSH = 2: one store per value into the NVSwitch multicast mapping of the gathered arrays (multimem.st: the switch replicates it
+// into every rank's copy, this rank's included) — NVLink egress of 40 bytes per Gaussian whatever the number of ranks.
+__device__ __forceinline__ void multimem_st(float* p, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void multimem_st(float* p, float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+template <int PUSH>
 __global__ void __launch_bounds__(FIT_TILE, 4)
 k_apply_union(long long N, const NodeXf32* __restrict__ nodes, const uint16_t* __restrict__ gtile_cnt,
               const uint16_t* __restrict__ gtile_nodes, const int* __restrict__ uoff, const int* __restrict__ woff,
@@ -915,12 +923,14 @@ k_apply_union(long long N, const NodeXf32* __restrict__ nodes, const uint16_t* _
       for (int c = tid; c < n4; c += FIT_TILE) {
         const float4 v = __ldcg(reinterpret_cast<const float4*>(own + o) + c);
 #pragma unroll
-        for (int q = 0; q < ARAP_MAX_PEERS; q++) if (q < pp.n) reinterpret_cast<float4*>(peer[q] + o)[c] = v;
+        for (int q = 0; q < ARAP_MAX_PEERS; q++)
+          if (q < pp.n) { if (PUSH == 2) multimem_st(peer[q] + o + 4 * c, v); else reinterpret_cast<float4*>(peer[q] + o)[c] = v; }
       }
       for (int c = n4 * 4 + tid; c < nf; c += FIT_TILE) {
         const float v = __ldcg(own + o + c);
 #pragma unroll
-        for (int q = 0; q < ARAP_MAX_PEERS; q++) if (q < pp.n) peer[q][o + c] = v;
+        for (int q = 0; q < ARAP_MAX_PEERS; q++)
+          if (q < pp.n) { if (PUSH == 2) multimem_st(peer[q] + o + c, v); else peer[q][o + c] = v; }
       }
     };
     push(pos, pp.pos, 3); push(rot, pp.rot, 4); push(scale, pp.scale, 3);
@@ -1585,17 +1595,22 @@ extern "C" int arapk_apply_union_push(long long N, const void* node_xf32, const 
   const size_t smem = sizeof(float4) * FIT_TILE * FIT_PITCH4 + sizeof(float) * FIT_TILE * END_PITCH + sizeof(float4) * GT_CAP * 3;
   static bool attr_set = false;
   if (!attr_set) {
-    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_apply_union<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_apply_union<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_apply_union<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_apply_union<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_apply_union<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   ArapPeerPush pp{};
-  if (peers && peers->n > 0) {
+  if (peers && peers->n > 0 && peers->multicast) {
     pp = *peers;
-    k_apply_union<true><<<(unsigned)arapk_gtile_count(N), FIT_TILE, smem, st>>>(N, (const NodeXf32*)node_xf32, gtile_cnt, gtile_nodes, uoff, woff, usw,
-                                                                              unode, uw, ends, scale_backup, is_static, pos, rot, scale, shs, pp);
+    k_apply_union<2><<<(unsigned)arapk_gtile_count(N), FIT_TILE, smem, st>>>(N, (const NodeXf32*)node_xf32, gtile_cnt, gtile_nodes, uoff, woff, usw,
+                                                                           unode, uw, ends, scale_backup, is_static, pos, rot, scale, shs, pp);
+  } else if (peers && peers->n > 0) {
+    pp = *peers;
+    k_apply_union<1><<<(unsigned)arapk_gtile_count(N), FIT_TILE, smem, st>>>(N, (const NodeXf32*)node_xf32, gtile_cnt, gtile_nodes, uoff, woff, usw,
+                                                                           unode, uw, ends, scale_backup, is_static, pos, rot, scale, shs, pp);
   } else
-    k_apply_union<false><<<(unsigned)arapk_gtile_count(N), FIT_TILE, smem, st>>>(N, (const NodeXf32*)node_xf32, gtile_cnt, gtile_nodes, uoff, woff, usw,
+    k_apply_union<0><<<(unsigned)arapk_gtile_count(N), FIT_TILE, smem, st>>>(N, (const NodeXf32*)node_xf32, gtile_cnt, gtile_nodes, uoff, woff, usw,
                                                                                unode, uw, ends, scale_backup, is_static, pos, rot, scale, shs, pp);
   ARAP_KERNEL_CHECK();
   return ARAP_OK;

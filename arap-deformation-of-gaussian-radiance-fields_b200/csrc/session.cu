@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "session.h"
+#include "mcast.h"
 
 namespace arapgs {
 
@@ -207,8 +208,9 @@ struct arap_ctx {
     ArapPeerPush push{};                                  // peers' gathered arrays, offset to this rank's range
     void* ipc_base[3][ARAP_MAX_PEERS] = {{nullptr}};      // what cudaIpcOpenMemHandle returned (for the close)
     DBuf<unsigned long long> flags;                       // [2 * world]: ready[r], done[r] written by rank r
-    unsigned long long* peer_flags[ARAP_MAX_PEERS] = {nullptr};
+    unsigned long long* peer_flags[ARAP_MAX_PEERS] = {nullptr}; int n_flag_peers = 0;
     unsigned long long epoch = 0; bool last_pushed = false;
+    Mcast mcast;                                          // mode 2: the gathered pose arrays live in NVSwitch multicast memory
   } comm;
   // timing
   // timing: a ring of per-step event sets so a whole timed region can be read back afterwards
@@ -988,7 +990,7 @@ __global__ void k_comm_flags(FlagPeers dst, int slot, unsigned long long epoch, 
 
 static FlagPeers flag_targets(arap_ctx* ctx) {
   FlagPeers f; f.n = 0;
-  for (int q = 0; q < ctx->comm.push.n; q++) f.p[f.n++] = ctx->comm.peer_flags[q];
+  for (int q = 0; q < ctx->comm.n_flag_peers; q++) f.p[f.n++] = ctx->comm.peer_flags[q];
   f.p[f.n++] = ctx->comm.flags.p;
   return f;
 }
@@ -1074,7 +1076,7 @@ extern "C" int arap_apply(arap_ctx* ctx) {
   if (fused) {   // tolerance mode: end-point skinning + fit + SH rotation in one pass (end points of static Gaussians stay put)
     const RowTable& t = ctx->end_rows;
     arap_ctx::Comm& cm = ctx->comm;
-    const bool push = cm.mode == 1 && cm.nccl;
+    const bool push = cm.mode >= 1 && cm.nccl && cm.push.n > 0;
     cm.last_pushed = push;
     if (push) {   // ready handshake: every rank is past its consumers of the previous pose (see arap_comm_set_mode)
       cm.epoch++;
@@ -1277,49 +1279,95 @@ extern "C" int arap_comm_set_mode(arap_ctx* ctx, int mode) {
   CTX_CHECK(ctx);
   arap_ctx::Comm& cm = ctx->comm;
   if (!cm.nccl) { set_error("comm_set_mode: arap_comm_init first"); return ARAP_ERR_STATE; }
-  if (mode != 0 && mode != 1) { set_error("comm_set_mode: mode must be 0 (all-gather) or 1 (fused peer stores)"); return ARAP_ERR_INVALID; }
-  if (mode == 0 || cm.mode == 1) { cm.mode = mode; return ARAP_OK; }
+  if (mode < 0 || mode > 2) { set_error("comm_set_mode: mode must be 0 (all-gather), 1 (fused peer stores) or 2 (fused multicast stores)"); return ARAP_ERR_INVALID; }
+  if (mode == cm.mode) return ARAP_OK;
+  if (mode == 0) { cm.mode = 0; return ARAP_OK; }   // mappings stay; the exchange is the all-gather again
+  if (cm.mode != 0 || cm.flags.p) { set_error("comm_set_mode: the fused modes can only be entered once, from mode 0"); return ARAP_ERR_STATE; }
   if (cm.world - 1 > ARAP_MAX_PEERS) { set_error("comm_set_mode: more than 8 ranks"); return ARAP_ERR_UNSUPPORTED; }
   cudaStream_t st = ctx->stream;
   const int W = cm.world;
+  const size_t n = (size_t)ctx->N;
+  DBuf<float> hbuf; TRY(hbuf.alloc((size_t)W * 64));
+  auto gather64 = [&](const void* mine256, void* all) -> int {   // all-gather of 256 bytes per rank through NCCL (host in, host out)
+    ARAP_CUDA_TRY(cudaMemcpyAsync(hbuf.p + (size_t)cm.rank * 64, mine256, 256, cudaMemcpyHostToDevice, st));
+    NCCL_TRY(g_nccl.AllGather(hbuf.p + (size_t)cm.rank * 64, hbuf.p, 64, kNcclFloat, cm.nccl, st));
+    ARAP_CUDA_TRY(cudaMemcpyAsync(all, hbuf.p, (size_t)W * 256, cudaMemcpyDeviceToHost, st));
+    ARAP_CUDA_TRY(cudaStreamSynchronize(st));
+    return ARAP_OK;
+  };
+  struct Blob { char b[256]; };
+  std::vector<Blob> all((size_t)W);
+  if (mode == 2) {
+    // ---- the three gathered pose arrays move into one multicast-bound allocation (same layout on every rank)
+    Blob mine; memset(&mine, 0, sizeof(mine));
+    int ok = mcast_supported(ctx->device) ? 1 : 0;
+    const size_t o_pos = 0, o_rot = ((W * n * 3 * 4 + 255) / 256) * 256, o_scale = o_rot + ((W * n * 4 * 4 + 255) / 256) * 256;
+    const size_t bytes = o_scale + W * n * 3 * 4;
+    size_t size = 0;
+    if (ok && mcast_size(bytes, W, ctx->device, &size) != ARAP_OK) ok = 0;
+    char name[ARAP_MCAST_NAME] = {0};
+    if (ok && cm.rank == 0 && mcast_root_begin(&cm.mcast, size, W, name) != ARAP_OK) ok = 0;
+    mine.b[0] = (char)ok; memcpy(mine.b + 8, name, ARAP_MCAST_NAME);
+    const std::string why = arap_last_error();
+    TRY(gather64(&mine, all.data()));
+    for (int r = 0; r < W; r++) if (!all[(size_t)r].b[0]) { mcast_destroy(&cm.mcast); set_error("comm_set_mode: NVSwitch multicast unavailable on rank " + std::to_string(r) + (ok ? "" : " (" + why + ")")); return ARAP_ERR_UNSUPPORTED; }
+    int rc = cm.rank == 0 ? mcast_root_serve(&cm.mcast, W - 1) : mcast_peer_join(&cm.mcast, size, all[0].b + 8);
+    if (rc == ARAP_OK) rc = mcast_bind_and_map(&cm.mcast, ctx->device);
+    mine.b[0] = (char)(rc == ARAP_OK);
+    const std::string why2 = arap_last_error();
+    TRY(gather64(&mine, all.data()));
+    for (int r = 0; r < W; r++) if (!all[(size_t)r].b[0]) { mcast_destroy(&cm.mcast); set_error("comm_set_mode: multicast set-up failed on rank " + std::to_string(r) + (rc == ARAP_OK ? "" : " (" + why2 + ")")); return ARAP_ERR_UNSUPPORTED; }
+    char* L = (char*)cm.mcast.local;
+    ARAP_CUDA_TRY(cudaMemcpyAsync(L + o_pos, cm.pos_all.p, W * n * 3 * 4, cudaMemcpyDeviceToDevice, st));
+    ARAP_CUDA_TRY(cudaMemcpyAsync(L + o_rot, cm.rot_all.p, W * n * 4 * 4, cudaMemcpyDeviceToDevice, st));
+    ARAP_CUDA_TRY(cudaMemcpyAsync(L + o_scale, cm.scale_all.p, W * n * 3 * 4, cudaMemcpyDeviceToDevice, st));
+    ARAP_CUDA_TRY(cudaStreamSynchronize(st));
+    cm.pos_all.view((float*)(L + o_pos), W * n * 3); cm.rot_all.view((float*)(L + o_rot), W * n * 4); cm.scale_all.view((float*)(L + o_scale), W * n * 3);
+    ctx->pos.view(cm.pos_all.p + (size_t)cm.rank * n * 3, n * 3); ctx->rot.view(cm.rot_all.p + (size_t)cm.rank * n * 4, n * 4);
+    ctx->scale.view(cm.scale_all.p + (size_t)cm.rank * n * 3, n * 3);
+    char* Mc = (char*)cm.mcast.mc_ptr;
+    cm.push.n = 1; cm.push.multicast = 1;
+    cm.push.pos[0] = (float*)(Mc + o_pos) + (size_t)cm.rank * n * 3;
+    cm.push.rot[0] = (float*)(Mc + o_rot) + (size_t)cm.rank * n * 4;
+    cm.push.scale[0] = (float*)(Mc + o_scale) + (size_t)cm.rank * n * 3;
+  }
+  // ---- epoch flags (and, mode 1, the pose arrays) exported with cudaIpc
   TRY(cm.flags.alloc((size_t)2 * W));
   ARAP_CUDA_TRY(cudaMemsetAsync(cm.flags.p, 0, (size_t)2 * W * sizeof(unsigned long long), st));
-  // all-gather the four IPC handles (64 bytes each) of every rank
   struct Handles { cudaIpcMemHandle_t h[4]; };
   static_assert(sizeof(Handles) == 256, "cudaIpcMemHandle_t is 64 bytes");
-  Handles mine;
+  Handles mineh; memset(&mineh, 0, sizeof(mineh));
   void* bases[4] = {cm.pos_all.p, cm.rot_all.p, cm.scale_all.p, cm.flags.p};
-  for (int a = 0; a < 4; a++) ARAP_CUDA_TRY(cudaIpcGetMemHandle(&mine.h[a], bases[a]));
-  DBuf<float> hbuf; TRY(hbuf.alloc((size_t)W * 64));
-  ARAP_CUDA_TRY(cudaMemcpyAsync(hbuf.p + (size_t)cm.rank * 64, &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
-  NCCL_TRY(g_nccl.AllGather(hbuf.p + (size_t)cm.rank * 64, hbuf.p, 64, kNcclFloat, cm.nccl, st));
-  std::vector<Handles> all((size_t)W);
-  ARAP_CUDA_TRY(cudaMemcpyAsync(all.data(), hbuf.p, (size_t)W * sizeof(Handles), cudaMemcpyDeviceToHost, st));
-  ARAP_CUDA_TRY(cudaStreamSynchronize(st));
-  const size_t n = (size_t)ctx->N;
+  const int first = mode == 2 ? 3 : 0;
+  for (int a = first; a < 4; a++) ARAP_CUDA_TRY(cudaIpcGetMemHandle(&mineh.h[a], bases[a]));
+  TRY(gather64(&mineh, all.data()));
   int q = 0;
   for (int r = 0; r < W; r++) {
     if (r == cm.rank) continue;
+    const Handles& hr = *reinterpret_cast<const Handles*>(all[(size_t)r].b);
     void* m[4] = {nullptr, nullptr, nullptr, nullptr};
-    for (int a = 0; a < 4; a++) {
-      cudaError_t e = cudaIpcOpenMemHandle(&m[a], all[(size_t)r].h[a], cudaIpcMemLazyEnablePeerAccess);
+    for (int a = first; a < 4; a++) {
+      cudaError_t e = cudaIpcOpenMemHandle(&m[a], hr.h[a], cudaIpcMemLazyEnablePeerAccess);
       if (e != cudaSuccess) { set_error(std::string("comm_set_mode: cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); return ARAP_ERR_UNSUPPORTED; }
     }
-    for (int a = 0; a < 3; a++) cm.ipc_base[a][q] = m[a];
-    cm.push.pos[q] = (float*)m[0] + (size_t)cm.rank * n * 3;
-    cm.push.rot[q] = (float*)m[1] + (size_t)cm.rank * n * 4;
-    cm.push.scale[q] = (float*)m[2] + (size_t)cm.rank * n * 3;
+    if (mode == 1) {
+      for (int a = 0; a < 3; a++) cm.ipc_base[a][q] = m[a];
+      cm.push.pos[q] = (float*)m[0] + (size_t)cm.rank * n * 3;
+      cm.push.rot[q] = (float*)m[1] + (size_t)cm.rank * n * 4;
+      cm.push.scale[q] = (float*)m[2] + (size_t)cm.rank * n * 3;
+    }
     cm.peer_flags[q] = (unsigned long long*)m[3];
     q++;
   }
-  cm.push.n = q;
+  cm.n_flag_peers = q;
+  if (mode == 1) { cm.push.n = q; cm.push.multicast = 0; }
   cm.epoch = 0;
-  // nobody pushes before everybody's flags are zeroed and mapped
-  NCCL_TRY(g_nccl.AllGather(hbuf.p + (size_t)cm.rank * 64, hbuf.p, 64, kNcclFloat, cm.nccl, st));
-  ARAP_CUDA_TRY(cudaStreamSynchronize(st));
-  cm.mode = 1;
+  Blob sync; memset(&sync, 0, sizeof(sync));
+  TRY(gather64(&sync, all.data()));   // nobody pushes before everybody's flags are zeroed and mapped
+  cm.mode = mode;
   return ARAP_OK;
 }
+
 // One exchange per drag step, after arap_step / arap_apply: asynchronous (side stream), ordered after the step's six-point fit;
 // the next arap_apply waits for it before it overwrites the SoA.
 extern "C" int arap_comm_exchange(arap_ctx* ctx) {
@@ -1328,7 +1376,7 @@ extern "C" int arap_comm_exchange(arap_ctx* ctx) {
   if (!cm.nccl) { set_error("comm_exchange: arap_comm_init first"); return ARAP_ERR_STATE; }
   const size_t n = (size_t)ctx->N;
   ARAP_CUDA_TRY(cudaStreamWaitEvent(cm.side, ctx->ev_soa, 0));
-  if (cm.mode == 1 && cm.last_pushed) {   // the poses were pushed by the apply kernels: wait until every rank's "done" flag reached this epoch
+  if (cm.mode >= 1 && cm.last_pushed) {   // the poses were pushed by the apply kernels: wait until every rank's "done" flag reached this epoch
     FlagPeers none; none.n = 0;
     k_comm_flags<<<1, 32, 0, cm.side>>>(none, -1, cm.epoch, cm.flags.p, cm.world, 2 * cm.world);
     ARAP_KERNEL_CHECK();
@@ -1439,11 +1487,13 @@ extern "C" int arap_comm_view(arap_ctx* ctx, arap_gathered_view* o) {
 static void comm_destroy(arap_ctx* ctx) {
   arap_ctx::Comm& cm = ctx->comm;
   if (cm.side) { cudaStreamSynchronize(cm.side); }
-  for (int q = 0; q < cm.push.n; q++) {
+  for (int q = 0; q < ARAP_MAX_PEERS; q++) {
     for (int a = 0; a < 3; a++) if (cm.ipc_base[a][q]) { cudaIpcCloseMemHandle(cm.ipc_base[a][q]); cm.ipc_base[a][q] = nullptr; }
     if (cm.peer_flags[q]) { cudaIpcCloseMemHandle(cm.peer_flags[q]); cm.peer_flags[q] = nullptr; }
   }
-  cm.push.n = 0; cm.mode = 0;
+  cm.push.n = 0; cm.n_flag_peers = 0; cm.mode = 0;
+  // mode 2: the session's pose arrays live in the multicast-bound allocation; it stays mapped (the session keeps working on one GPU)
+  // and is returned to the driver at process exit
   if (cm.nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(cm.nccl);
   if (cm.ev_done) cudaEventDestroy(cm.ev_done);
   if (cm.side) cudaStreamDestroy(cm.side);

@@ -128,6 +128,21 @@ def setup_session(pkg, scenes, workload, n, rank, world, stream):
                                                                  **{k2: st_graph[k2] for k2 in ("fps", "node_graph", "knn_ends", "knn_samples", "tile_tables")}})
 
 
+def set_exchange_mode(s):
+    """ARAP_COMM_PUSH = 2 (default): the exchange fused into the apply kernel with NVSwitch multicast stores, falling back to unicast
+    peer stores (1) where the platform has no multicast; 1: peer stores; 0: NCCL all-gather.  Returns the mode in effect."""
+    want = int(os.environ.get("ARAP_COMM_PUSH", "2"))
+    for mode in ([2, 1] if want == 2 else [want]):
+        if mode == 0:
+            return 0
+        try:
+            s.comm_set_mode(mode)
+            return mode
+        except Exception as e:      # collective outcome: every rank fails alike
+            print(f"bench: exchange mode {mode} unavailable ({e})", file=sys.stderr, flush=True)
+    return 0
+
+
 def setup_session_sharded(pkg, scenes, workload, n_total, rank, world, stream, dist, torch):
     """BASELINE configs[4]: ONE scene of n_total Gaussians, rank r holds the contiguous part r of its global cell order; the grid
     is built over everybody's Gaussians and each rank bins / evaluates its x-slab of cells (arap_comm_grid_build)."""
@@ -143,8 +158,7 @@ def setup_session_sharded(pkg, scenes, workload, n_total, rank, world, stream, d
     t0 = time.perf_counter()
     s.set_gaussians(sc["pos"], sc["rot"], sc["scale"], sc["opacity"], sc["shs"])
     s.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
-    if os.environ.get("ARAP_COMM_PUSH", "1") == "1" and world > 1:
-        s.comm_set_mode(1)            # the exchange fused into the apply kernel (peer stores over NVLink)
+    xmode = set_exchange_mode(s) if world > 1 else 0
     gi = s.comm_grid_build()
     s.grid_eval(0)
     s.sync(); t_grid = time.perf_counter() - t0
@@ -164,7 +178,7 @@ def setup_session_sharded(pkg, scenes, workload, n_total, rank, world, stream, d
     blocks, types = scenes.cap_blocks(g["node_pos"])
     s.set_blocks(blocks, types)
     lo, hi = s.comm_slab()
-    return s, sc, gi, dict(t_grid_s=t_grid, t_graph_s=t_graph, n_active=len(blocks[0]), n_pinned=len(blocks[1]), active=blocks[0], slab=[lo, hi],
+    return s, sc, gi, dict(t_grid_s=t_grid, t_graph_s=t_graph, n_active=len(blocks[0]), n_pinned=len(blocks[1]), active=blocks[0], slab=[lo, hi], xmode=xmode,
                            blocks=blocks, types=types, stage_ms={**{k2: st_grid[k2] for k2 in ("scene_aabb", "cell_assign", "reorder", "footprint_lists", "samples", "grid_eval")},
                                                                  **{k2: st_graph[k2] for k2 in ("fps", "node_graph", "knn_ends", "knn_samples", "tile_tables")}})
 
@@ -228,8 +242,7 @@ def run_own(args):
             idt.copy_(torch.frombuffer(bytearray(pkg.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
         s.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
-        if os.environ.get("ARAP_COMM_PUSH", "1") == "1":
-            s.comm_set_mode(1)        # the exchange fused into the apply kernel (peer stores over NVLink); ARAP_COMM_PUSH=0: NCCL all-gather
+        setup["xmode"] = set_exchange_mode(s)
         abi_comm = True
     elif world > 1:   # first-round variants through torch.distributed (parallel.py): whole-SoA NCCL gather, peer stores, pose + eager SH replay
         par = importlib.import_module(ge.PKG + ".parallel")
@@ -399,7 +412,7 @@ def run_own(args):
         side_s = torch.cuda.ExternalStream(gv.side_stream)
         m0e, m1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         m0e.record(side_s); s.comm_materialize_sh(); m1e.record(side_s); s.comm_sync()
-        exchange = {"per_step": ("peer stores from the apply kernel's epilogue" if os.environ.get("ARAP_COMM_PUSH", "1") == "1" and world > 1 else "in-place grouped ncclAllGather of pos/rot/scale") + " (40 B x %d Gaussians received per rank)" % (N * (world - 1)),
+        exchange = {"per_step": {2: "NVSwitch multicast stores from the apply kernel's epilogue", 1: "peer stores from the apply kernel's epilogue", 0: "in-place grouped ncclAllGather of pos/rot/scale"}[setup.get("xmode", 0)] + " (40 B x %d Gaussians received per rank)" % (N * (world - 1)),
                     "materialize_remote_sh_ms": round(m0e.elapsed_time(m1e), 3), "remote_rows": N * (world - 1)}
         if os.environ.get("ARAP_GATHER_CHECK"):   # the gathered copy against a full all-gather of the owners' arrays
             par = importlib.import_module(ge.PKG + ".parallel")
@@ -455,7 +468,7 @@ def run_own(args):
                    "active_nodes": setup["n_active"], "pinned_nodes": setup["n_pinned"], "lbs_mode": lbs_mode,
                    "l2": "inputs (>1.4 GB SoA + tables per step) exceed the 126 MB L2",
                    **({"sharded_scene": {"x_slab_of_rank0": setup["slab"], "what": "ONE scene; rank r holds part r of its global cell order, the grid is built over all ranks' Gaussians (gathered arrays) and every rank bins / evaluates / advects only its x-slab of cells (arap_comm_grid_build); total work is fixed as N grows"}} if sharded else {}),
-                   "parallelism": (("replicated solve, Gaussians/samples sharded by index; every step all ranks exchange the deformed Gaussians through the C ABI, FUSED into the apply kernel (arap_comm_set_mode(1): each tile's final pos/rot/scale is stored straight into the peers' gathered arrays over NVLink, cudaIpc mappings, epoch flags instead of a collective); remote SH rows are rotated on demand (arap_comm_materialize_sh, timed in `exchange`)" if os.environ.get("ARAP_COMM_PUSH", "1") == "1" else "replicated solve, Gaussians/samples sharded by index; every step all ranks exchange the deformed Gaussians through the C ABI (arap_comm_exchange): in-place grouped NCCL all-gather of pos/rot/scale on a high-priority side stream, started when the six-point fit is done (overlaps the sample passes); remote SH rows are rotated on demand (arap_comm_materialize_sh, timed in `exchange`)") if abi_comm else "replicated solve, Gaussians/samples sharded by index; exchange variant ARAP_GATHER=" + gmode) if world > 1 else "single GPU"},
+                   "parallelism": (("replicated solve, Gaussians/samples sharded by index; every step all ranks exchange the deformed Gaussians through the C ABI, " + {2: "FUSED into the apply kernel (arap_comm_set_mode(2): one multimem.st per value into an NVSwitch multicast mapping of the gathered arrays, replicated by the switch into every rank; epoch flags instead of a collective)", 1: "FUSED into the apply kernel (arap_comm_set_mode(1): each tile's final pos/rot/scale is stored straight into the peers' gathered arrays over NVLink, cudaIpc mappings, epoch flags instead of a collective)", 0: "as an in-place grouped NCCL all-gather of pos/rot/scale on a high-priority side stream, started when the six-point fit is done (overlaps the sample passes)"}[setup.get("xmode", 0)] + "; remote SH rows are rotated on demand (arap_comm_materialize_sh, timed in `exchange`)") if abi_comm else "replicated solve, Gaussians/samples sharded by index; exchange variant ARAP_GATHER=" + gmode) if world > 1 else "single GPU"},
         "stages_ms": {"solve": round(float(mean[0]), 4), "sample_advect": round(float(mean[1]), 4), "endpoint_lbs": round(float(mean[2]), 4),
                       "six_point_fit": round(float(mean[3]), 4), "sample_sh_rotate": round(float(mean[4]), 4),
                       "note": "lbs_mode = 3: end-point skinning is fused into six_point_fit (k_apply_union); endpoint_lbs is then the node / mesh-point pass only" if lbs_mode == 3 else ""},

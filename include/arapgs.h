@@ -315,8 +315,13 @@ int arap_comm_grid_build(arap_ctx* ctx, int x_lo, int x_hi);
 /* mode 0 (default): arap_comm_exchange is an in-place NCCL all-gather.  mode 1: the exchange is FUSED into the apply kernel —
  * every tile's final pos / rot / scale is stored straight into the other ranks' gathered arrays over NVLink (peer mappings via
  * cudaIpc: one process per GPU, one node, <= 8 ranks), ordered by per-rank epoch flags instead of a collective; arap_comm_exchange
- * then only waits for the ranks' "done" flags.  Collective (call on every rank after arap_comm_init); needs lbs_mode = 3.
- * Like the all-gather it requires every rank to run the same sequence of arap_step / arap_apply calls. */
+ * then only waits for the ranks' "done" flags.  mode 2: the same with ONE store per value into an NVSwitch multicast mapping of the
+ * gathered pose arrays (multimem.st; CUDA driver VMM API, the multicast object's descriptor is handed from rank 0 to the other
+ * processes over a unix socket): the switch replicates the store into every rank's copy, so a rank's NVLink egress is 40 bytes
+ * per Gaussian whatever the number of ranks (mode 1: 40 bytes per peer).  ARAP_ERR_UNSUPPORTED (on every rank alike) if the
+ * platform has no multicast; the pose pointers of arap_device_view / arap_comm_view change (fetch them again).
+ * Collective (call on every rank after arap_comm_init, once, from mode 0); needs lbs_mode = 3.
+ * Like the all-gather the fused modes require every rank to run the same sequence of arap_step / arap_apply calls. */
 int arap_comm_set_mode(arap_ctx* ctx, int mode);
 int arap_comm_slab_get(arap_ctx* ctx, int* x_lo, int* x_hi);
 

@@ -57,7 +57,8 @@ int arapk_apply_union(long long N, const void* node_xf32, const uint16_t* gtile_
 /* the same pass with the fused multi-GPU epilogue: every tile's final pos / rot / scale is also stored into the peers' arrays
  * (pointers already offset to THIS rank's range; peers = NULL or n = 0: no epilogue) */
 #define ARAP_MAX_PEERS 7
-typedef struct ArapPeerPush { float* pos[ARAP_MAX_PEERS]; float* rot[ARAP_MAX_PEERS]; float* scale[ARAP_MAX_PEERS]; int n; } ArapPeerPush;
+typedef struct ArapPeerPush { float* pos[ARAP_MAX_PEERS]; float* rot[ARAP_MAX_PEERS]; float* scale[ARAP_MAX_PEERS]; int n;
+                               int multicast; /* 1: n = 1 and the pointers are an NVSwitch multicast mapping (multimem.st) */ } ArapPeerPush;
 int arapk_apply_union_push(long long N, const void* node_xf32, const uint16_t* gtile_cnt, const uint16_t* gtile_nodes, const int* uoff,
                       const int* woff, const uint32_t* usw, const uint16_t* unode, const float* uw, float* ends,
                       const float* scale_backup, const uint8_t* is_static, float* pos, float* rot, float* scale, float* shs,
