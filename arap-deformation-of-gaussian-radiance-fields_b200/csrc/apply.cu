@@ -1063,11 +1063,11 @@ __device__ __noinline__ void slerp_ratios_slow(float cf, float t, float& rA, flo
   rB = (float)(sin(td * ang) / sina);
 }
 
-template <int K>
+template <int K, bool PP>
 __global__ void __launch_bounds__(RS_TILE, 3)
 k_rotate_sample_shs(long long S, long long ntiles, int k, const float* __restrict__ w, const uint16_t* __restrict__ idx,
                     const float4* __restrict__ q_xyzw, const uint8_t* __restrict__ is_static,
-                    float* __restrict__ feature, int order) {
+                    float* __restrict__ feature, int order, ArapPosePush ps) {
   // stage = [SH rows: RS_STAGE4 float4][weights: 128 K float][node ids: 128 K u16], all blocked like the global tables
   // K = compile-time bound of the neighbour count k (register arrays); k sets the table layout
   const int STAGE16 = RS_STAGE4 + k * 32 + k * 16;   // 16-byte units
@@ -1111,6 +1111,30 @@ k_rotate_sample_shs(long long S, long long ntiles, int k, const float* __restric
       cp_async_wait<0>();
     }
     __syncthreads();
+    if (PP) {   // multi-GPU: this tile's share of the (final) pose arrays goes to the other ranks while the SH rows are in flight
+      const long long p4 = ps.n * 3 / 4, total4 = 2 * p4 + ps.n, c4 = (total4 + ntiles - 1) / ntiles;
+      const long long hi = min((tile + 1) * c4, total4);
+      for (long long i = tile * c4 + tid; i < hi; i += RS_TILE) {
+        if (i < p4) {
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(ps.pos) + i);
+#pragma unroll
+          for (int q = 0; q < ARAP_MAX_PEERS; q++)
+            if (q < ps.peers.n) { if (ps.peers.multicast) multimem_st(ps.peers.pos[q] + 4 * i, v); else reinterpret_cast<float4*>(ps.peers.pos[q])[i] = v; }
+        } else if (i < p4 + ps.n) {
+          const long long o = i - p4;
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(ps.rot) + o);
+#pragma unroll
+          for (int q = 0; q < ARAP_MAX_PEERS; q++)
+            if (q < ps.peers.n) { if (ps.peers.multicast) multimem_st(ps.peers.rot[q] + 4 * o, v); else reinterpret_cast<float4*>(ps.peers.rot[q])[o] = v; }
+        } else {
+          const long long o = i - p4 - ps.n;
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(ps.scale) + o);
+#pragma unroll
+          for (int q = 0; q < ARAP_MAX_PEERS; q++)
+            if (q < ps.peers.n) { if (ps.peers.multicast) multimem_st(ps.peers.scale[q] + 4 * o, v); else reinterpret_cast<float4*>(ps.peers.scale[q])[o] = v; }
+        }
+      }
+    }
     float4* st4 = s_tile + stage * STAGE16;
     // The quaternion gathers go out BEFORE the next tile's 32 KB of bulk loads (order = 1): memory responses come back
     // roughly in issue order per SM, so a gather queued behind the bulk loads waits for all of them (16 % of the stall
@@ -1653,7 +1677,14 @@ static EncodeTiledFn tensor_map_encoder() {
 
 extern "C" int arapk_rotate_sample_shs(long long S, int k, const float* w, const uint16_t* idx, const float* q_xyzw,
                                        const uint8_t* is_static, float* feature, cudaStream_t st) {
+  return arapk_rotate_sample_shs_push(S, k, w, idx, q_xyzw, is_static, feature, nullptr, st);
+}
+extern "C" int arapk_rotate_sample_shs_push(long long S, int k, const float* w, const uint16_t* idx, const float* q_xyzw,
+                                            const uint8_t* is_static, float* feature, const ArapPosePush* push, cudaStream_t st) {
   if (S <= 0) return ARAP_OK;
+  if (push && (push->peers.n <= 0 || push->peers.n > ARAP_MAX_PEERS || (push->n & 3) || (((uintptr_t)push->pos | (uintptr_t)push->rot | (uintptr_t)push->scale) & 15))) {
+    set_error("rotate_sample_shs: pose push needs 1..7 peers, a Gaussian count divisible by 4 and 16-byte aligned arrays"); return ARAP_ERR_INVALID;
+  }
   int rc = ensure_sh_tables(); if (rc) return rc;
   if (k < 1 || k > 12) { set_error("rotate_sample_shs: k out of range"); return ARAP_ERR_INVALID; }
   const long long ntiles = (S + RS_TILE - 1) / RS_TILE;
@@ -1661,9 +1692,12 @@ extern "C" int arapk_rotate_sample_shs(long long S, int k, const float* w, const
   if (!sms) {
     int dev = 0; ARAP_CUDA_TRY(cudaGetDevice(&dev)); ARAP_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int mx = (int)(2 * (sizeof(float4) * RS_STAGE4 + (size_t)RS_TILE * 12 * 6));
-    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_rotate_sample_shs<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_rotate_sample_shs<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_rotate_sample_shs<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_rotate_sample_shs<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_rotate_sample_shs<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_rotate_sample_shs<12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_rotate_sample_shs<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_rotate_sample_shs<10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    ARAP_CUDA_TRY(cudaFuncSetAttribute(k_rotate_sample_shs<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     const int mt = 2 * RT_STAGE + 1024;
     ARAP_CUDA_TRY(cudaFuncSetAttribute(k_rotate_sample_shs_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mt));
     ARAP_CUDA_TRY(cudaFuncSetAttribute(k_rotate_sample_shs_tma<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, mt));
@@ -1677,7 +1711,7 @@ extern "C" int arapk_rotate_sample_shs(long long S, int k, const float* w, const
   // selectable, default off.
   static int use_tma = -1;
   if (use_tma < 0) { const char* ev = getenv("ARAP_ROT_TMA"); use_tma = ev ? atoi(ev) : 0; }
-  EncodeTiledFn enc = use_tma ? tensor_map_encoder() : nullptr;
+  EncodeTiledFn enc = (use_tma && !push) ? tensor_map_encoder() : nullptr;
   if (enc && ((uintptr_t)feature & 15) == 0 && S < (1LL << 31)) {
     // one tensor map per (pointer, row count): cached for the session's aim-feature array
     static CUtensorMap tmap; static const float* m_ptr = nullptr; static long long m_S = 0;
@@ -1701,9 +1735,15 @@ extern "C" int arapk_rotate_sample_shs(long long S, int k, const float* w, const
   const size_t smem = 2 * (sizeof(float4) * RS_STAGE4 + (size_t)RS_TILE * k * 6);
   static int order = -1;   // ARAP_ROT_ORDER=0: bulk loads of the next tile issued before the gathers (first version)
   if (order < 0) { const char* ev = getenv("ARAP_ROT_ORDER"); order = ev ? atoi(ev) : 1; }
-  if (k <= 8) k_rotate_sample_shs<8><<<nb, RS_TILE, smem, st>>>(S, ntiles, k, w, idx, q4, is_static, feature, order);
-  else if (k <= 10) k_rotate_sample_shs<10><<<nb, RS_TILE, smem, st>>>(S, ntiles, k, w, idx, q4, is_static, feature, order);
-  else k_rotate_sample_shs<12><<<nb, RS_TILE, smem, st>>>(S, ntiles, k, w, idx, q4, is_static, feature, order);
+  ArapPosePush ps{};
+  if (push) {
+    ps = *push;
+    if (k <= 8) k_rotate_sample_shs<8, true><<<nb, RS_TILE, smem, st>>>(S, ntiles, k, w, idx, q4, is_static, feature, order, ps);
+    else if (k <= 10) k_rotate_sample_shs<10, true><<<nb, RS_TILE, smem, st>>>(S, ntiles, k, w, idx, q4, is_static, feature, order, ps);
+    else k_rotate_sample_shs<12, true><<<nb, RS_TILE, smem, st>>>(S, ntiles, k, w, idx, q4, is_static, feature, order, ps);
+  } else if (k <= 8) k_rotate_sample_shs<8, false><<<nb, RS_TILE, smem, st>>>(S, ntiles, k, w, idx, q4, is_static, feature, order, ps);
+  else if (k <= 10) k_rotate_sample_shs<10, false><<<nb, RS_TILE, smem, st>>>(S, ntiles, k, w, idx, q4, is_static, feature, order, ps);
+  else k_rotate_sample_shs<12, false><<<nb, RS_TILE, smem, st>>>(S, ntiles, k, w, idx, q4, is_static, feature, order, ps);
   ARAP_KERNEL_CHECK();
   return ARAP_OK;
 }

@@ -1073,28 +1073,34 @@ extern "C" int arap_apply(arap_ctx* ctx) {
   TRY(lbs_family(ctx, ctx->node_pos.p, ctx->node_next.p, ctx->node_rows, nullptr, 1));
   if (tm) cudaEventRecord(ctx->ev[2], st);
   if (ctx->ev_release) { ARAP_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_release, 0)); ctx->ev_release = nullptr; }
+  // Fused multi-GPU exchange (arap_comm_set_mode 1 / 2): the pose stores ride in the sample SH kernel when it runs this step — the
+  // longest kernel of the step, so the (world - 1) x 40 B per Gaussian every rank receives are spread under it — else in the
+  // epilogue of the fused apply kernel.  ARAP_PUSH_SITE=0 forces the epilogue (measurement aid).
+  arap_ctx::Comm& cm = ctx->comm;
+  static int site_pref = -1;
+  if (site_pref < 0) { const char* ev = getenv("ARAP_PUSH_SITE"); site_pref = ev ? atoi(ev) : 1; }
+  const bool want_push = cm.mode >= 1 && cm.nccl && cm.push.n > 0;
+  const bool sh_runs = ctx->S > 0 && ctx->aim_feature.p && !ctx->prm.lazy_sample_sh;
+  const bool push_in_sh = want_push && sh_runs && site_pref == 1 && (ctx->N & 3) == 0 &&
+                          ((((uintptr_t)ctx->pos.p | (uintptr_t)ctx->rot.p | (uintptr_t)ctx->scale.p) & 15) == 0);
+  const bool push_in_apply = want_push && !push_in_sh && fused;
+  cm.last_pushed = push_in_sh || push_in_apply;
   if (fused) {   // tolerance mode: end-point skinning + fit + SH rotation in one pass (end points of static Gaussians stay put)
     const RowTable& t = ctx->end_rows;
-    arap_ctx::Comm& cm = ctx->comm;
-    const bool push = cm.mode >= 1 && cm.nccl && cm.push.n > 0;
-    cm.last_pushed = push;
-    if (push) {   // ready handshake: every rank is past its consumers of the previous pose (see arap_comm_set_mode)
+    if (push_in_apply) {   // ready handshake: every rank is past its consumers of the previous pose (see arap_comm_set_mode)
       cm.epoch++;
       k_comm_flags<<<1, 32, 0, st>>>(flag_targets(ctx), cm.rank, cm.epoch, cm.flags.p, 0, cm.world);
       ARAP_KERNEL_CHECK();
     }
     TRY(arapk_apply_union_push(ctx->N, ctx->node_xf32.p, t.gtile_cnt.p, t.gtile_nodes.p, t.uoff.p, t.woff.p, t.usw.p, t.unode.p, t.uw.p,
                                ctx->ends.p, ctx->scale_backup.p, ctx->gs_static.p, ctx->pos.p, ctx->rot.p, ctx->scale.p, ctx->shs.p,
-                               push ? &cm.push : nullptr, st));
-    if (push) {
-      FlagPeers f = flag_targets(ctx);
-      k_comm_flags<<<1, 32, 0, st>>>(f, cm.world + cm.rank, cm.epoch, cm.flags.p, 0, 0);
+                               push_in_apply ? &cm.push : nullptr, st));
+    if (push_in_apply) {
+      k_comm_flags<<<1, 32, 0, st>>>(flag_targets(ctx), cm.world + cm.rank, cm.epoch, cm.flags.p, 0, 0);
       ARAP_KERNEL_CHECK();
     }
-  } else {
-    ctx->comm.last_pushed = false;
+  } else
     TRY(arapk_fit_gaussians(ctx->N, ctx->ends.p, ctx->scale_backup.p, ctx->gs_static.p, ctx->pos.p, ctx->rot.p, ctx->scale.p, ctx->shs.p, st));
-  }
   ARAP_CUDA_TRY(cudaEventRecord(ctx->ev_soa, st));
   if (tm) cudaEventRecord(ctx->ev[3], st);
   if (ctx->S > 0) TRY(lbs_family(ctx, ctx->sample_pos.p, ctx->sample_pos.p, ctx->sample_rows, ctx->sample_static.p, 1));
@@ -1107,7 +1113,19 @@ extern "C" int arap_apply(arap_ctx* ctx) {
       ctx->sample_sh_pending = true;
     } else {
       TRY(materialize_sample_sh(ctx));   // a switch from lazy to eager in mid-stroke
-      TRY(arapk_rotate_sample_shs(ctx->S, k, ctx->sample_rows.wf.p, ctx->sample_rows.idx.p, ctx->node_q.p, ctx->sample_static.p, ctx->aim_feature.p, st));
+      ArapPosePush pp;
+      if (push_in_sh) {   // ready handshake, then the kernel that carries the exchange, then this rank's done flag
+        cm.epoch++;
+        k_comm_flags<<<1, 32, 0, st>>>(flag_targets(ctx), cm.rank, cm.epoch, cm.flags.p, 0, cm.world);
+        ARAP_KERNEL_CHECK();
+        pp.peers = cm.push; pp.pos = ctx->pos.p; pp.rot = ctx->rot.p; pp.scale = ctx->scale.p; pp.n = ctx->N;
+      }
+      TRY(arapk_rotate_sample_shs_push(ctx->S, k, ctx->sample_rows.wf.p, ctx->sample_rows.idx.p, ctx->node_q.p, ctx->sample_static.p, ctx->aim_feature.p,
+                                       push_in_sh ? &pp : nullptr, st));
+      if (push_in_sh) {
+        k_comm_flags<<<1, 32, 0, st>>>(flag_targets(ctx), cm.world + cm.rank, cm.epoch, cm.flags.p, 0, 0);
+        ARAP_KERNEL_CHECK();
+      }
     }
   }
   if (tm) cudaEventRecord(ctx->ev[5], st);

@@ -128,10 +128,14 @@ def setup_session(pkg, scenes, workload, n, rank, world, stream):
                                                                  **{k2: st_graph[k2] for k2 in ("fps", "node_graph", "knn_ends", "knn_samples", "tile_tables")}})
 
 
-def set_exchange_mode(s):
-    """ARAP_COMM_PUSH = 2 (default): the exchange fused into the apply kernel with NVSwitch multicast stores, falling back to unicast
-    peer stores (1) where the platform has no multicast; 1: peer stores; 0: NCCL all-gather.  Returns the mode in effect."""
-    want = int(os.environ.get("ARAP_COMM_PUSH", "2"))
+def set_exchange_mode(s, default):
+    """ARAP_COMM_PUSH = 2: the exchange fused into the apply kernel with NVSwitch multicast stores, falling back to unicast peer
+    stores (1) where the platform has no multicast; 1: peer stores; 0: NCCL all-gather on the side stream.  Returns the mode in
+    effect.  Defaults (measured, profiles/multi_gpu_r02.txt): every rank RECEIVES 40 B x (world - 1) x N per step whatever the
+    transport (1.68 GB = 1.9 ms of NVLink ingress at 8 x 6M), so the fused epilogue stretches the 1.3 ms apply kernel to 2.5-2.7 ms
+    at 8 GPUs, while the all-gather hides behind the 7 ms of sample passes of the weak-scaling workload (12.15 against 12.6-12.9
+    ms); on the sharded 50M scene the sample passes are short and the fused exchange wins (6.92 against 7.07 ms)."""
+    want = int(os.environ.get("ARAP_COMM_PUSH", str(default)))
     for mode in ([2, 1] if want == 2 else [want]):
         if mode == 0:
             return 0
@@ -158,7 +162,7 @@ def setup_session_sharded(pkg, scenes, workload, n_total, rank, world, stream, d
     t0 = time.perf_counter()
     s.set_gaussians(sc["pos"], sc["rot"], sc["scale"], sc["opacity"], sc["shs"])
     s.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
-    xmode = set_exchange_mode(s) if world > 1 else 0
+    xmode = set_exchange_mode(s, 2) if world > 1 else 0
     gi = s.comm_grid_build()
     s.grid_eval(0)
     s.sync(); t_grid = time.perf_counter() - t0
@@ -242,7 +246,7 @@ def run_own(args):
             idt.copy_(torch.frombuffer(bytearray(pkg.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
         s.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
-        setup["xmode"] = set_exchange_mode(s)
+        setup["xmode"] = set_exchange_mode(s, 0)
         abi_comm = True
     elif world > 1:   # first-round variants through torch.distributed (parallel.py): whole-SoA NCCL gather, peer stores, pose + eager SH replay
         par = importlib.import_module(ge.PKG + ".parallel")
