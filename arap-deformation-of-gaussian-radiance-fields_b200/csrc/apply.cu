@@ -1094,15 +1094,44 @@ k_rotate_sample_shs(long long S, long long ntiles, int k, const float* __restric
     for (int c = tid; c < nblk * k * 8; c += RS_TILE) cp_async16(d + RS_STAGE4 + c, gw + c);
     for (int c = tid; c < nblk * k * 4; c += RS_TILE) cp_async16(d + RS_STAGE4 + k * 32 + c, gi + c);
   };
-  long long tile = blockIdx.x;
+  // multi-GPU (PP): the first ps.copy_ctas CTAs of the launch do nothing but the exchange — they stream this rank's final pose arrays
+  // into the other ranks' copies (unicast peer stores or one multicast store) while the remaining CTAs rotate the SH rows; the
+  // transfer is spread under the longest kernel of the step without stalling its tile pipeline on NVLink back-pressure
+  const int ncopy = PP ? ps.copy_ctas : 0;
+  if (PP && (int)blockIdx.x < ncopy) {
+    const long long p4 = ps.n * 3 / 4, total4 = 2 * p4 + ps.n;
+    for (long long i = (long long)blockIdx.x * RS_TILE + tid; i < total4; i += (long long)ncopy * RS_TILE) {
+      if (i < p4) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(ps.pos) + i);
+#pragma unroll
+        for (int q = 0; q < ARAP_MAX_PEERS; q++)
+          if (q < ps.peers.n) { if (ps.peers.multicast) multimem_st(ps.peers.pos[q] + 4 * i, v); else reinterpret_cast<float4*>(ps.peers.pos[q])[i] = v; }
+      } else if (i < p4 + ps.n) {
+        const long long o = i - p4;
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(ps.rot) + o);
+#pragma unroll
+        for (int q = 0; q < ARAP_MAX_PEERS; q++)
+          if (q < ps.peers.n) { if (ps.peers.multicast) multimem_st(ps.peers.rot[q] + 4 * o, v); else reinterpret_cast<float4*>(ps.peers.rot[q])[o] = v; }
+      } else {
+        const long long o = i - p4 - ps.n;
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(ps.scale) + o);
+#pragma unroll
+        for (int q = 0; q < ARAP_MAX_PEERS; q++)
+          if (q < ps.peers.n) { if (ps.peers.multicast) multimem_st(ps.peers.scale[q] + 4 * o, v); else reinterpret_cast<float4*>(ps.peers.scale[q])[o] = v; }
+      }
+    }
+    return;
+  }
+  const long long tstride = (long long)gridDim.x - ncopy;
+  long long tile = (long long)blockIdx.x - ncopy;
   if (tile < ntiles) issue(tile, 0);
   cp_async_commit();
-  for (int it = 0; tile < ntiles; tile += gridDim.x, it++) {
+  for (int it = 0; tile < ntiles; tile += tstride, it++) {
     const int stage = it & 1;
     const long long s0 = tile * RS_TILE;
     const int rows = (int)min((long long)RS_TILE, S - s0);
     const bool stat = (is_static && tid < rows) ? is_static[s0 + tid] != 0 : false;
-    const long long next = tile + gridDim.x;
+    const long long next = tile + tstride;
     if (!order) {
       if (next < ntiles) issue(next, stage ^ 1);
       cp_async_commit();
@@ -1111,30 +1140,6 @@ k_rotate_sample_shs(long long S, long long ntiles, int k, const float* __restric
       cp_async_wait<0>();
     }
     __syncthreads();
-    if (PP) {   // multi-GPU: this tile's share of the (final) pose arrays goes to the other ranks while the SH rows are in flight
-      const long long p4 = ps.n * 3 / 4, total4 = 2 * p4 + ps.n, c4 = (total4 + ntiles - 1) / ntiles;
-      const long long hi = min((tile + 1) * c4, total4);
-      for (long long i = tile * c4 + tid; i < hi; i += RS_TILE) {
-        if (i < p4) {
-          const float4 v = __ldcg(reinterpret_cast<const float4*>(ps.pos) + i);
-#pragma unroll
-          for (int q = 0; q < ARAP_MAX_PEERS; q++)
-            if (q < ps.peers.n) { if (ps.peers.multicast) multimem_st(ps.peers.pos[q] + 4 * i, v); else reinterpret_cast<float4*>(ps.peers.pos[q])[i] = v; }
-        } else if (i < p4 + ps.n) {
-          const long long o = i - p4;
-          const float4 v = __ldcg(reinterpret_cast<const float4*>(ps.rot) + o);
-#pragma unroll
-          for (int q = 0; q < ARAP_MAX_PEERS; q++)
-            if (q < ps.peers.n) { if (ps.peers.multicast) multimem_st(ps.peers.rot[q] + 4 * o, v); else reinterpret_cast<float4*>(ps.peers.rot[q])[o] = v; }
-        } else {
-          const long long o = i - p4 - ps.n;
-          const float4 v = __ldcg(reinterpret_cast<const float4*>(ps.scale) + o);
-#pragma unroll
-          for (int q = 0; q < ARAP_MAX_PEERS; q++)
-            if (q < ps.peers.n) { if (ps.peers.multicast) multimem_st(ps.peers.scale[q] + 4 * o, v); else reinterpret_cast<float4*>(ps.peers.scale[q])[o] = v; }
-        }
-      }
-    }
     float4* st4 = s_tile + stage * STAGE16;
     // The quaternion gathers go out BEFORE the next tile's 32 KB of bulk loads (order = 1): memory responses come back
     // roughly in issue order per SM, so a gather queued behind the bulk loads waits for all of them (16 % of the stall
@@ -1738,6 +1743,9 @@ extern "C" int arapk_rotate_sample_shs_push(long long S, int k, const float* w, 
   ArapPosePush ps{};
   if (push) {
     ps = *push;
+    static int copy_ctas = -1;   // ARAP_PUSH_CTAS: CTAs of the launch that carry the exchange (default 16)
+    if (copy_ctas < 0) { const char* ev = getenv("ARAP_PUSH_CTAS"); copy_ctas = ev ? atoi(ev) : 16; }
+    ps.copy_ctas = std::max(1, std::min(copy_ctas, (int)nb - 1));
     if (k <= 8) k_rotate_sample_shs<8, true><<<nb, RS_TILE, smem, st>>>(S, ntiles, k, w, idx, q4, is_static, feature, order, ps);
     else if (k <= 10) k_rotate_sample_shs<10, true><<<nb, RS_TILE, smem, st>>>(S, ntiles, k, w, idx, q4, is_static, feature, order, ps);
     else k_rotate_sample_shs<12, true><<<nb, RS_TILE, smem, st>>>(S, ntiles, k, w, idx, q4, is_static, feature, order, ps);

@@ -1073,12 +1073,11 @@ extern "C" int arap_apply(arap_ctx* ctx) {
   TRY(lbs_family(ctx, ctx->node_pos.p, ctx->node_next.p, ctx->node_rows, nullptr, 1));
   if (tm) cudaEventRecord(ctx->ev[2], st);
   if (ctx->ev_release) { ARAP_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_release, 0)); ctx->ev_release = nullptr; }
-  // Fused multi-GPU exchange (arap_comm_set_mode 1 / 2): the pose stores ride in the sample SH kernel when it runs this step — the
-  // longest kernel of the step, so the (world - 1) x 40 B per Gaussian every rank receives are spread under it — else in the
-  // epilogue of the fused apply kernel.  ARAP_PUSH_SITE=0 forces the epilogue (measurement aid).
+  // Fused multi-GPU exchange (arap_comm_set_mode 1 / 2): the pose stores ride in the epilogue of the fused apply kernel, or
+  // (ARAP_PUSH_SITE=1) in a few dedicated CTAs of the sample SH kernel — the longest kernel of the step — when it runs this step.
   arap_ctx::Comm& cm = ctx->comm;
   static int site_pref = -1;
-  if (site_pref < 0) { const char* ev = getenv("ARAP_PUSH_SITE"); site_pref = ev ? atoi(ev) : 1; }
+  if (site_pref < 0) { const char* ev = getenv("ARAP_PUSH_SITE"); site_pref = ev ? atoi(ev) : 0; }
   const bool want_push = cm.mode >= 1 && cm.nccl && cm.push.n > 0;
   const bool sh_runs = ctx->S > 0 && ctx->aim_feature.p && !ctx->prm.lazy_sample_sh;
   const bool push_in_sh = want_push && sh_runs && site_pref == 1 && (ctx->N & 3) == 0 &&

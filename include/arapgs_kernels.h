@@ -69,9 +69,10 @@ int arapk_replay_shs(long long N, const float* rot_old, const float* rot_new, co
 int arapk_node_quats(int M, const double* rot, float* q_xyzw, cudaStream_t st);
 int arapk_rotate_sample_shs(long long S, int k, const float* w, const uint16_t* idx, const float* q_xyzw,
                             const uint8_t* is_static, float* feature, cudaStream_t st);
-/* the same pass carrying the multi-GPU exchange: every tile iteration also stores its share of this rank's (final) pose arrays
- * pos / rot / scale [n] into the peers' copies, so the transfer is spread under the longest kernel of the step */
-typedef struct ArapPosePush { ArapPeerPush peers; const float* pos; const float* rot; const float* scale; long long n; } ArapPosePush;
+/* the same pass carrying the multi-GPU exchange: a few CTAs of the launch stream this rank's (final) pose arrays pos / rot / scale [n]
+ * into the peers' copies while the others rotate the SH rows, so the transfer is spread under the longest kernel of the step */
+typedef struct ArapPosePush { ArapPeerPush peers; const float* pos; const float* rot; const float* scale; long long n;
+                               int copy_ctas; /* set by the launcher */ } ArapPosePush;
 int arapk_rotate_sample_shs_push(long long S, int k, const float* w, const uint16_t* idx, const float* q_xyzw,
                             const uint8_t* is_static, float* feature, const ArapPosePush* push, cudaStream_t st);
 /* deferred sample SH rotation (arap_params.lazy_sample_sh): compose the step's blended sample quaternion onto an accumulator;
