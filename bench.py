@@ -17,6 +17,8 @@ Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
+import os as _os
+_os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")   # kernels loaded at context creation: the set-up stage timers must not contain lazy module loads
 import argparse
 import importlib
 import json
