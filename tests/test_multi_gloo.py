@@ -91,3 +91,23 @@ def test_gather_world2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == {0: True, 1: True}
+
+
+def test_sharded_scene_generator_tiles_one_scene(scenes):
+    """scenes.make_scene_shard (BASELINE configs[4], bench.py --workload shells50m): the parts of world = 1, 2, 4, 8 are contiguous ranges
+    of the SAME scene in global cell order — positions from per-chunk streams, attributes from per-block streams — so the scene does
+    not depend on the number of ranks, and every part is an x-slab up to cell granularity."""
+    n_total = 64 * 500
+    whole = scenes.make_scene_shard("shells50m", n_total, 0, 1)
+    assert whole["pos"].shape == (n_total, 3) and whole["shs"].shape == (n_total, 48)
+    G = 128
+    cell = np.clip(np.floor((whole["pos"] + np.float32(0.8)) * np.float32(G / 1.6)), 0, G - 1).astype(np.int64)
+    key = (cell[:, 0] * G + cell[:, 1]) * G + cell[:, 2]
+    assert np.all(np.diff(key) >= 0)                                   # global cell order
+    for world in (2, 4, 8):
+        n = n_total // world
+        for rank in (0, world - 1, world // 2):
+            part = scenes.make_scene_shard("shells50m", n_total, rank, world)
+            for kk in ("pos", "rot", "scale", "opacity", "shs"):
+                assert np.array_equal(part[kk], whole[kk][rank * n:(rank + 1) * n]), (world, rank, kk)
+    assert np.allclose(np.linalg.norm(whole["rot"], axis=1), 1.0, atol=1e-5) and (whole["opacity"] > 0).all() and (whole["scale"] > 0).all()
