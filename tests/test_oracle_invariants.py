@@ -170,6 +170,130 @@ def test_jacobian_matches_finite_differences_of_the_residual(orc, scenes, on_cen
         assert np.allclose((fp - fm) / (2 * eps), J[:, u], atol=2e-7), (u, np.abs((fp - fm) / (2 * eps) - J[:, u]).max())
 
 
+@pytest.mark.parametrize("on_center", [False, True])
+def test_explicit_normal_equation_stencil_equals_JtJ(orc, scenes, on_center):
+    """csrc/solve_pipe.cu applies H = J^T J as an explicit stencil (header of that file): per node i and component j the 4-vector
+    y_ij = (A_j0, A_j1, A_j2, t_j) sees  w_reg^2 [C_i y_ij - sum_s c_is t_{q(s) j}] from its own E_reg rows, the mirror terms of
+    its in-edges, w_reg^2 (static in-edges) on t, the node-local E_rot block, and sum_g r_g r_g^T from the constraint rows with
+    r_g = w_con wei (v_c - g_q, 1) on y_qj.  Built here entry by entry from those formulas (numpy) and compared with J^T J of the
+    oracle's Jacobian (Deform.cpp:180-376) at a generic x, per-node and centre constraints, with an excluded block."""
+    o = _session(scenes, n=3000, nodes=60, k=6)
+    rng = np.random.default_rng(5)
+    z = o.node_pos[:, 2]
+    blocks = [np.nonzero(z > 0.25)[0].astype(np.uint32), np.nonzero(z < -0.25)[0].astype(np.uint32),
+              np.nonzero(np.abs(z) < 0.05)[0].astype(np.uint32)[:3], np.nonzero(o.node_pos[:, 0] > 0.4)[0].astype(np.uint32)[:4]]
+    types = [1, 0, 0, -1]
+    o.set_blocks(blocks, types)
+    o.aim_translate([0.01, 0.0, 0.03])
+    M, k = o.M, o.nbr.shape[1]
+    rot = np.tile(np.eye(3).reshape(-1), (M, 1)) + rng.normal(size=(M, 9)) * 0.05      # column-major A (Deform.hpp:29-36)
+    trans = rng.normal(size=(M, 3)) * 0.02
+    R, Cc, V, f0, (m, n) = orc.jacobian(o.node_pos, o.nbr, o.anc_idx, o.anc_w, o.node_static, o.blocks, o.block_types, o.aim, on_center, rot, trans)
+    J = np.zeros((m, n)); np.add.at(J, (R, Cc), V)
+    want = J.T @ J
+    free = o.node_static == 0
+    rank = np.cumsum(free) - 1
+    assert n == 12 * free.sum()
+    w_rot2, w_reg2, w_con = 1.0, 10.0, 10.0
+    g = o.node_pos.astype(np.float32)
+
+    def y_idx(i, j):      # unknown indices of (A_j0, A_j1, A_j2, t_j): x[j + 3c] = A[j, c], x[9 + j] = t_j
+        b = 12 * rank[i]
+        return np.array([b + j, b + j + 3, b + j + 6, b + 9 + j])
+    H = np.zeros((n, n))
+    for i in range(M):
+        for s in range(k):
+            q = int(o.nbr[i, s])
+            c = np.append((g[q] - g[i]).astype(np.float64), 1.0)          # float position differences (Deform.cpp:254-256)
+            for j in range(3):
+                if free[i]:
+                    yi = y_idx(i, j)
+                    H[np.ix_(yi, yi)] += w_reg2 * np.outer(c, c)            # C_i
+                    if free[q]:
+                        tq = y_idx(q, j)[3]
+                        H[yi, tq] -= w_reg2 * c; H[tq, yi] -= w_reg2 * c     # own rows <-> the neighbour's t, and its mirror (in-edge partial)
+                        H[tq, tq] += w_reg2                                  # in-degree term
+                elif free[q]:
+                    tq = y_idx(q, j)[3]
+                    H[tq, tq] += w_reg2                                      # static in-edge
+    for i in np.nonzero(free)[0]:
+        A = rot[i].reshape(3, 3).T                                           # A[j, c]
+        Jr = np.zeros((6, 9))                                                # columns: x[j + 3c]
+        for r, (a, b) in enumerate(((0, 1), (0, 2), (1, 2))):
+            for j in range(3):
+                Jr[r, j + 3 * a] = A[j, b]; Jr[r, j + 3 * b] = A[j, a]
+        for c in range(3):
+            for j in range(3):
+                Jr[3 + c, j + 3 * c] = 2.0 * A[j, c]
+        b0 = 12 * rank[i]
+        H[b0:b0 + 9, b0:b0 + 9] += w_rot2 * Jr.T @ Jr
+    groups = []
+    for blk, t in zip(blocks, types):
+        if t == -1:
+            continue
+        groups += [sorted(set(int(v) for v in blk[:20]))] if on_center else [[int(v)] for v in blk]
+    for members in groups:
+        for j in range(3):
+            r = np.zeros(n)
+            for c_node in members:
+                for s in range(k):
+                    q = int(o.anc_idx[c_node, s])
+                    if free[q]:
+                        r[y_idx(q, j)] += w_con * o.anc_w[c_node, s] * np.append((g[c_node] - g[q]).astype(np.float64), 1.0)
+            H += np.outer(r, r)
+    scale = np.abs(want).max()
+    assert np.abs(H - want).max() <= 1e-9 * scale, np.abs(H - want).max() / scale
+
+
+def test_pipelined_pcg_recurrences_solve_the_gauss_newton_system(orc, scenes):
+    """The recurrences of csrc/solve_pipe.cu (pipelined PCG, Ghysels & Vanroose 2014, with the diagonal preconditioner folded in:
+    u = D^-1 r, q = D^-1 s, m = D^-1 w; dots taken before the product of the same iteration; warm start x0 = alpha h' with the
+    exact line-search alpha) restated in numpy on the oracle's first Gauss-Newton system: same solution as a direct solve, the
+    same iteration count as classical Jacobi-PCG (+-2), and the warm start from a nearby solution needs fewer products."""
+    o = _session(scenes, n=4000, nodes=150, k=8)
+    blocks, types = scenes.cap_blocks(o.node_pos, lo=-0.3, hi=0.3)
+    o.set_blocks(blocks, types)
+    o.aim_translate([0.0, 0.0, 0.02])
+    I = np.tile(np.eye(3).reshape(-1), (o.M, 1)); Z = np.zeros((o.M, 3))
+    R, Cc, V, f, (m, n) = orc.jacobian(o.node_pos, o.nbr, o.anc_idx, o.anc_w, o.node_static, o.blocks, o.block_types, o.aim, False, I, Z)
+    J = np.zeros((m, n)); np.add.at(J, (R, Cc), V)
+    H = J.T @ J; g = -(J.T @ f); di = 1.0 / np.diag(H)
+    exact = np.linalg.solve(H, g)
+
+    def classical(tol):
+        x = np.zeros(n); r = g.copy(); z = r * di; p = z.copy(); rz = r @ z
+        for it in range(1, 5000):
+            q = H @ p; a = rz / (p @ q); x += a * p; r -= a * q
+            if r @ r <= tol * tol * (g @ g): return it, x
+            z = r * di; rzn = r @ z; p = z + (rzn / rz) * p; rz = rzn
+
+    def pipelined(tol, warm=None):
+        x = np.zeros(n); r = g.copy(); products = 0
+        if warm is not None:                                   # x0 = alpha h', alpha = g.h' / h'.H h'
+            q = H @ warm; products += 1
+            a = (g @ warm) / (warm @ q) if warm @ q > 0 else 0.0
+            x = a * warm; r = g - a * q
+        w = H @ (r * di); products += 1
+        z = np.zeros(n); s = np.zeros(n); p = np.zeros(n)
+        gam_old = alpha_old = 1.0
+        for it in range(5000):
+            u = r * di
+            gam, dlt, rr = r @ u, w @ u, r @ r                 # one reduction, before this iteration's product
+            if rr <= tol * tol * (g @ g): return products, x
+            nn = H @ (w * di); products += 1
+            beta = gam / gam_old if it else 0.0
+            alpha = gam / (dlt - beta * gam / alpha_old) if it else gam / dlt
+            z = nn + beta * z; s = w + beta * s; p = u + beta * p
+            x = x + alpha * p; r = r - alpha * s; w = w - alpha * z
+            gam_old, alpha_old = gam, alpha
+    it_c, x_c = classical(1e-8)
+    it_p, x_p = pipelined(1e-8)
+    assert abs(it_p - 1 - it_c) <= 2, (it_p, it_c)
+    assert np.abs(x_p - exact).max() <= 1e-6 * np.abs(exact).max() and np.abs(x_p - x_c).max() <= 1e-6 * np.abs(exact).max()
+    it_w, x_w = pipelined(1e-8, warm=exact * 1.02 + 1e-4 * np.abs(exact).max() * np.sin(np.arange(n)))
+    assert it_w < 0.8 * it_p and np.abs(x_w - exact).max() <= 1e-6 * np.abs(exact).max(), (it_w, it_p)
+
+
 def test_six_point_fit_recovers_a_rigid_motion_and_axis_stretch(orc, scenes):
     """End points moved by x -> Q x + t: the fit returns rot = Q rot, same scales, pos = Q pos + t; stretched along the
     Gaussian's own axes by (a, b, c): scale_i' = ((s_i + 1e-3) a_i - 1e-3 ... ) as GaussianView.cpp:3124-3132 defines it."""
