@@ -294,3 +294,25 @@ def test_selectable_kernel_variants_keep_parity():
         r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_kernels.py"), os.path.join(here, "test_gpu_session.py"),
                             "-m", "gpu", "-x", "-q", "-k", sel], env={**os.environ, **env}, capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, (env, r.stdout[-2000:] + r.stderr[-2000:])
+
+
+def test_one_barrier_solver_eligibility_check(pkg):
+    """arapk_solve_pipe_eligible (host side, csrc/solve_pipe.cu): the one-barrier kernel is selected only when every CTA's slice of
+    constraint entries fits its shared-memory table, there are at most 8 multi-member groups and none has more than 20 members;
+    the session asks it at the first solve after arap_set_blocks and otherwise runs the two-barrier kernel."""
+    lib = pkg.lib()
+    M, k = 3000, 10
+
+    def ask(grp_sizes, per_node, max_ctas=0):
+        grp_off = np.concatenate([[0], np.cumsum(grp_sizes)]).astype(np.int32)
+        cin_off = np.concatenate([[0], np.cumsum(per_node)]).astype(np.int32)
+        return lib.arapk_solve_pipe_eligible(M, k, len(grp_sizes), grp_off.ctypes.data_as(C.c_void_p), cin_off.ctypes.data_as(C.c_void_p), max_ctas)
+    ones = np.ones(500, np.int64)
+    assert ask(ones, np.full(M, 2)) == 1                      # 125 CTAs x 24 nodes x 2 entries
+    assert ask(ones, np.full(M, 50)) == 0                     # 1200 entries per CTA > 1024
+    assert ask(ones, np.full(M, 6), max_ctas=24) == 0         # 125 nodes per CTA (the NL = 136 slice: 672 entries) x 6 = 750
+    assert ask(ones, np.full(M, 5), max_ctas=24) == 1
+    assert ask(ones, np.full(M, 2), max_ctas=18) == 0         # 167 nodes per CTA: no slice of this kernel
+    assert ask(np.array([20, 20, 20, 1, 1]), np.full(M, 2)) == 1
+    assert ask(np.array([21, 1]), np.full(M, 2)) == 0         # more members than a centre-constraint group can have (DC:4)
+    assert ask(np.full(9, 2), np.full(M, 2)) == 0             # nine multi-member groups
