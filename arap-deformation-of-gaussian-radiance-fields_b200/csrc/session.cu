@@ -1428,6 +1428,25 @@ extern "C" int arap_comm_materialize_sh(arap_ctx* ctx) {
   return ARAP_OK;
 }
 
+// Balanced x-slab cuts of a G-layer grid for `world` ranks from the number of Gaussians per x-layer (host only, deterministic):
+// rank r starts at the first layer where the running count reaches r / world of the total; every rank gets at least one layer.
+// cuts_out[world + 1], cuts_out[0] = 0, cuts_out[world] = G.
+extern "C" int arapk_slab_cuts(const int* layer_count, int G, int world, int* cuts_out) {
+  if (!layer_count || !cuts_out || G < 1 || world < 1 || world > G) { set_error("slab_cuts: need 1 <= world <= G"); return ARAP_ERR_INVALID; }
+  long long total = 0;
+  for (int x = 0; x < G; x++) total += layer_count[x];
+  for (int q = 0; q <= world; q++) cuts_out[q] = G;
+  cuts_out[0] = 0;
+  long long run = 0; int r = 1;
+  for (int x = 0; x < G && r < world; x++) {
+    run += layer_count[x];
+    while (r < world && run * world >= (long long)r * total) { cuts_out[r] = x + 1; r++; }
+  }
+  for (int q = 1; q <= world; q++) cuts_out[q] = std::min(std::max(cuts_out[q], cuts_out[q - 1] + 1), G - (world - q));   // at least one layer each
+  cuts_out[world] = G;
+  return ARAP_OK;
+}
+
 // One scene sharded over the ranks (BASELINE configs[4]): rank r holds the Gaussians [r N, (r + 1) N) of a
 // scene that is already in cell order (what a single-GPU arap_grid_build leaves behind: contiguous index ranges are x-slabs
 // up to boundary effects).  The grid stages then work on ONE grid over all ranks' Gaussians — every rank sees them in the
@@ -1463,14 +1482,7 @@ extern "C" int arap_comm_grid_build(arap_ctx* ctx, int x_lo, int x_hi) {
       TRY(download(h.data(), hist.p, h.size(), st));
       ARAP_CUDA_TRY(cudaStreamSynchronize(st));
       std::vector<int> cut((size_t)cm.world + 1, ctx->G);
-      cut[0] = 0;
-      long long run = 0; int r = 1;
-      for (int x = 0; x < ctx->G && r < cm.world; x++) {
-        run += h[(size_t)x];
-        while (r < cm.world && run * cm.world >= (long long)r * n_all) { cut[(size_t)r] = x + 1; r++; }
-      }
-      for (int q = 1; q <= cm.world; q++) cut[(size_t)q] = std::min(std::max(cut[(size_t)q], cut[(size_t)q - 1] + 1), ctx->G - (cm.world - q));   // at least one layer each
-      cut[(size_t)cm.world] = ctx->G;
+      TRY(arapk_slab_cuts(h.data(), ctx->G, cm.world, cut.data()));
       x_lo = cut[(size_t)cm.rank]; x_hi = cut[(size_t)cm.rank + 1];
     }
   }

@@ -177,6 +177,8 @@ int arapk_footprint_count_slab(long long N, const float* aabb, const float* min3
 int arapk_footprint_fill_slab(long long N, const float* aabb, const float* min3_host, float step, int G, int padding, int xlo, int xhi,
                               const int* prefix, int* lists_out, void* scratch, size_t scratch_bytes, cudaStream_t st);
 int arapk_xlayer_hist(const float* pos, long long N, const float* min3_host, float step, int G, int* hist_dev /* G */, cudaStream_t st);
+/* host only: balanced x-slab cuts [world + 1] from the per-layer counts (every rank at least one layer) */
+int arapk_slab_cuts(const int* layer_count_host, int G, int world, int* cuts_out);
 int arapk_valid_cells(const int* prefix, int G, int* valid_out, int* count_host, void* scratch, size_t scratch_bytes,
                       cudaStream_t st);
 int arapk_emit_samples(const int* valid, int V, const float* min3_host, float step, int G, float* out, cudaStream_t st);

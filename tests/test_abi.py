@@ -54,3 +54,34 @@ def test_product_never_imports_the_oracle():
     for f in list(pkgdir.glob("*.py")) + list((pkgdir / "csrc").glob("*")):
         if f.is_file():
             assert "oracle" not in f.read_text(errors="ignore").replace("the oracle", "").replace("as the oracle", ""), f
+
+
+def test_slab_cuts_host_logic(pkg):
+    """arapk_slab_cuts (host side of arap_comm_grid_build): x-slab cuts balanced by Gaussians per x-layer —
+    strictly increasing from 0 to G (every rank at least one layer), each slab within one layer's count of the ideal share,
+    deterministic, and robust to degenerate histograms.  No GPU involved."""
+    import ctypes as C
+    import numpy as np
+    lib = pkg.lib()
+
+    def cuts(h, world):
+        h = np.ascontiguousarray(h, np.int32)
+        out = np.zeros(world + 1, np.int32)
+        rc = lib.arapk_slab_cuts(h.ctypes.data_as(C.c_void_p), len(h), world, out.ctypes.data_as(C.c_void_p))
+        return rc, out
+    rng = np.random.default_rng(0)
+    for G, world in ((128, 8), (128, 2), (64, 4), (32, 3), (16, 16), (128, 1)):
+        h = rng.integers(0, 5000, size=G)
+        h[: G // 8] = 0; h[-G // 8:] = 0                       # empty margins, as in a scene inside the [-0.75, 0.75]^3 box
+        rc, c = cuts(h, world)
+        assert rc == 0 and c[0] == 0 and c[-1] == G and np.all(np.diff(c) >= 1), (G, world, c)
+        assert np.array_equal(c, cuts(h, world)[1])
+        if world < G // 4:
+            share = np.add.reduceat(h, c[:-1])
+            assert np.abs(share - h.sum() / world).max() <= 2 * h.max(), (share, h.sum() / world)
+    one = np.zeros(64, np.int32); one[10] = 1000                 # everything in one layer: still one layer per rank
+    rc, c = cuts(one, 8)
+    assert rc == 0 and c[0] == 0 and c[-1] == 64 and np.all(np.diff(c) >= 1)
+    rc, c = cuts(np.zeros(32, np.int32), 4)
+    assert rc == 0 and np.all(np.diff(c) >= 1) and c[-1] == 32
+    assert cuts(np.ones(4, np.int32), 5)[0] != 0                 # more ranks than layers
