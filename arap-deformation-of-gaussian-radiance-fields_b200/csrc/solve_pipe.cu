@@ -348,6 +348,8 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_solve_pipe(SolveDev S, unsign
   }
   {  // constraint partial slots that belong to excluded anchors are never written: zero both buffers once
     const int n_mem = S.n_groups > 0 ? S.grp_off[S.n_groups] : 0;
+    if (n_mem > (S.n_groups + 1) * 20) { if (tid == 0) s_cnt[2] = 1; }   // more members than the workspace holds partial blocks for: misfit (flag bit 2)
+    else
     for (size_t t = (size_t)b * SM_THREADS + tid; t < (size_t)n_mem * MS; t += (size_t)B * SM_THREADS) { PB.pi[0][t] = 0.0; PB.pi[1][t] = 0.0; }
     for (int g = tid; g < S.n_groups; g += SM_THREADS)   // multi-member groups of the solve (any order: sums are per group)
       if (S.grp_off[g + 1] - S.grp_off[g] > 1) { const int at = atomicAdd(&s_cnt[0], 1); if (at < PIPE_NBIG) s_big_g[at] = g; }
@@ -372,7 +374,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_solve_pipe(SolveDev S, unsign
   __syncthreads();
   const int nbig = s_cnt[0];
   L.nent = s_cnt[1];
-  const bool misfit = nbig > PIPE_NBIG || L.nent > ccap;
+  const bool misfit = nbig > PIPE_NBIG || L.nent > ccap || s_cnt[2] != 0;
   if (!misfit)
     for (int li = tid; li < nloc; li += SM_THREADS)   // same thread that wrote these ccoef rows above
       for (int t = L.cb[li]; t < L.ce[li]; t++) {
